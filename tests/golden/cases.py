@@ -1,0 +1,136 @@
+"""Input recipes for the golden vectors.  Every case is either handcrafted bytes or a deterministic
+tools/fqgen.c product (optionally mutated), so only the REFERENCE's outputs need to be committed."""
+import numpy as np
+
+from tools import fqgen
+
+KAT_A1 = (b"@A00250:26:H3YTWDSXX:1:1101:1000:1000 1:N:0:ACTG\nACGTACGTACGTACGTNCGT\n+\nFFFFFFFF:FFFFFFF#FFF\n"
+          b"@A00250:26:H3YTWDSXX:1:1101:1031:1000 1:N:0:ACTG\nGGGGCCCCAAAATTTTACGT\n+\nFF,FFFFFFFFFFFFFFFFF\n")
+KAT_A2 = (b"@A00250:26:H3YTWDSXX:1:1101:1000:1000 2:N:0:ACTG\nACGNACGTACGTACGTACGT\n+\nFFF#FFFFFFFFFFFFFFFF\n"
+          b"@A00250:26:H3YTWDSXX:1:1101:1031:1000 2:N:0:ACTG\nTTTTTTTTTTACGTAAAATT\n+\nFFFFFFFFFFFFFFFFFF::\n")
+
+# SURVEY.md section 8c KAT-names: name -> (has, name1, lane, tile, x, y, name2) as printed by the reference's FastqMeta::parse
+KAT_NAMES = [
+    (b"@A00251:28:H3YV7DSXX:40:1101:2356:1000 1:N:0:TAAGTGGC", (1, b"@A00251:28:H3YV7DSXX", 40, 1101, 2356, 1000, b" 1:N:0:TAAGTGGC")),
+    (b"@A00251:28:H3YV7DSXX:40:1101:2356:1000", (0, b"@A00251:28:H3YV7DSXX:40:1101:2356:1000", 0, 0, 0, 0, b"")),
+    (b"@A00251:28:H3YV7DSXX:4:1101:2356:1000:UMIACGT 1:N:0:TAAG", (1, b"@A00251:28:H3YV7DSXX", 4, 1101, 2356, 1000, b":UMIACGT 1:N:0:TAAG")),
+    (b"@V300035135L2C001R0010000001/1", (0, b"@V300035135L2C001R0010000001/1", 0, 0, 0, 0, b"")),
+    (b"@SRR123456.1 A00251:28:H3YV7DSXX:4:1101:2356:1000", (0, b"@SRR123456.1 A00251:28:H3YV7DSXX:4:1101:2356:1000", 0, 0, 0, 0, b"")),
+    (b"@HWI-ST1234:100:C1234ACXX:1:1101:1234:2000#ACGT/1", (0, b"@HWI-ST1234:100:C1234ACXX:1:1101:1234:2000#ACGT/1", 0, 0, 0, 0, b"")),
+    (b"@a:b:c:d:5 xxx", (1, b"@a:b:c:d", 5, 0, 0, 0, b" xxx")),
+    (b"@a:b:c:1:2 yy", (1, b"@a:b:c:1", 2, 0, 0, 0, b" yy")),
+    (b"@a:b:c:300:70000:2097151:4000000000 1:N:0:1", (1, b"@a:b:c", 44, 4464, 2097151, 4000000000, b" 1:N:0:1")),
+    (b"@a:b:c:004:01101:0002356:01000 1:N:0:1", (1, b"@a:b:c", 4, 1101, 2356, 1000, b" 1:N:0:1")),
+    (b"@a:b:c:1:2:3: 4", (1, b"@a:b:c", 1, 2, 3, 0, b" 4")),
+    (b"@a:b:c:1:2:3:-7 1", (1, b"@a:b:c", 1, 2, 3, 4294967289, b" 1")),
+    (b"@a:b 1:2:3:4:5:6:7", (0, b"@a:b 1:2:3:4:5:6:7", 0, 0, 0, 0, b"")),
+    (b"@a:b:c:1:2:x3:y4 q", (1, b"@a:b:c", 1, 2, 0, 0, b" q")),
+    (b"@a:b:c:1:2: 12:9 q", (1, b"@a:b:c", 1, 0, 0, 0, b" 12:9 q")),
+    (b"@NS500713:64:HFKJJBGXY:1:11101:20469:1097 1:N:0:TATAGCCT+GGTCCCGA", (1, b"@NS500713:64:HFKJJBGXY", 1, 11101, 20469, 1097, b" 1:N:0:TATAGCCT+GGTCCCGA")),
+]
+
+
+def records(buf):
+    lines = bytes(buf).split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    return [lines[i:i + 4] for i in range(0, len(lines) - 3, 4)]
+
+
+def join(recs):
+    return b"".join(b"\n".join(r) + b"\n" for r in recs)
+
+
+def _names_file():
+    # one record per KAT name; sequence/quality constant so only the name path varies
+    return [(b"name%02d" % i, n + b"\nACGTTGCAACGTTGCAACGT\n+\nFFFFFFFFFFFFFFFFFFFF\n") for i, (n, _) in enumerate(KAT_NAMES)]
+
+
+def build_cases():
+    """-> list of dict(name, r1, r2|None, k (chunk kilobases), interleaved)"""
+    cases = []
+
+    def add(name, r1, r2=None, k=1000, interleaved=False):
+        cases.append(dict(name=name, r1=bytes(r1), r2=None if r2 is None else bytes(r2), k=k, interleaved=interleaved))
+
+    add("kat_se", KAT_A1)
+    add("kat_pe", KAT_A1, KAT_A2)
+    for nm, data in _names_file():
+        add(nm.decode(), data)
+    # all KAT names in one file: mixed has/no-has => header without lane/tile/x/y
+    add("names_mixed", b"".join(d for _, d in _names_file()))
+
+    r1, _ = fqgen.generate(2100, seed=1)
+    add("nova_se_k100", r1, k=100)
+    r1, _ = fqgen.generate(7200, seed=12)
+    add("nova_se_k1000", r1)                       # >= 100 N in chunk 0: N-from-quality path, 2 chunks
+    r1, r2 = fqgen.generate(3600, seed=2, paired=True)
+    add("nova_pe_k1000", r1, r2)                   # 2 chunks, overlaps +/-, tile change absent
+    r1, r2 = fqgen.generate(1500, seed=3, paired=True)
+    add("nova_pe_k100_npos", r1, r2, k=100)        # < 100 N in chunk 0 => ENCODE_N_POS
+    r1, _ = fqgen.generate(3000, seed=5, shape=fqgen.BGI)
+    add("bgi_se_k100", r1, k=100)
+    r1, r2 = fqgen.generate(1500, seed=4, paired=True, flags=fqgen.VARLEN)
+    add("nova_pe_varlen_k100", r1, r2, k=100)
+    r1, r2 = fqgen.generate(900, seed=6, paired=True, flags=fqgen.LONG)
+    add("nova_pe_300bp_k100", r1, r2, k=100)
+    r1, r2 = fqgen.generate(900, seed=7, paired=True, flags=fqgen.CRLF)
+    add("nova_pe_crlf_k100", r1, r2, k=100)
+    r1, r2 = fqgen.generate(1500, seed=8, paired=True)
+    add("nova_pe_nonl_k100", bytes(r1)[:-1], bytes(r2)[:-1], k=100)
+    add("nova_pe_nonl_r2only_k100", bytes(r1), bytes(r2)[:-1], k=100)
+    r1, _ = fqgen.generate(1200, seed=9)
+    add("nova_se_nonl_k100", bytes(r1)[:-1], k=100)
+    r1, _ = fqgen.generate(1200, seed=10, shape=fqgen.BGI, flags=fqgen.VARLEN)
+    add("bgi_se_varlen_k100", r1, k=100)
+
+    # interleaved input
+    r1, r2 = fqgen.generate(900, seed=11, paired=True)
+    il = join([x for pair in zip(records(r1), records(r2)) for x in pair])
+    add("nova_interleaved_in_k100", il, k=100, interleaved=True)
+
+    # Q10: R2 with a different tile mid-chunk (chunk 1 of 3) and on the last pair of a chunk
+    r1, r2 = fqgen.generate(1200, seed=13, paired=True)
+    a, b = records(r1), records(r2)
+    b2 = [list(r) for r in b]
+    b2[500][0] = b2[500][0].replace(b":1101:", b":1102:")
+    add("pe_demoted_mid_k100", join(a), join(b2), k=100)
+    b3 = [list(r) for r in b]
+    b3[333][0] = b3[333][0].replace(b":1101:", b":1102:")      # k=100 => 334 pairs per chunk; index 333 = last pair of chunk 0
+    add("pe_demoted_lastpair_k100", join(a), join(b3), k=100)
+    b4 = [list(r) for r in b]
+    b4[700][0] = b4[700][0].replace(b" 2:N:0:", b" 2:Y:0:")     # name2 mismatch in a later chunk
+    add("pe_name2_mismatch_late_k100", join(a), join(b4), k=100)
+    b5 = [list(r) for r in b]
+    b5[0][0] = b5[0][0].replace(b" 2:N:0:", b" 2:Y:1:")         # two differing chars in pair 0 => no interleave support
+    add("pe_no_support_k100", join(a), join(b5), k=100)
+
+    # Q3: quality value unseen in chunk 0 (exception records), and a non-N base carrying the N quality later
+    r1, _ = fqgen.generate(7200 + 900, seed=14)
+    recs = [list(r) for r in records(r1)]
+    q = bytearray(recs[7000][3]); q[10] = ord('5'); q[11] = ord('5'); q[100] = ord('J'); recs[7000][3] = bytes(q)
+    q = bytearray(recs[7100][3]); s = recs[7100][1]
+    for i in range(len(q)):
+        if s[i:i + 1] != b"N":
+            q[i] = ord('#'); break
+    recs[7100][3] = bytes(q)
+    add("nova_se_late_quality", join(recs))
+
+    # tile changes inside a chunk (tileSame false) and lane column: stitch rows of two tiles
+    ra, _ = fqgen.generate(600, seed=15, first_row=1998)           # rows 1998..1999 of tile 1101, then tile 1102
+    add("nova_se_tile_change_k100", ra, k=100)
+
+    # read length > 255 mixed with short: 2-byte length column, variable
+    r1, r2 = fqgen.generate(600, seed=16, paired=True, flags=fqgen.LONG | fqgen.VARLEN)
+    add("nova_pe_300bp_varlen_k100", r1, r2, k=100)
+
+    # single read, single pair, empty-ish
+    add("one_read", join(records(KAT_A1)[:1]))
+    add("one_pair", join(records(KAT_A1)[:1]), join(records(KAT_A2)[:1]))
+    # strand line that repeats the name (old style) and differing strand lines
+    recs = [list(r) for r in records(fqgen.generate(600, seed=17)[0])]
+    for i, r in enumerate(recs):
+        if i % 2:
+            r[2] = b"+" + r[0][1:]
+    add("se_strand_varies_k100", join(recs), k=100)
+    return cases
