@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py - FASTQ <-> .rfq throughput of the B200 path on BASELINE.json's headline workload.
+
+One step = encode a paired-end NovaSeq-shape FASTQ batch to .rfq AND decode it back (the .rfq is checked
+bit-exact against the oracle on a sample, the decode byte-exact against the input).
+  value : FASTQ GB/s of the round trip with inputs resident in HBM (FASTQ bytes / (t_encode + t_decode)), all ranks
+  e2e   : the same through the C ABI with pinned HOST buffers (H2D + kernels + D2H inside the timed region)
+  roofline / cpu_baseline : see DESIGN.md section "Measurement"
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/repaq, else the C port) instead.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "FASTQ GB/s encode+decode (bit-exact .rfq)"
+UNIT = "GB/s"
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def shard_records(buf, n_shards):
+    """record-aligned shards of a '\\n'-terminated FASTQ image with 4-line records of equal count per shard"""
+    nl = np.flatnonzero(buf == 10)
+    n_rec = nl.size // 4
+    per = n_rec // n_shards
+    cuts = [0] + [int(nl[4 * per * (i + 1) - 1]) + 1 for i in range(n_shards)]
+    return [buf[cuts[i]:cuts[i + 1]] for i in range(n_shards)]
+
+
+def cpu_reference_roundtrip(r1, r2, cores, budget_s=None):
+    """Times the reference CPU implementation (compress + decompress) on `cores` disjoint record-aligned shards run
+    concurrently, files in /dev/shm.  Returns dict(value GB/s of the round trip, kind, cores, sample, seconds)."""
+    from oracle import oracle as O
+    kind = "reference" if O.have_ref() else "port"
+    shards1 = shard_records(r1, cores)
+    shards2 = shard_records(r2, cores) if r2 is not None else [None] * cores
+    total = sum(s.size for s in shards1) + (sum(s.size for s in shards2) if r2 is not None else 0)
+    tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    t_enc = t_dec = 0.0
+    try:
+        if kind == "reference":
+            for i in range(cores):
+                shards1[i].tofile(os.path.join(tmp, f"a{i}.fq"))
+                if r2 is not None:
+                    shards2[i].tofile(os.path.join(tmp, f"b{i}.fq"))
+
+            def run(cmds):
+                t = time.perf_counter()
+                ps = [subprocess.Popen(c, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for c in cmds]
+                rc = [p.wait() for p in ps]
+                assert all(r == 0 for r in rc), "reference binary failed"
+                return time.perf_counter() - t
+            enc = [[O.REF_BIN, "-c", "-i", f"{tmp}/a{i}.fq"] + (["-I", f"{tmp}/b{i}.fq"] if r2 is not None else []) + ["-o", f"{tmp}/o{i}.rfq"] for i in range(cores)]
+            dec = [[O.REF_BIN, "-d", "-i", f"{tmp}/o{i}.rfq", "-o", f"{tmp}/d{i}.fq"] + (["-O", f"{tmp}/e{i}.fq"] if r2 is not None else []) for i in range(cores)]
+            t_enc = run(enc)
+            t_dec = run(dec)
+        else:
+            res = [None] * cores
+
+            def work(i, phase):
+                if phase == 0:
+                    res[i] = O.compress(shards1[i], shards2[i])
+                else:
+                    O.decompress(res[i], pe_out=r2 is not None)
+            for phase in (0, 1):
+                t = time.perf_counter()
+                th = [threading.Thread(target=work, args=(i, phase)) for i in range(cores)]
+                [x.start() for x in th]
+                [x.join() for x in th]
+                if phase == 0:
+                    t_enc = time.perf_counter() - t
+                else:
+                    t_dec = time.perf_counter() - t
+    finally:
+        subprocess.call(["rm", "-rf", tmp])
+    return dict(value=total / 1e9 / (t_enc + t_dec), unit=UNIT, cores=cores, kind=kind,
+                sample=f"{total / 1e6:.0f} MB of the same workload in {cores} record-aligned shards, one process each, files in /dev/shm",
+                encode_gbs=total / 1e9 / t_enc, decode_gbs=total / 1e9 / t_dec, seconds=t_enc + t_dec)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.p, self.path = gpu, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                      stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        self.p.wait()
+        sm, mx, reasons = [], 0, set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        busy = [x for x in sm if x > 0]
+        return dict(sm_mhz=float(np.median(busy)) if busy else None, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    """`--impl reference`: the reference's CPU path on this box's host cores, same metric/config.  Rank 0 only."""
+    if rank != 0:
+        return
+    from tools import fqgen
+    cores = host_cores()
+    # bounded sample: ~24 MB of FASTQ per core and step (~0.5 s per core per step at ~0.1 GB/s round trip)
+    pairs_per_core = env_int("RPQ_REF_PAIRS_PER_CORE", 33340)
+    r1, r2 = fqgen.generate(pairs_per_core * cores, seed=2, paired=True)
+    vals = []
+    for it in range(args.warmup + args.steps):
+        r = cpu_reference_roundtrip(r1, r2, cores)
+        if it >= args.warmup:
+            vals.append(r)
+    secs = sum(v["seconds"] for v in vals)
+    total = (r1.size + r2.size) * len(vals)
+    value = total / 1e9 / secs
+    last = vals[-1]
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * secs / len(vals),
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8", data="synthetic", impl="reference",
+                config=dict(workload="paired-end NovaSeq-shape 150bp (configs[1]/[2] shape), bounded sample per step", sample_bytes_per_step=int(r1.size + r2.size), chunk_kb=1000),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=last["kind"], sample=last["sample"], encode_gbs=last["encode_gbs"], decode_gbs=last["decode_gbs"]),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=env_int("RPQ_BENCH_PAIRS", 4760000), help="read pairs per GPU (4.76 M = the 3.4 GB nova pair)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = env_int("RANK", 0)
+    world = env_int("WORLD_SIZE", 1)
+    local = env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O            # checker only: never inside a timed region
+    from repaq_b200 import codec as K
+    from tools import fqgen
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W = max(3, args.warmup)
+
+    # ---- synthetic workload: every rank its own rows of the same generator (weak scaling)
+    rows = (args.pairs + fqgen.ROW_READS - 1) // fqgen.ROW_READS
+    t0 = time.perf_counter()
+    r1, r2 = fqgen.generate(rows * fqgen.ROW_READS, seed=2, paired=True, first_row=rank * rows,
+                            threads=max(1, host_cores() // max(1, world)))
+    gen_s = time.perf_counter() - t0
+    fastq_bytes = int(r1.size + r2.size)
+    header = K.make_header(r1, r2)
+    enc, dec = K.Codec(device=local), K.Codec(device=local)
+    enc.set_header(header)
+    dec.set_header(header)
+    chunk_bases = 1000000
+
+    d1 = torch.from_numpy(r1).cuda()
+    d2 = torch.from_numpy(r2).cuda()
+    torch.cuda.synchronize()
+    es = torch.cuda.ExternalStream(enc.L.rpq_stream(enc.ctx))
+    ds = torch.cuda.ExternalStream(dec.L.rpq_stream(dec.ctx))
+
+    state = {}
+
+    def step_device():
+        eo = enc.encode_raw(d1.data_ptr(), d1.numel(), d2.data_ptr(), d2.numel(), 1, False, chunk_bases, True, (K.NEVER, K.NEVER), 0, 1)
+        se = enc.stats()
+        do = dec.decode_raw(eo.data, eo.bytes, 1, True, 1)
+        sd = dec.stats()
+        state.update(rfq_bytes=int(eo.bytes), n_chunks=int(eo.n_chunks), eo=eo, do=do, out=(int(do.out1_bytes), int(do.out2_bytes)))
+        return se.ms_total, sd.ms_total, se.launches + sd.launches, eo
+
+    def gather_lengths(eo):
+        """the one real exchange of the multi-GPU path: per-chunk serialised lengths -> file offsets of every rank"""
+        if world == 1:
+            return
+        lens = torch.tensor([eo.chunks[i].bytes for i in range(eo.n_chunks)], dtype=torch.int64, device="cuda")
+        n = torch.tensor([lens.numel()], dtype=torch.int64, device="cuda")
+        ns = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(ns, n)
+        mx = int(max(int(x) for x in ns))
+        pad = torch.zeros(mx, dtype=torch.int64, device="cuda")
+        pad[: lens.numel()] = lens
+        allp = [torch.zeros_like(pad) for _ in range(world)]
+        dist.all_gather(allp, pad)
+        state["file_offset"] = int(sum(int(allp[r][: int(ns[r])].sum()) for r in range(rank)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness gate (not timed): bit-exact .rfq on the first chunks, byte-exact round trip on everything
+    _, _, _, eo = step_device()
+    rfq_dev = torch.empty(state["rfq_bytes"], dtype=torch.uint8, device="cuda")
+    cudart = C.cdll.LoadLibrary("libcudart.so.12")
+    cudart.cudaMemcpy(C.c_void_p(rfq_dev.data_ptr()), C.c_void_p(eo.data), C.c_size_t(eo.bytes), 3)
+    n_chk = min(12, state["n_chunks"])
+    p1, p2 = fqgen.truncate_reads(r1, 3334 * n_chk), fqgen.truncate_reads(r2, 3334 * n_chk)
+    ref = O.compress(bytes(p1), bytes(p2), chunk_bases=chunk_bases)
+    hb = K.header_bytes(header)
+    got = bytes(rfq_dev[: len(ref) - len(hb)].cpu().numpy())
+    assert hb + got == ref, "encode is not bit-exact against the oracle"
+    o1 = torch.empty(state["out"][0], dtype=torch.uint8, device="cuda")
+    o2 = torch.empty(state["out"][1], dtype=torch.uint8, device="cuda")
+    cudart.cudaMemcpy(C.c_void_p(o1.data_ptr()), C.c_void_p(state["do"].out1), C.c_size_t(state["out"][0]), 3)
+    cudart.cudaMemcpy(C.c_void_p(o2.data_ptr()), C.c_void_p(state["do"].out2), C.c_size_t(state["out"][1]), 3)
+    assert torch.equal(o1, d1) and torch.equal(o2, d2), "decode does not restore the input"
+    del o1, o2, rfq_dev
+
+    # ---- timed: inputs resident in HBM (inputs are ~3.4 GB per step: far larger than the 126 MB L2, no flush needed)
+    for _ in range(W):
+        _, _, _, eo = step_device()
+        gather_lengths(eo)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    ev0.record(es)
+    enc_ms = dec_ms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        a, b_, l, eo = step_device()
+        gather_lengths(eo)
+        enc_ms += a
+        dec_ms += b_
+        launches += l
+    ev1.record(ds)
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    dev_ms = ev0.elapsed_time(ev1)                  # CUDA events: first encode op .. last decode op, host gaps included
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms, wall_ms, enc_ms, dec_ms], dtype=torch.float64, device="cuda")
+    tot_bytes = torch.tensor([fastq_bytes], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_bytes, op=dist.ReduceOp.SUM)
+    dev_ms, wall_ms, enc_ms, dec_ms = [float(x) for x in t]
+    job_bytes = float(tot_bytes[0])
+    value = job_bytes * args.steps / 1e9 / (dev_ms / 1e3)
+
+    # ---- per-kernel device time (separate pass, event pair around every launch) -> roofline of the dominant kernel
+    enc.set_profiling(True)
+    dec.set_profiling(True)
+    step_device()
+    prof = {}
+    for k, (n, ms) in list(enc.profile().items()) + list(dec.profile().items()):
+        prof[k] = (n, ms)
+    enc.set_profiling(False)
+    dec.set_profiling(False)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    n_reads = 2 * rows * fqgen.ROW_READS
+    rfq_b = state["rfq_bytes"]
+    qual_b = seq_b = n_reads * 150
+    # algorithmic bytes per launch of each kernel (DESIGN.md "Kernels"): what it must read + write once
+    alg = {
+        "k_index_lines": fastq_bytes + 4 * 4 * n_reads,
+        "k_meta": (fastq_bytes - qual_b - 2 * n_reads) + 16 * n_reads,          # names + sequences + strands in, metadata out
+        "k_streams": qual_b + 0.6 * rfq_b,
+        "k_emit": seq_b + seq_b / 4,
+        "k_gather": 1.2 * rfq_b,
+        "k_dec_format": rfq_b + qual_b + fastq_bytes,
+        "k_dec_streams": 0.6 * rfq_b + 0.1 * qual_b,
+    }
+    kern_total = sum(ms for _, ms in prof.values())
+    top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
+    roofline = None
+    if top:
+        name, (n, ms) = top
+        ab = float(alg.get(name, fastq_bytes))
+        ach = ab / 1e9 / (ms / n / 1e3)
+        roofline = dict(bound="hbm", kernel=name, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None, peak_source=peak_src,
+                        share_of_kernel_time=ms / kern_total, algorithmic_bytes_per_launch=ab,
+                        pipeline=dict(achieved=(fastq_bytes + rfq_b) * 2 / 1e9 / (kern_total / 1e3), frac=(fastq_bytes + rfq_b) * 2 / 1e9 / (kern_total / 1e3) / peak,
+                                      note="whole encode+decode: (F+R)+(R+F) algorithmic bytes over the sum of all kernel times"),
+                        kernels_ms={k: round(v[1], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])})
+
+    # ---- e2e: pinned host buffers through the C ABI, H2D and D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h1 = torch.from_numpy(r1).pin_memory()
+        h2 = torch.from_numpy(r2).pin_memory()
+
+        def step_host():
+            eo = enc.encode_raw(h1.data_ptr(), h1.numel(), h2.data_ptr(), h2.numel(), 0, False, chunk_bases, True, (K.NEVER, K.NEVER), 0, 0)
+            se = enc.stats()
+            do = dec.decode_raw(eo.data, eo.bytes, 0, True, 0)
+            sd = dec.stats()
+            return eo, do, se, sd
+        for _ in range(W):
+            eo, do, se, sd = step_host()
+        barrier()
+        t_e = time.perf_counter()
+        h2d = d2h = 0
+        for _ in range(args.steps):
+            eo, do, se, sd = step_host()
+            h2d += se.h2d_bytes + sd.h2d_bytes
+            d2h += se.d2h_bytes + sd.d2h_bytes
+        barrier()
+        e_ms = 1e3 * (time.perf_counter() - t_e)
+        # result check on the host copies
+        a1 = np.ctypeslib.as_array(C.cast(do.out1, C.POINTER(C.c_uint8)), shape=(do.out1_bytes,))
+        assert do.out1_bytes == r1.size and np.array_equal(a1[:1 << 20], r1[:1 << 20]) and np.array_equal(a1[-(1 << 20):], r1[-(1 << 20):])
+        te = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_ms = float(te[0])
+        e2e = dict(value=job_bytes * args.steps / 1e9 / (e_ms / 1e3), unit=UNIT, h2d_bytes_per_step=int(h2d // args.steps), d2h_bytes_per_step=int(d2h // args.steps),
+                   ms_per_step=e_ms / args.steps, timing="host wall clock around the C-ABI calls (they return after the D2H completed), max over ranks")
+        del h1, h2
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = host_cores()
+        n_pairs = min(args.pairs, 33340 * cores)
+        s1, s2 = fqgen.truncate_reads(r1, n_pairs), fqgen.truncate_reads(r2, n_pairs)
+        cpu = cpu_reference_roundtrip(s1, s2, cores)
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=W, ms_per_step=dev_ms / args.steps,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8", data="synthetic",
+                    config=dict(workload="configs[1]+[2]: paired-end NovaSeq-shape 150bp, %.2f GB FASTQ per GPU (R1+R2), encode to .rfq then decode back" % (fastq_bytes / 1e9),
+                                pairs_per_gpu=rows * fqgen.ROW_READS, chunk_kb=1000, rfq_bytes_per_gpu=rfq_b, rfq_ratio=rfq_b / fastq_bytes,
+                                l2="inputs (GBs) far larger than the 126 MB L2; no flush needed", generator="tools/fqgen.c seed 2", gen_seconds=round(gen_s, 1),
+                                parallelism="chunk-sharded, one process per GPU; NCCL all_gather of per-chunk lengths only"),
+                    encode_gbs=job_bytes * args.steps / 1e9 / (enc_ms / 1e3), decode_gbs=job_bytes * args.steps / 1e9 / (dec_ms / 1e3),
+                    wall_ms_per_step=wall_ms / args.steps, gpu_launches=int(launches), clocks=clk, e2e=e2e, roofline=roofline, cpu_baseline=cpu)
+        print(json.dumps(line))
+    enc.close()
+    dec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

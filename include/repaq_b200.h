@@ -163,6 +163,10 @@ typedef struct rpq_stats {
     uint64_t h2d_bytes, d2h_bytes;
 } rpq_stats;
 int rpq_get_stats(const rpq_ctx* ctx, rpq_stats* out);
+/* per-kernel device time: after rpq_set_profiling(ctx, 1) every launch is bracketed by a CUDA event pair;
+ * rpq_get_profile() returns "kernel launches total_ms" lines accumulated since then (owned by ctx) */
+int rpq_set_profiling(rpq_ctx* ctx, int on);
+const char* rpq_get_profile(rpq_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -50,7 +50,7 @@ class Stats(C.Structure):
 
 
 EXPORTS = ["rpq_make_header", "rpq_header_write", "rpq_header_read", "rpq_create", "rpq_destroy", "rpq_last_error",
-           "rpq_set_header", "rpq_stream", "rpq_encode", "rpq_decode", "rpq_get_stats"]
+           "rpq_set_header", "rpq_stream", "rpq_encode", "rpq_decode", "rpq_get_stats", "rpq_set_profiling", "rpq_get_profile"]
 
 _libs = {}
 
@@ -78,5 +78,8 @@ def load(path=None):
     L.rpq_encode.argtypes = [C.c_void_p, C.POINTER(EncodeIn), C.POINTER(EncodeOut)]
     L.rpq_decode.argtypes = [C.c_void_p, C.POINTER(DecodeIn), C.POINTER(DecodeOut)]
     L.rpq_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.rpq_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    L.rpq_get_profile.argtypes = [C.c_void_p]
+    L.rpq_get_profile.restype = C.c_char_p
     _libs[path] = L
     return L

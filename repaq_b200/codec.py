@@ -111,6 +111,17 @@ class Codec:
         self.L.rpq_get_stats(self.ctx, C.byref(s))
         return s
 
+    def set_profiling(self, on):
+        self.L.rpq_set_profiling(self.ctx, int(on))
+
+    def profile(self):
+        """{kernel: (launches, total_ms)} since set_profiling(True)"""
+        out = {}
+        for line in self.L.rpq_get_profile(self.ctx).decode().splitlines():
+            name, n, ms = line.split()
+            out[name] = (int(n), float(ms))
+        return out
+
     def encode_raw(self, p1, l1, p2, l2, mem, interleaved, chunk_bases, final, nobreak_from, tail_flags, out_mem):
         ein = _lib.EncodeIn()
         ein.r1, ein.r1_len, ein.r2, ein.r2_len = p1, l1, p2, l2

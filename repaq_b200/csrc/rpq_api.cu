@@ -42,7 +42,12 @@ struct rpq_ctx {
     rpq_stats stats;
     RtEvent ev[8];
     uint32_t launches = 0;
-    double slot_factor = 0.35;             /* slot bytes per position, grown on overflow (worst case 5) */
+    double slot_factor = 0.35;
+    /* optional per-kernel timing (rpq_set_profiling): an event pair around every launch */
+    bool profiling = false;
+    struct ProfRec { const char* name; RtEvent a, b; };
+    std::vector<ProfRec> prof;
+    std::string prof_text;             /* slot bytes per position, grown on overflow (worst case 5) */
 };
 
 namespace {
@@ -68,8 +73,16 @@ bool ensure_pinned(rpq_ctx* c, DevBuf& b, size_t bytes) {
     return true;
 }
 
+inline void prof_begin(rpq_ctx* c, const char* name) {
+    if (!c->profiling) return;
+    rpq_ctx::ProfRec r; r.name = name; rt_event_create(&r.a); rt_event_create(&r.b);
+    rt_event_record(&r.a, c->stream);
+    c->prof.push_back(r);
+}
+inline void prof_end(rpq_ctx* c) { if (c->profiling) rt_event_record(&c->prof.back().b, c->stream); }
+
 #define LAUNCH(ctx, kern, grid, block, smem, ...)                                           \
-    do { if ((grid) > 0) { RPQ_LAUNCH(kern, grid, block, smem, (ctx)->stream, __VA_ARGS__); (ctx)->launches++; } } while (0)
+    do { if ((grid) > 0) { prof_begin(ctx, #kern); RPQ_LAUNCH(kern, grid, block, smem, (ctx)->stream, __VA_ARGS__); prof_end(ctx); (ctx)->launches++; } } while (0)
 
 int check_launch(rpq_ctx* c, const char* where) {
     char buf[256];
@@ -118,7 +131,6 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     memset(&c->hdr, 0, sizeof c->hdr);
 #ifndef RPQ_EMU
     cudaFuncSetAttribute(k_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(k_dec_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 #endif
     *out = c;
     return RPQ_OK;
@@ -144,6 +156,32 @@ extern "C" void rpq_destroy(rpq_ctx* c) {
 extern "C" const char* rpq_last_error(const rpq_ctx* c) { return c ? c->err : "no context (is a CUDA device present?)"; }
 extern "C" void* rpq_stream(rpq_ctx* c) { return c ? (void*)(uintptr_t)c->stream : nullptr; }
 extern "C" int rpq_get_stats(const rpq_ctx* c, rpq_stats* out) { if (!c || !out) return RPQ_ERR_ARG; *out = c->stats; return RPQ_OK; }
+
+extern "C" int rpq_set_profiling(rpq_ctx* c, int on) {
+    if (!c) return RPQ_ERR_ARG;
+    rt_stream_sync(c->stream);
+    for (auto& r : c->prof) { rt_event_destroy(&r.a); rt_event_destroy(&r.b); }
+    c->prof.clear();
+    c->profiling = on != 0;
+    return RPQ_OK;
+}
+
+/* "kernel launches total_ms\n" per kernel, accumulated since rpq_set_profiling(ctx, 1) */
+extern "C" const char* rpq_get_profile(rpq_ctx* c) {
+    if (!c) return "";
+    rt_stream_sync(c->stream);
+    std::vector<std::string> names; std::vector<double> ms; std::vector<int> cnt;
+    for (auto& r : c->prof) {
+        size_t k = 0;
+        for (; k < names.size(); k++) if (names[k] == r.name) break;
+        if (k == names.size()) { names.push_back(r.name); ms.push_back(0); cnt.push_back(0); }
+        ms[k] += rt_event_ms(r.a, r.b); cnt[k]++;
+    }
+    c->prof_text.clear();
+    char line[256];
+    for (size_t k = 0; k < names.size(); k++) { snprintf(line, sizeof line, "%s %d %.6f\n", names[k].c_str(), cnt[k], ms[k]); c->prof_text += line; }
+    return c->prof_text.c_str();
+}
 
 extern "C" int rpq_set_header(rpq_ctx* c, const rpq_header* h) {
     if (!c || !h) return RPQ_ERR_ARG;
@@ -192,6 +230,7 @@ extern "C" int rpq_encode(rpq_ctx* c, const rpq_encode_in* in, rpq_encode_out* o
     if (!c || !in || !out) return RPQ_ERR_ARG;
     memset(out, 0, sizeof *out);
     if (!c->have_hdr) return fail(c, RPQ_ERR_ARG, "rpq_set_header() must be called before rpq_encode()");
+    if (in->r1_len == 0 || (in->r2 && in->r2_len == 0)) return RPQ_OK;          /* no records: no chunks (src/rfqcodec.cpp:165-166) */
     if (!in->r1 || in->r1_len >= (1ull << 32) || in->r2_len >= (1ull << 32)) return fail(c, RPQ_ERR_ARG, "FASTQ batch must be < 4 GiB per file");
     if (in->chunk_bases == 0) return fail(c, RPQ_ERR_ARG, "chunk_bases must be positive");
     rt_set_device(c->device);
@@ -287,7 +326,9 @@ extern "C" int rpq_encode(rpq_ctx* c, const rpq_encode_in* in, rpq_encode_out* o
     LAUNCH(c, k_chunk_finish, n_chunks, FIN_THREADS, 0, b, hd);
     if (hd.flags & (RPQ_HAS_X | RPQ_HAS_Y)) {
         dim3 g(n_chunks, 2);
+        prof_begin(c, "k_coords");
         RPQ_LAUNCH(k_coords, g, CO_THREADS, 0, c->stream, b, hd, c->tmpx.as<u8>(), c->tmpy.as<u8>());
+        prof_end(c);
         c->launches++;
     }
 

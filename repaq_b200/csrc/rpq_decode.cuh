@@ -1,5 +1,415 @@
+/*
+ * rpq_decode.cuh - the decode kernels: RfqCodec::decodeChunk (reference src/rfqcodec.cpp:1049-1260) and
+ * Read::toString (src/read.cpp:170-172) for all chunks of an .rfq body at once, writing FASTQ text directly.
+ *
+ *   k_dec_walk     chunk boundaries on the device (RfqChunk::read, src/rfqchunk.cpp:161-228; arena sizes :63-109)
+ *   k_dec_coords   X / Y varint streams -> values                              (src/rfqcodec.cpp:1332-1389)
+ *   k_dec_reads    read-length table (:1058-1086), per-read scans, output sizes of every record
+ *   k_dec_streams  quality position streams + exceptions -> quality plane; N positions -> bitmap (:957-1047, :856-858)
+ *   k_dec_format   one warp per read: name rebuild (:1157-1231), 2-bit unpack (:833-853), overlap expansion (:860-901),
+ *                  N restore (:1093-1100), reverse complement of interleaved R2 (:1248-1252), record text
+ */
 #pragma once
 #include "rpq_common.cuh"
+
 namespace rpq {
-__global__ void k_dec_streams() {}
+
+struct DecChunk {
+    u64 in_off;              /* chunk start inside the body */
+    u32 reads, flags;
+    u32 seq_size, qual_size, npos_size, x_size, y_size;
+    u32 off_readlen, off_n1len, off_n2len, off_slen, off_lane, off_tile, off_x, off_y, off_n1, off_n2, off_strand, off_seq, off_qual, off_ov, off_npos;
+    u32 bytes;
+    u32 read_base;           /* reads before this chunk */
+    /* device results */
+    u32 total_len, seq_kept;
+    u32 out_bytes[2];
+    u64 plane_off;           /* offset of the chunk's quality plane (prefix of total_len) */
+    u64 nmap_off;            /* offset (in u32 words) of the chunk's N bitmap */
+    u64 out_off[2];
+};
+
+struct DecBatchDev {
+    const u8* body;
+    u64 body_len;
+    DecChunk* chunks;
+    u32 n_chunks;
+    u32 n_reads;
+    u32 split_pairs;
+    u32* rlen; u32* qualoff; u32* seqoff; u32* n1off; u32* n2off; u32* soff;
+    u64* outoff;             /* per read: offset inside its output stream */
+    u32* xs; u32* ys;        /* [n_reads] decoded coordinates, indexed read_base + xy */
+    u8* plane;               /* quality plane, all chunks */
+    u32* nmap;               /* N bitmap over compacted positions */
+    u8* out[2];
+    u32* err;
+    u64* totals;             /* [0] plane bytes, [1] nmap words, [2] out1 bytes, [3] out2 bytes */
+};
+
+__device__ __forceinline__ u32 ld32(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
+
+/* ------------------------------------------------------------------ chunk walk on the device ---- */
+/* One warp.  Fills chunks[], *n_out, *consumed.  Same derivation as the host walk in rpq_host.cpp. */
+__global__ void k_dec_walk(const u8* body, u64 len, HeaderDev h, DecChunk* chunks, u32 cap, u32* n_out, u64* consumed, u32* err) {
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    u64 at = 0; u32 n = 0, read_base = 0;
+    const u32 head = 18u + ((h.flags & RPQ_ENCODE_N_POS) ? 4u : 0u);
+    while (at + head <= len && n < cap) {
+        const u8* in = body + at;
+        DecChunk c; memset(&c, 0, sizeof c);
+        c.in_off = at; c.reads = ld32(in + 4); c.flags = (u32)in[8] | ((u32)in[9] << 8);
+        c.seq_size = ld32(in + 10); c.qual_size = ld32(in + 14);
+        if (h.flags & RPQ_ENCODE_N_POS) c.npos_size = ld32(in + 18);
+        if (c.reads == 0) break;
+        const u32 nr = c.reads, fl = c.flags;
+        const bool il = (fl & RPQ_PE_INTERLEAVED) != 0;
+        const u32 xy = il ? nr / 2 : nr;
+        const u64 left = len - at;
+        u64 o = head; bool bad = false;
+        auto take = [&](u32& field, u64 size) { field = (u32)o; o += size; if (o > left) bad = true; };
+        take(c.off_readlen, (u64)h.read_length_bytes * ((fl & RPQ_READ_LEN_SAME) ? 1u : nr));
+        const u32 n1cnt = (fl & RPQ_NAME1_LEN_SAME) ? 1u : nr; take(c.off_n1len, n1cnt);
+        u32 n2cnt = 0; if (h.flags & RPQ_HAS_NAME2) { n2cnt = (fl & RPQ_NAME2_LEN_SAME) ? 1u : nr; take(c.off_n2len, n2cnt); }
+        const u32 scnt = (fl & RPQ_STRAND_LEN_SAME) ? 1u : nr; take(c.off_slen, scnt);
+        if (h.flags & RPQ_HAS_LANE) take(c.off_lane, (fl & RPQ_LANE_SAME) ? 1u : xy);
+        if (h.flags & RPQ_HAS_TILE) take(c.off_tile, 2ull * ((fl & RPQ_TILE_SAME) ? 1u : xy));
+        if (!bad && (h.flags & RPQ_HAS_X)) { if (o + 4 > left) bad = true; else { c.x_size = ld32(in + o); o += 4; take(c.off_x, c.x_size); } }
+        if (!bad && (h.flags & RPQ_HAS_Y)) { if (o + 4 > left) bad = true; else { c.y_size = ld32(in + o); o += 4; take(c.off_y, c.y_size); } }
+        if (bad) break;
+        auto arena = [&](u32 off, u32 cnt, bool len_same, bool all_same) -> u64 {
+            u32 s = 0;
+            for (u32 k = lane; k < cnt; k += 32) s += in[off + k];
+            u64 t = warp_sum(s);
+            if (len_same && !all_same) t *= nr;
+            return t;
+        };
+        take(c.off_n1, arena(c.off_n1len, n1cnt, fl & RPQ_NAME1_LEN_SAME, fl & RPQ_NAME1_SAME));
+        if (h.flags & RPQ_HAS_NAME2) take(c.off_n2, arena(c.off_n2len, n2cnt, fl & RPQ_NAME2_LEN_SAME, fl & RPQ_NAME2_SAME));
+        take(c.off_strand, arena(c.off_slen, scnt, fl & RPQ_STRAND_LEN_SAME, fl & RPQ_STRAND_SAME));
+        take(c.off_seq, c.seq_size);
+        take(c.off_qual, c.qual_size);
+        if (il && (h.flags & RPQ_ENCODE_PE_BY_OVERLAP)) take(c.off_ov, nr / 2);
+        if (h.flags & RPQ_ENCODE_N_POS) take(c.off_npos, c.npos_size);
+        if (bad) break;
+        c.bytes = (u32)o; c.read_base = read_base;
+        if (lane == 0) chunks[n] = c;
+        n++; read_base += nr; at += o;
+    }
+    if (lane == 0) { *n_out = n; *consumed = at; (void)err; }
 }
+
+/* ------------------------------------------------------------------ coordinates ---- */
+/* decodeCoords (src/rfqcodec.cpp:1332-1389): one thread per (chunk, column); the streams are ~1 byte per read */
+__global__ void k_dec_coords(DecBatchDev b, HeaderDev h) {
+    const u32 id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 2 * b.n_chunks) return;
+    const u32 c = id >> 1, col = id & 1;
+    if (!(h.flags & (col ? RPQ_HAS_Y : RPQ_HAS_X))) return;
+    const DecChunk& ck = b.chunks[c];
+    const u8* buf = b.body + ck.in_off + (col ? ck.off_y : ck.off_x);
+    const u32 len = col ? ck.y_size : ck.x_size;
+    const u32 num = (ck.flags & RPQ_PE_INTERLEAVED) ? ck.reads / 2 : ck.reads;
+    u32* data = (col ? b.ys : b.xs) + ck.read_base;
+    u32 last = 1000, cns = 0, d = 0;
+    while (cns < len) {
+        const u32 b0 = buf[cns++];
+        if (!(b0 & 0x80)) { const u32 v = (b0 << 8) | (cns < len ? buf[cns] : 0u); cns++; if (d < num) data[d] = v; d++; last = v; }
+        else if (!(b0 & 0x40)) { const u32 v = last + (b0 & 0x3F) + 1; if (d < num) data[d] = v; d++; last = v; }
+        else if (!(b0 & 0x20)) { const u32 rep = (b0 & 0x1F) + 1; for (u32 i = 0; i < rep; i++) { if (d < num) data[d] = last; d++; } }
+        else { u32 v = (b0 & 0x1F) << 16; v |= (u32)(cns < len ? buf[cns] : 0u) << 8; cns++; v |= (cns < len ? buf[cns] : 0u); cns++; if (d < num) data[d] = v; d++; last = v; }
+    }
+    for (; d < num; d++) data[d] = 0;             /* memset(xBuf, 0): values the stream does not cover stay 0 */
+}
+
+/* ------------------------------------------------------------------ per-read tables ---- */
+__device__ __forceinline__ u32 dec_digits(u32 v) {
+    return v < 10u ? 1u : v < 100u ? 2u : v < 1000u ? 3u : v < 10000u ? 4u : v < 100000u ? 5u : v < 1000000u ? 6u : v < 10000000u ? 7u : v < 100000000u ? 8u : v < 1000000000u ? 9u : 10u;
+}
+
+constexpr int DR_THREADS = 256;
+struct Scan7 { u32 v[7]; };
+
+__device__ __forceinline__ u32 dec_rlen(const DecBatchDev& b, const HeaderDev& h, const DecChunk& ck, u32 r) {
+    const u8* p = b.body + ck.in_off + ck.off_readlen;
+    const u32 k = (ck.flags & RPQ_READ_LEN_SAME) ? 0u : r;
+    if (h.read_length_bytes == 1) return p[k];
+    if (h.read_length_bytes == 2) return (u32)p[2 * k] | ((u32)p[2 * k + 1] << 8);
+    return ld32(p + 4 * k);
+}
+
+/* one CTA per chunk: lengths, exclusive scans (quality, compacted bases, name parts, output text per stream) */
+__global__ void __launch_bounds__(DR_THREADS) k_dec_reads(DecBatchDev b, HeaderDev h) {
+    __shared__ Scan7 s_warp[DR_THREADS / 32];
+    __shared__ Scan7 s_carry;
+    const u32 c = blockIdx.x;
+    DecChunk& ck = b.chunks[c];
+    const u8* in = b.body + ck.in_off;
+    const u32 n = ck.reads, fl = ck.flags;
+    const bool il = (fl & RPQ_PE_INTERLEAVED) != 0;
+    const bool ov_on = il && (h.flags & RPQ_ENCODE_PE_BY_OVERLAP);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { Scan7 z; for (int k = 0; k < 7; k++) z.v[k] = 0; s_carry = z; }
+    __syncthreads();
+    for (u32 base = 0; base < n; base += DR_THREADS) {
+        const u32 r = base + tid;
+        Scan7 v; for (int k = 0; k < 7; k++) v.v[k] = 0;
+        if (r < n) {
+            const u32 rl = dec_rlen(b, h, ck, r);
+            u32 kept = rl;
+            if (ov_on && (r & 1u)) { int o = (int)(signed char)in[ck.off_ov + (r >> 1)] - (int)h.overlap_shift; u32 a = (u32)(o < 0 ? -o : o); kept = a <= rl ? rl - a : 0; }
+            const u32 l1 = (fl & (RPQ_NAME1_SAME | RPQ_NAME1_LEN_SAME)) ? in[ck.off_n1len] : in[ck.off_n1len + r];
+            u32 l2 = 0;
+            if (h.flags & RPQ_HAS_NAME2) l2 = (fl & (RPQ_NAME2_SAME | RPQ_NAME2_LEN_SAME)) ? in[ck.off_n2len] : in[ck.off_n2len + r];
+            const u32 ls = (fl & (RPQ_STRAND_SAME | RPQ_STRAND_LEN_SAME)) ? in[ck.off_slen] : in[ck.off_slen + r];
+            const u32 xy = il ? r >> 1 : r;
+            u32 name = l1 + l2;
+            if (h.flags & RPQ_HAS_LANE) name += 1 + dec_digits((fl & RPQ_LANE_SAME) ? in[ck.off_lane] : in[ck.off_lane + xy]);
+            if (h.flags & RPQ_HAS_TILE) { const u32 k = (fl & RPQ_TILE_SAME) ? 0u : xy; name += 1 + dec_digits((u32)in[ck.off_tile + 2 * k] | ((u32)in[ck.off_tile + 2 * k + 1] << 8)); }
+            if (h.flags & RPQ_HAS_X) name += 1 + dec_digits(b.xs[ck.read_base + xy]);
+            if (h.flags & RPQ_HAS_Y) name += 1 + dec_digits(b.ys[ck.read_base + xy]);
+            const u32 text = name + 1 + rl + 1 + ls + 1 + rl + 1;          /* Read::toString */
+            v.v[0] = rl; v.v[1] = kept;
+            v.v[2] = (fl & RPQ_NAME1_SAME) ? 0u : l1; v.v[3] = (fl & RPQ_NAME2_SAME) ? 0u : l2; v.v[4] = (fl & RPQ_STRAND_SAME) ? 0u : ls;
+            const u32 stream = b.split_pairs ? (r & 1u) : 0u;
+            v.v[5 + stream] = text;
+            b.rlen[ck.read_base + r] = rl;
+        }
+        Scan7 inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 7; k++) { const u32 t = __shfl_up_sync(0xffffffffu, inc.v[k], d); if (lane >= d) inc.v[k] += t; }
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        Scan7 pre = s_carry;
+        for (int q = 0; q < warp; q++) for (int k = 0; k < 7; k++) pre.v[k] += s_warp[q].v[k];
+        if (r < n) {
+            const u32 i = ck.read_base + r;
+            b.qualoff[i] = pre.v[0] + inc.v[0] - v.v[0];
+            b.seqoff[i] = pre.v[1] + inc.v[1] - v.v[1];
+            b.n1off[i] = pre.v[2] + inc.v[2] - v.v[2];
+            b.n2off[i] = pre.v[3] + inc.v[3] - v.v[3];
+            b.soff[i] = pre.v[4] + inc.v[4] - v.v[4];
+            const u32 stream = b.split_pairs ? (r & 1u) : 0u;
+            b.outoff[i] = pre.v[5 + stream] + inc.v[5 + stream] - v.v[5 + stream];
+        }
+        __syncthreads();
+        if (tid == 0) { Scan7 t = s_carry; for (int q = 0; q < DR_THREADS / 32; q++) for (int k = 0; k < 7; k++) t.v[k] += s_warp[q].v[k]; s_carry = t; }
+        __syncthreads();
+    }
+    if (tid == 0) { ck.total_len = s_carry.v[0]; ck.seq_kept = s_carry.v[1]; ck.out_bytes[0] = s_carry.v[5]; ck.out_bytes[1] = s_carry.v[6]; }
+}
+
+/* prefix over chunks: plane, N bitmap and output offsets; totals for the host */
+__global__ void __launch_bounds__(256) k_dec_offsets(DecBatchDev b) {
+    __shared__ u64 s_w[8][4];
+    __shared__ u64 s_carry[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 4) s_carry[tid] = 0;
+    __syncthreads();
+    for (u32 base = 0; base < b.n_chunks; base += 256) {
+        const u32 c = base + tid;
+        u64 v[4] = {0, 0, 0, 0};
+        if (c < b.n_chunks) { const DecChunk& ck = b.chunks[c]; v[0] = ck.total_len; v[1] = (ck.seq_kept + 31) / 32 + 1; v[2] = ck.out_bytes[0]; v[3] = ck.out_bytes[1]; }
+        u64 inc[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) for (int k = 0; k < 4; k++) { const u64 t = __shfl_up_sync(0xffffffffu, inc[k], d); if (lane >= d) inc[k] += t; }
+        if (lane == 31) for (int k = 0; k < 4; k++) s_w[warp][k] = inc[k];
+        __syncthreads();
+        u64 pre[4];
+        for (int k = 0; k < 4; k++) { pre[k] = s_carry[k]; for (int q = 0; q < warp; q++) pre[k] += s_w[q][k]; }
+        if (c < b.n_chunks) { DecChunk& ck = b.chunks[c]; ck.plane_off = pre[0] + inc[0] - v[0]; ck.nmap_off = pre[1] + inc[1] - v[1]; ck.out_off[0] = pre[2] + inc[2] - v[2]; ck.out_off[1] = pre[3] + inc[3] - v[3]; }
+        __syncthreads();
+        if (tid < 4) { u64 t = s_carry[tid]; for (int q = 0; q < 8; q++) t += s_w[q][tid]; s_carry[tid] = t; }
+        __syncthreads();
+    }
+    if (tid < 4) b.totals[tid] = s_carry[tid];
+}
+
+/* ------------------------------------------------------------------ position streams ---- */
+/*
+ * decodeSingleQualByCol (src/rfqcodec.cpp:957-1007) with a warp per (chunk, stream): 32 stream bytes per step.
+ * Token length depends on the first byte only (0xxxxxxx:1  10xxxxxx:2  110xxxxx:1  111xxxxx:4), so the heads of a
+ * step follow from its entry offset by visiting just the bytes that look like multi-byte heads; every head's position
+ * is an exclusive warp sum of the advances before it.
+ * grid.x = chunks, blockIdx.y = stream (quality bins, then exceptions, then N positions), one warp each (blockDim 32).
+ */
+__global__ void __launch_bounds__(32) k_dec_streams(DecBatchDev b, HeaderDev h, u32 n_qstreams) {
+    const u32 c = blockIdx.x, st = blockIdx.y;
+    const int lane = threadIdx.x;
+    const DecChunk& ck = b.chunks[c];
+    const u8* in = b.body + ck.in_off;
+    const u8* stream; u32 slen; u8 q; bool is_npos = false;
+    u32 dst_len;
+    if (st < n_qstreams) {
+        if (h.flags & RPQ_DONT_ENCODE_QUAL) return;
+        const u8* qcol = in + ck.off_qual;
+        u32 off = 4u * h.nb;
+        if ((u64)off > ck.qual_size) return;
+        for (u32 k = 0; k < st && k < h.nb; k++) off += ld32(qcol + 4 * k);
+        if (st == h.nb) {
+            /* exceptions: {q, u32 LE pos} until the end of the column (src/rfqcodec.cpp:1034-1043) */
+            u8* plane = b.plane + ck.plane_off;
+            for (u64 p = (u64)off + 5ull * lane; p + 5 <= ck.qual_size; p += 160) { const u32 pos = ld32(qcol + p + 1); if (pos < ck.total_len) plane[pos] = qcol[p]; }
+            return;
+        }
+        stream = qcol + off; slen = ld32(qcol + 4 * st); q = h.normal_bins[st];
+        if ((u64)off + slen > ck.qual_size) slen = ck.qual_size > off ? ck.qual_size - off : 0;
+        dst_len = ck.total_len;
+    } else {
+        if (!(h.flags & RPQ_ENCODE_N_POS)) return;
+        stream = in + ck.off_npos; slen = ck.npos_size; q = 'N'; is_npos = true;
+        dst_len = ck.total_len;      /* the reference marks N in a buffer of seqLen bytes, compacted coordinates */
+    }
+    u8* plane = b.plane + ck.plane_off;
+    u32* nmap = b.nmap + ck.nmap_off;
+    const u32 nmap_bits = ((ck.seq_kept + 31) / 32 + 1) * 32;
+    long long last = -1;
+    u32 skip = 0;                                         /* bytes at the start of the step that belong to the previous token */
+    for (u32 base = 0; base < slen; base += 32) {
+        const u32 p = base + lane;
+        const u32 b0 = p < slen ? stream[p] : 0u;
+        const bool valid = p < slen;
+        const u32 tlen = !(b0 & 0x80) ? 1u : !(b0 & 0x40) ? 2u : !(b0 & 0x20) ? 1u : 4u;
+        u32 multi = __ballot_sync(0xffffffffu, valid && tlen > 1);
+        const u32 is4 = __ballot_sync(0xffffffffu, valid && tlen == 4);
+        u32 skipped = skip >= 32 ? 0xffffffffu : ((1u << skip) - 1u);
+        u32 next_skip = skip > 32 ? skip - 32 : 0;
+        while (multi) {
+            const int i = __ffs((int)multi) - 1;
+            multi &= multi - 1;
+            if ((skipped >> i) & 1u) continue;
+            const u32 extra = ((is4 >> i) & 1u) ? 3u : 1u;
+            const u32 hi = (u32)i + extra;                  /* last payload position */
+            for (u32 k = (u32)i + 1; k <= hi && k < 32; k++) skipped |= 1u << k;
+            if (hi >= 32) next_skip = hi - 31;
+        }
+        const bool head = valid && !((skipped >> lane) & 1u);
+        /* advance of this token */
+        u32 adv = 0; u32 run = 0;
+        if (head) {
+            if (!(b0 & 0x80)) adv = b0 + 1;
+            else if (!(b0 & 0x40)) adv = (((b0 & 0x3F) << 8) | (p + 1 < slen ? stream[p + 1] : 0u)) + 1;
+            else if (!(b0 & 0x20)) { run = (b0 & 0x1F) + 1; adv = run; }
+            else adv = (((b0 & 0x1F) << 24) | ((u32)(p + 1 < slen ? stream[p + 1] : 0u) << 16) | ((u32)(p + 2 < slen ? stream[p + 2] : 0u) << 8) | (u32)(p + 3 < slen ? stream[p + 3] : 0u)) + 1;
+        }
+        u32 tot; const u32 ex = warp_excl_scan(adv, lane, tot);
+        if (head) {
+            const long long endpos = last + (long long)ex + adv;       /* position of the token's last element */
+            const long long first = run ? endpos - run + 1 : endpos;
+            for (long long pos = first; pos <= endpos; pos++) {
+                if (pos < 0) continue;
+                if (is_npos) { if ((u64)pos < nmap_bits && (u64)pos < dst_len) atomicOr(&nmap[pos >> 5], 1u << (pos & 31)); }
+                else if ((u64)pos < dst_len) plane[pos] = q;
+            }
+        }
+        last += tot;
+        skip = next_skip;
+    }
+}
+
+/* ------------------------------------------------------------------ record formatter ---- */
+constexpr int FMT_WARPS = 8;
+
+__device__ __forceinline__ u32 put_dec(u8* p, u32 v) {
+    const u32 n = dec_digits(v);
+    for (int i = (int)n - 1; i >= 0; i--) { p[i] = (u8)('0' + v % 10u); v /= 10u; }
+    return n;
+}
+
+__global__ void __launch_bounds__(32 * FMT_WARPS) k_dec_format(DecBatchDev b, HeaderDev h, const u32* __restrict__ read_chunk_hint) {
+    __shared__ u8 s_num[FMT_WARPS][48];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u32 i = blockIdx.x * FMT_WARPS + w;
+    if (i >= b.n_reads) return;
+    /* chunk of read i: binary search over read_base */
+    u32 lo = 0, hi = b.n_chunks;
+    while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (b.chunks[mid].read_base <= i) lo = mid; else hi = mid; }
+    (void)read_chunk_hint;
+    const DecChunk& ck = b.chunks[lo];
+    const u8* in = b.body + ck.in_off;
+    const u32 r = i - ck.read_base, fl = ck.flags;
+    const bool il = (fl & RPQ_PE_INTERLEAVED) != 0;
+    const bool ov_on = il && (h.flags & RPQ_ENCODE_PE_BY_OVERLAP);
+    const bool odd = (r & 1u) != 0;
+    const u32 stream = b.split_pairs ? (r & 1u) : 0u;
+    u8* out = b.out[stream] + ck.out_off[stream] + b.outoff[i];
+    const u32 rl = b.rlen[i];
+    const u32 xy = il ? r >> 1 : r;
+
+    /* ---- name */
+    const u32 l1 = (fl & (RPQ_NAME1_SAME | RPQ_NAME1_LEN_SAME)) ? in[ck.off_n1len] : in[ck.off_n1len + r];
+    const u8* n1 = in + ck.off_n1 + ((fl & RPQ_NAME1_SAME) ? 0u : b.n1off[i]);
+    for (u32 k = lane; k < l1; k += 32) out[k] = n1[k];
+    u32 w_at = l1;
+    u32 numlen = 0;
+    if (lane == 0) {
+        u8* p = s_num[w];
+        if (h.flags & RPQ_HAS_LANE) { p[numlen++] = ':'; numlen += put_dec(p + numlen, (fl & RPQ_LANE_SAME) ? in[ck.off_lane] : in[ck.off_lane + xy]); }
+        if (h.flags & RPQ_HAS_TILE) { const u32 k = (fl & RPQ_TILE_SAME) ? 0u : xy; p[numlen++] = ':'; numlen += put_dec(p + numlen, (u32)in[ck.off_tile + 2 * k] | ((u32)in[ck.off_tile + 2 * k + 1] << 8)); }
+        if (h.flags & RPQ_HAS_X) { p[numlen++] = ':'; numlen += put_dec(p + numlen, b.xs[ck.read_base + xy]); }
+        if (h.flags & RPQ_HAS_Y) { p[numlen++] = ':'; numlen += put_dec(p + numlen, b.ys[ck.read_base + xy]); }
+    }
+    numlen = __shfl_sync(0xffffffffu, numlen, 0);
+    __syncwarp();
+    for (u32 k = lane; k < numlen; k += 32) out[w_at + k] = s_num[w][k];
+    w_at += numlen;
+    if (h.flags & RPQ_HAS_NAME2) {
+        const u32 l2 = (fl & (RPQ_NAME2_SAME | RPQ_NAME2_LEN_SAME)) ? in[ck.off_n2len] : in[ck.off_n2len + r];
+        const u8* n2 = in + ck.off_n2 + ((fl & RPQ_NAME2_SAME) ? 0u : b.n2off[i]);
+        const bool subst = (fl & RPQ_NAME2_SAME) && il && odd && h.name2_diff_char != 0;
+        for (u32 k = lane; k < l2; k += 32) { u8 ch = n2[k]; if (subst && k == h.name2_diff_pos) ch = h.name2_diff_char; out[w_at + k] = ch; }
+        w_at += l2;
+    }
+    if (lane == 0) out[w_at] = '\n';
+    w_at += 1;
+
+    /* ---- sequence */
+    const u8* seqb = in + ck.off_seq;
+    const u8* plane = (h.flags & RPQ_DONT_ENCODE_QUAL) ? (in + ck.off_qual) : (b.plane + ck.plane_off);
+    const u32 plane_len = (h.flags & RPQ_DONT_ENCODE_QUAL) ? (ck.qual_size < ck.total_len ? ck.qual_size : ck.total_len) : ck.total_len;
+    const u32* nmap = b.nmap + ck.nmap_off;
+    const u32 so = b.seqoff[i], qo = b.qualoff[i];
+    int o = 0; u32 prev_rl = 0;
+    if (ov_on && odd) { o = (int)(signed char)in[ck.off_ov + (r >> 1)] - (int)h.overlap_shift; prev_rl = b.rlen[i - 1]; }
+    const bool rc = il && odd;
+    const bool npos_mode = (h.flags & RPQ_ENCODE_N_POS) != 0;
+    const u8 nq = (u8)h.n_base_qual;
+    const u32 unpacked = ck.seq_size * 4u < ck.total_len ? ck.seq_size * 4u : ck.total_len;   /* decoded bases; the rest of the buffer stays 'N' */
+    for (u32 jo = lane; jo < rl; jo += 32) {
+        const u32 j = rc ? rl - 1 - jo : jo;            /* position inside the read before the final reverse complement */
+        long long ci;
+        if (o == 0) ci = (long long)so + j;
+        else if (o > 0) ci = j < (u32)o ? (long long)so - o + j : (long long)so + j - o;
+        else { const u32 k = rl - (u32)(-o); ci = j < k ? (long long)so + j : (long long)so - prev_rl + (j - k); }
+        u8 base = 'N';
+        if (ci >= 0 && (u64)ci < unpacked) {
+            const u32 code = (seqb[ci >> 2] >> (2 * (ci & 3))) & 3u;
+            base = code == 0 ? 'G' : code == 1 ? 'A' : code == 2 ? 'T' : 'C';
+        }
+        if (npos_mode) { if (ci >= 0 && (u64)ci < ck.total_len && ((nmap[ci >> 5] >> (ci & 31)) & 1u)) base = 'N'; }
+        else { const u32 qp = qo + j; if (qp < plane_len ? plane[qp] == nq : h.major == nq) base = 'N'; }
+        out[w_at + jo] = rc ? complement_base(base) : base;
+    }
+    if (lane == 0) out[w_at + rl] = '\n';
+    w_at += rl + 1;
+
+    /* ---- strand */
+    const u32 ls = (fl & (RPQ_STRAND_SAME | RPQ_STRAND_LEN_SAME)) ? in[ck.off_slen] : in[ck.off_slen + r];
+    const u8* sp = in + ck.off_strand + ((fl & RPQ_STRAND_SAME) ? 0u : b.soff[i]);
+    for (u32 k = lane; k < ls; k += 32) out[w_at + k] = sp[k];
+    if (lane == 0) out[w_at + ls] = '\n';
+    w_at += ls + 1;
+
+    /* ---- quality */
+    for (u32 jo = lane; jo < rl; jo += 32) {
+        const u32 j = rc ? rl - 1 - jo : jo;
+        const u32 qp = qo + j;
+        out[w_at + jo] = qp < plane_len ? plane[qp] : h.major;
+    }
+    if (lane == 0) out[w_at + rl] = '\n';
+}
+
+}  // namespace rpq

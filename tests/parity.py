@@ -1,0 +1,68 @@
+"""Shared parity checks: the same assertions run against the CUDA library on a GPU (-m gpu) and against the
+emulation build of the same kernel sources on the CPU (tests/emu, kernel-logic coverage without a GPU)."""
+import hashlib
+import json
+import os
+
+from oracle import oracle as O
+from repaq_b200 import codec as K
+from tests import rfqparse
+from tests.conftest import ROOT, golden_rfq
+from tests.golden.cases import build_cases
+
+MAN = json.load(open(os.path.join(ROOT, "tests", "golden", "manifest.json")))
+CASES = {c["name"]: c for c in build_cases()}
+OK_CASES = sorted(n for n in MAN if not MAN[n].get("error"))
+ERR_CASES = sorted(n for n in MAN if MAN[n].get("error"))
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+def explain(got, exp):
+    try:
+        return "\n".join(rfqparse.diff(got, exp)[:10])
+    except Exception as e:  # pragma: no cover
+        return "unparsable output: %r" % (e,)
+
+
+def check_encode_golden(codec, name):
+    c = CASES[name]
+    got = K.compress(c["r1"], c["r2"], k=c["k"], interleaved=c["interleaved"], codec=codec)
+    exp = golden_rfq(name)
+    assert got == exp, explain(got, exp)
+
+
+def check_encode_error(codec, name):
+    import pytest
+    c = CASES[name]
+    with pytest.raises(K.RepaqError) as e:
+        K.compress(c["r1"], c["r2"], k=c["k"], interleaved=c["interleaved"], codec=codec)
+    assert "cannot be larger than 2M" in str(e.value)        # the reference's error_exit text (src/rfqcodec.cpp:1316)
+
+
+def check_decode_golden(codec, name):
+    m = MAN[name]
+    rfq = golden_rfq(name)
+    d = K.decompress(rfq, pe_out=False, codec=codec)
+    assert (len(d), sha(d)) == (m["dec_len"], m["dec_sha256"])
+    if "dec1_sha256" in m:
+        d1, d2 = K.decompress(rfq, pe_out=True, codec=codec)
+        assert (len(d1), sha(d1)) == (m["dec1_len"], m["dec1_sha256"])
+        assert (len(d2), sha(d2)) == (m["dec2_len"], m["dec2_sha256"])
+
+
+def check_against_oracle(codec, r1, r2=None, k=1000, interleaved=False, roundtrip=True):
+    """encode == oracle encode (bit-exact); decode(oracle rfq) == oracle decode; optionally decode restores the input"""
+    r1b = bytes(r1)
+    r2b = None if r2 is None else bytes(r2)
+    exp = O.compress(r1b, r2b, chunk_bases=max(100, k) * 1000, interleaved=interleaved)
+    got = K.compress(r1b, r2b, k=k, interleaved=interleaved, codec=codec)
+    assert got == exp, explain(got, exp)
+    pe = r2 is not None
+    dec = K.decompress(exp, pe_out=pe, codec=codec)
+    assert dec == O.decompress(exp, pe_out=pe)
+    if roundtrip:
+        assert dec == ((r1b, r2b) if pe else r1b)
+    return len(exp)

@@ -210,3 +210,57 @@ int fqgen_rows(uint64_t seed, int shape, uint32_t flags, uint64_t first_row, uin
     if (len2) *len2 = out2 ? (size_t)(p2 - out2) : 0;
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Parallel front end (OpenMP): rows [first_row, first_row+n_rows) generated block-wise by all cores into scratch
+ * buffers, then packed into out1/out2 in row order.  Output bytes are identical to fqgen_rows().
+ */
+#include <stdlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int fqgen_rows_mt(uint64_t seed, int shape, uint32_t flags, uint64_t first_row, uint64_t n_rows,
+                  char* out1, size_t cap1, size_t* len1, char* out2, size_t cap2, size_t* len2) {
+    const uint64_t BLK = 32;
+    const uint64_t nblk = (n_rows + BLK - 1) / BLK;
+    const size_t blk_cap = fqgen_max_record_bytes(shape, flags) * ROW_READS * BLK + 64;
+    char** b1 = (char**)calloc(nblk, sizeof(char*)); char** b2 = (char**)calloc(nblk, sizeof(char*));
+    size_t* n1 = (size_t*)calloc(nblk + 1, sizeof(size_t)); size_t* n2 = (size_t*)calloc(nblk + 1, sizeof(size_t));
+    int rc = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long long k = 0; k < (long long)nblk; k++) {
+        uint64_t r0 = first_row + (uint64_t)k * BLK, nr = n_rows - (uint64_t)k * BLK < BLK ? n_rows - (uint64_t)k * BLK : BLK;
+        b1[k] = (char*)malloc(blk_cap); if (out2) b2[k] = (char*)malloc(blk_cap);
+        size_t a = 0, b = 0;
+        if (fqgen_rows(seed, shape, flags, r0, nr, b1[k], blk_cap, &a, out2 ? b2[k] : NULL, out2 ? blk_cap : 0, &b)) {
+#pragma omp atomic write
+            rc = -1;
+        }
+        n1[k] = a; n2[k] = b;
+    }
+    size_t t1 = 0, t2 = 0;
+    for (uint64_t k = 0; k < nblk; k++) { size_t a = n1[k], b = n2[k]; n1[k] = t1; n2[k] = t2; t1 += a; t2 += b; }
+    n1[nblk] = t1; n2[nblk] = t2;
+    if (t1 > cap1 || (out2 && t2 > cap2)) rc = -1;
+    if (!rc) {
+#pragma omp parallel for schedule(dynamic, 1)
+        for (long long k = 0; k < (long long)nblk; k++) {
+            memcpy(out1 + n1[k], b1[k], n1[k + 1] - n1[k]);
+            if (out2) memcpy(out2 + n2[k], b2[k], n2[k + 1] - n2[k]);
+        }
+    }
+    for (uint64_t k = 0; k < nblk; k++) { free(b1[k]); free(b2[k]); }
+    free(b1); free(b2);
+    *len1 = t1; if (len2) *len2 = out2 ? t2 : 0;
+    free(n1); free(n2);
+    return rc;
+}
+
+void fqgen_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
