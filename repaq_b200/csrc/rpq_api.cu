@@ -290,9 +290,6 @@ extern "C" int rpq_encode(rpq_ctx* c, const rpq_encode_in* in, rpq_encode_out* o
     if (int rc = read_back(c, c->ustats.p, &us)) return fail(c, rc, "CUDA failure in k_unit_lengths");
     if (us.first_empty < n_units) n_units = us.first_empty;       /* the reference stops at the first record with an empty line */
     if (n_units == 0) { rt_event_record(&c->ev[7], c->stream); rt_stream_sync(c->stream); return RPQ_OK; }
-    if (us.first_qual_len < n_units) return fail(c, RPQ_ERR_FASTQ, "quality and sequence lengths differ in record " + std::to_string(us.first_qual_len));
-    if (us.first_name_len < n_units) return fail(c, RPQ_ERR_FASTQ, "name or strand line longer than 255 bytes in record " + std::to_string(us.first_name_len));
-    if (us.first_read_len < n_units) return fail(c, RPQ_ERR_FASTQ, "read longer than 65535 bases in record " + std::to_string(us.first_read_len));
     const u32 uniform = (us.min_bases == us.max_bases) ? us.min_bases : 0;
     if (!uniform) rt_inclusive_sum_u32_u64(c->unit_bases.as<u32>(), c->prefix.as<u64>(), n_units, c->scan_tmp.p, c->scan_tmp.cap, c->stream);
     const size_t chunk_cap = (size_t)((lens[0] + lens[1]) / in->chunk_bases) + 4;
@@ -302,6 +299,10 @@ extern "C" int rpq_encode(rpq_ctx* c, const rpq_encode_in* in, rpq_encode_out* o
     if (int rc = read_back(c, c->ustats.p, &us)) return fail(c, rc, "CUDA failure in k_cut");
     const u32 n_chunks = us.n_chunks;
     const u32 n_reads = us.units_in_chunks * per;
+    /* only records that end up in a chunk are validated (a batch that is not final may end inside a record) */
+    if (us.first_qual_len < us.units_in_chunks) return fail(c, RPQ_ERR_FASTQ, "quality and sequence lengths differ in record " + std::to_string(us.first_qual_len));
+    if (us.first_name_len < us.units_in_chunks) return fail(c, RPQ_ERR_FASTQ, "name or strand line longer than 255 bytes in record " + std::to_string(us.first_name_len));
+    if (us.first_read_len < us.units_in_chunks) return fail(c, RPQ_ERR_FASTQ, "read longer than 65535 bases in record " + std::to_string(us.first_read_len));
     if (n_chunks == 0) { rt_event_record(&c->ev[7], c->stream); rt_stream_sync(c->stream); return RPQ_OK; }
     if (n_chunks > chunk_cap) return fail(c, RPQ_ERR_FASTQ, "internal: chunk table overflow");
     b.n_reads = n_reads; b.n_chunks = n_chunks; b.chunk_first = c->chunk_first.as<u32>();
