@@ -10,7 +10,10 @@
 #include "rpq_common.cuh"
 #include "rpq_index.cuh"
 #include "rpq_encode.cuh"
+#include "rpq_streams2.cuh"
+#include "rpq_meta2.cuh"
 #include "rpq_decode.cuh"
+#include "rpq_decode2.cuh"
 #include "rpq_host.h"
 
 using namespace rpq;
@@ -32,9 +35,10 @@ struct rpq_ctx {
     bool have_hdr = false;
     HeaderDev hd;
     /* grow-only device buffers */
-    DevBuf text[2], nl[2], tile_state, counters, rlen, unit_bases, prefix, scan_tmp, ustats, chunk_first, chunks, meta, meta0, ov,
+    DevBuf loc, pk, pk_rc, text[2], nl[2], tile_state, counters, rlen, unit_bases, prefix, scan_tmp, ustats, chunk_first, chunks, meta, meta0, ov,
         seqoff, qualoff, n1off, n2off, soff, errbits, tmpx, tmpy, span_first[2], span_chunk[2], dir[2], slots[2], span_slot[2], misc, out,
-        d_in, d_desc, d_tmp[8], out2;
+        d_in, d_desc, d_tmp[8], d_tmp2, out2;
+    bool force_v1 = false;                 /* RPQ_DEBUG_FORCE_V1=1: take the long-read fallback kernels (test coverage) */
     void* pinned_small = nullptr;          /* 64 KiB scratch for scalar read-backs */
     DevBuf host_out, host_out2;            /* pinned host buffers for results */
     std::vector<rpq_chunk_info> infos;
@@ -129,8 +133,11 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     for (auto& e : c->ev) rt_event_create(&e);
     memset(&c->stats, 0, sizeof c->stats);
     memset(&c->hdr, 0, sizeof c->hdr);
+    { const char* e = getenv("RPQ_DEBUG_FORCE_V1"); c->force_v1 = e && e[0] == '1'; }
 #ifndef RPQ_EMU
-    cudaFuncSetAttribute(k_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_streams2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_meta2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_dec_format2, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
 #endif
     *out = c;
     return RPQ_OK;
@@ -140,11 +147,11 @@ extern "C" void rpq_destroy(rpq_ctx* c) {
     if (!c) return;
     rt_set_device(c->device);
     rt_stream_sync(c->stream);
-    DevBuf* all[] = {&c->text[0], &c->text[1], &c->nl[0], &c->nl[1], &c->tile_state, &c->counters, &c->rlen, &c->unit_bases, &c->prefix, &c->scan_tmp,
+    DevBuf* all[] = {&c->loc, &c->pk, &c->pk_rc, &c->text[0], &c->text[1], &c->nl[0], &c->nl[1], &c->tile_state, &c->counters, &c->rlen, &c->unit_bases, &c->prefix, &c->scan_tmp,
                      &c->ustats, &c->chunk_first, &c->chunks, &c->meta, &c->meta0, &c->ov, &c->seqoff, &c->qualoff, &c->n1off, &c->n2off, &c->soff,
                      &c->errbits, &c->tmpx, &c->tmpy, &c->span_first[0], &c->span_first[1], &c->span_chunk[0], &c->span_chunk[1], &c->dir[0], &c->dir[1],
                      &c->slots[0], &c->slots[1], &c->span_slot[0], &c->span_slot[1], &c->misc, &c->out, &c->d_in, &c->d_desc, &c->out2,
-                     &c->d_tmp[0], &c->d_tmp[1], &c->d_tmp[2], &c->d_tmp[3], &c->d_tmp[4], &c->d_tmp[5], &c->d_tmp[6], &c->d_tmp[7]};
+                     &c->d_tmp2, &c->d_tmp[0], &c->d_tmp[1], &c->d_tmp[2], &c->d_tmp[3], &c->d_tmp[4], &c->d_tmp[5], &c->d_tmp[6], &c->d_tmp[7]};
     for (DevBuf* b : all) rt_free_device(b->p);
     rt_free_pinned(c->pinned_small);
     rt_free_pinned(c->host_out.p); rt_free_pinned(c->host_out2.p);
@@ -278,9 +285,10 @@ extern "C" int rpq_encode(rpq_ctx* c, const rpq_encode_in* in, rpq_encode_out* o
     if (!ensure(c, c->rlen, 4 * n_reads_max) || !ensure(c, c->unit_bases, 4 * (size_t)n_units) || !ensure(c, c->prefix, 8 * (size_t)n_units) ||
         !ensure(c, c->ustats, sizeof(UnitStats)) || !ensure(c, c->scan_tmp, rt_scan_tmp_bytes(n_units)) || !ensure(c, c->errbits, 64))
         return fail(c, RPQ_ERR_NOMEM, "out of device memory (lengths)");
-    b.rlen = c->rlen.as<u32>(); b.err = c->errbits.as<u32>();
+    if (!ensure(c, c->loc, 16 * n_reads_max)) return fail(c, RPQ_ERR_NOMEM, "out of device memory (record index)");
+    b.rlen = c->rlen.as<u32>(); b.err = c->errbits.as<u32>(); b.loc = c->loc.as<uint4>();
     {
-        UnitStats init; memset(&init, 0xFF, sizeof init); init.max_bases = 0; init.max_read = 0; init.n_chunks = 0; init.units_in_chunks = 0;
+        UnitStats init; memset(&init, 0xFF, sizeof init); init.max_bases = 0; init.max_read = 0; init.max_head = 0; init.n_chunks = 0; init.units_in_chunks = 0;
         memcpy(c->pinned_small, &init, sizeof init);
         rt_memcpy_h2d(c->ustats.p, c->pinned_small, sizeof init, c->stream);
         rt_memset(c->errbits.p, 0, 64, c->stream);
@@ -319,10 +327,28 @@ extern "C" int rpq_encode(rpq_ctx* c, const rpq_encode_in* in, rpq_encode_out* o
     b.seqoff = c->seqoff.as<u32>(); b.qualoff = c->qualoff.as<u32>(); b.n1off = c->n1off.as<u32>(); b.n2off = c->n2off.as<u32>(); b.soff = c->soff.as<u32>();
     LAUNCH(c, k_init_chunks, (n_chunks + 255) / 256, 256, 0, b);
     LAUNCH(c, k_meta0, (n_chunks + META_WARPS - 1) / META_WARPS, 32 * META_WARPS, 0, b);
+    /* v2 path (thread per read on staged text) whenever a CTA's record heads fit in shared memory; very long reads
+     * fall back to the warp-per-pair kernels that read the text directly */
+    Meta2Cfg m2; memset(&m2, 0, sizeof m2);
+    bool v2 = false;
     {
-        const int use_smem = pe && us.max_read <= (u32)META_SEQ_SMEM;     /* longer reads: the overlap search reads the text directly */
         const u32 units = us.units_in_chunks;
-        LAUNCH(c, k_meta, (units + META_WARPS - 1) / META_WARPS, 32 * META_WARPS, use_smem ? META_WARPS * 2 * META_SEQ_SMEM : 0, b, hd, units, use_smem);
+        m2.slot_words = ((us.max_head + 6u) / 4u + 1u) | 1u;
+        m2.pkw = ((us.max_read + 15u) / 16u + 1u) | 1u;
+        size_t smem2 = 0;
+        for (u32 P : {128u, 64u, 32u}) {
+            smem2 = 4ull * P * per * m2.slot_words + 4ull * P * per * m2.pkw + 4ull * P * m2.pkw;
+            if (smem2 <= 160u * 1024u && !c->force_v1) { m2.units_per_cta = P; v2 = true; break; }
+        }
+        if (v2) {
+            if (!ensure(c, c->pk, 4ull * n_reads * m2.pkw + 64) || !ensure(c, c->pk_rc, 4ull * (n_reads / 2 + 1) * m2.pkw + 64))
+                return fail(c, RPQ_ERR_NOMEM, "out of device memory (packed reads)");
+            b.pk = c->pk.as<u32>(); b.pk_rc = c->pk_rc.as<u32>(); b.pkw = m2.pkw;
+            LAUNCH(c, k_meta2, (units + m2.units_per_cta - 1) / m2.units_per_cta, m2.units_per_cta, smem2, b, hd, units, m2);
+        } else {
+            const int use_smem = pe && us.max_read <= (u32)META_SEQ_SMEM;     /* longer reads: the overlap search reads the text directly */
+            LAUNCH(c, k_meta, (units + META_WARPS - 1) / META_WARPS, 32 * META_WARPS, use_smem ? META_WARPS * 2 * META_SEQ_SMEM : 0, b, hd, units, use_smem);
+        }
     }
     LAUNCH(c, k_chunk_finish, n_chunks, FIN_THREADS, 0, b, hd);
     if (hd.flags & (RPQ_HAS_X | RPQ_HAS_Y)) {
@@ -358,8 +384,8 @@ extern "C" int rpq_encode(rpq_ctx* c, const rpq_encode_in* in, rpq_encode_out* o
             j.slot_cursor = c->misc.as<u64>() + 2 * k; j.overflow = c->misc.as<u32>() + 16; j.span_slot = c->span_slot[k].as<u64>();
             j.n_spans = c->misc.as<u32>() + 20 + k;
             LAUNCH(c, k_span_plan, 1, 256, 0, b, (u32)k, c->span_first[k].as<u32>(), c->span_chunk[k].as<u32>(), span_cap, c->misc.as<u32>() + 20 + k);
-            const size_t smem = ST_SPAN + 2 * ST_HALO + 4 * sizeof(u32) * (size_t)j.nstreams * ST_NSEG;
-            LAUNCH(c, k_streams, span_cap, ST_THREADS, smem, b, hd, j, c->span_chunk[k].as<u32>());
+            const size_t smem = ST_SPAN + 2 * ST_HALO + (size_t)j.nstreams * S2_THREADS * (sizeof(u32) + 3 * sizeof(u16));
+            LAUNCH(c, k_streams2, span_cap, S2_THREADS, smem, b, hd, j, c->span_chunk[k].as<u32>());
         }
         u32 ovf = 0;
         if (have_q || have_n) { if (int rc = read_back(c, c->misc.as<u32>() + 16, &ovf)) return fail(c, rc, "CUDA failure in k_streams"); }
@@ -380,7 +406,12 @@ extern "C" int rpq_encode(rpq_ctx* c, const rpq_encode_in* in, rpq_encode_out* o
 
     /* ---- emit */
     LAUNCH(c, k_head, (n_chunks + 3) / 4, 128, 0, b, hd, d_out, c->tmpx.as<u8>(), c->tmpy.as<u8>(), *in);
-    LAUNCH(c, k_emit, (n_reads + EMIT_WARPS - 1) / EMIT_WARPS, 32 * EMIT_WARPS, 0, b, hd, d_out);
+    if (v2) {
+        LAUNCH(c, k_emit2, (n_reads + 255) / 256, 256, 0, b, hd, d_out);
+        if (errbits & INFOBIT_NEED_NAMES) LAUNCH(c, k_emit_names, (n_reads + 7) / 8, 256, 0, b, hd, d_out);
+    } else {
+        LAUNCH(c, k_emit, (n_reads + EMIT_WARPS - 1) / EMIT_WARPS, 32 * EMIT_WARPS, 0, b, hd, d_out);
+    }
     if (have_q) LAUNCH(c, k_gather, span_cap, 256, 0, b, jobs[0], c->span_chunk[0].as<u32>(), d_out, 0);
     else LAUNCH(c, k_raw_qual, (n_reads + EMIT_WARPS - 1) / EMIT_WARPS, 32 * EMIT_WARPS, 0, b, d_out);
     if (have_n) LAUNCH(c, k_gather, span_cap, 256, 0, b, jobs[1], c->span_chunk[1].as<u32>(), d_out, 1);

@@ -46,6 +46,7 @@ constexpr u32 ERRBIT_COORD = 1u << 3;          /* X/Y >= 2^21 */
 constexpr u32 ERRBIT_READ_LEN = 1u << 4;       /* read longer than 65535 (Q1) */
 constexpr u32 ERRBIT_INTERNAL = 1u << 5;
 constexpr u32 ERRBIT_RFQ = 1u << 6;            /* malformed stream on decode */
+constexpr u32 INFOBIT_NEED_NAMES = 1u << 16;   /* not an error: some chunk stores per-read name1 / name2 / strand bytes */
 
 /* one FASTQ image in HBM + its line index */
 struct TextDev {
@@ -108,6 +109,10 @@ struct EncBatchDev {
     u32 n_chunks;
     const u32* chunk_first;   /* [n_chunks+1] */
     u32* rlen;            /* [n_reads] */
+    uint4* loc;           /* [n_reads] text offsets of the read's 4 line starts: name, sequence, strand, quality */
+    u32* pk;              /* [n_reads][pkw] 2-bit packed bases of every read as stored (R2: forward); written by k_meta2 */
+    u32* pk_rc;           /* [n_reads/2][pkw] 2-bit packed reverse complement of every R2 */
+    u32 pkw;              /* words per read in pk / pk_rc */
     ReadMeta* meta;       /* [n_reads] */
     ReadMeta* meta0;      /* [n_chunks] FastqMeta of each chunk's first read */
     short* ov;            /* [n_reads/2] clamped overlap of each pair (valid when the chunk ends up interleaved) */

@@ -38,12 +38,14 @@ struct DecBatchDev {
     u32 split_pairs;
     u32* rlen; u32* qualoff; u32* seqoff; u32* n1off; u32* n2off; u32* soff;
     u64* outoff;             /* per read: offset inside its output stream */
+    u32* olen;               /* per read: bytes of its record text */
+    u32* read_chunk;         /* per read: its chunk */
     u32* xs; u32* ys;        /* [n_reads] decoded coordinates, indexed read_base + xy */
     u8* plane;               /* quality plane, all chunks */
     u32* nmap;               /* N bitmap over compacted positions */
     u8* out[2];
     u32* err;
-    u64* totals;             /* [0] plane bytes, [1] nmap words, [2] out1 bytes, [3] out2 bytes */
+    u64* totals;             /* [0] plane bytes, [1] nmap words, [2] out1 bytes, [3] out2 bytes, [4] = {u32 longest record text, u32 longest read} */
 };
 
 __device__ __forceinline__ u32 ld32(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
@@ -149,6 +151,7 @@ __global__ void __launch_bounds__(DR_THREADS) k_dec_reads(DecBatchDev b, HeaderD
     const bool il = (fl & RPQ_PE_INTERLEAVED) != 0;
     const bool ov_on = il && (h.flags & RPQ_ENCODE_PE_BY_OVERLAP);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u32 maxrec = 0, maxrl = 0;
     if (tid == 0) { Scan7 z; for (int k = 0; k < 7; k++) z.v[k] = 0; s_carry = z; }
     __syncthreads();
     for (u32 base = 0; base < n; base += DR_THREADS) {
@@ -174,6 +177,10 @@ __global__ void __launch_bounds__(DR_THREADS) k_dec_reads(DecBatchDev b, HeaderD
             const u32 stream = b.split_pairs ? (r & 1u) : 0u;
             v.v[5 + stream] = text;
             b.rlen[ck.read_base + r] = rl;
+            b.olen[ck.read_base + r] = text;
+            b.read_chunk[ck.read_base + r] = c;
+            if (text > maxrec) maxrec = text;
+            if (rl > maxrl) maxrl = rl;
         }
         Scan7 inc = v;
 #pragma unroll
@@ -200,6 +207,8 @@ __global__ void __launch_bounds__(DR_THREADS) k_dec_reads(DecBatchDev b, HeaderD
         __syncthreads();
     }
     if (tid == 0) { ck.total_len = s_carry.v[0]; ck.seq_kept = s_carry.v[1]; ck.out_bytes[0] = s_carry.v[5]; ck.out_bytes[1] = s_carry.v[6]; }
+    maxrec = warp_max(maxrec); maxrl = warp_max(maxrl);
+    if (lane == 0) { atomicMax(reinterpret_cast<u32*>(b.totals + 4), maxrec); atomicMax(reinterpret_cast<u32*>(b.totals + 4) + 1, maxrl); }
 }
 
 /* prefix over chunks: plane, N bitmap and output offsets; totals for the host */

@@ -542,11 +542,11 @@ __device__ inline void stage_positions(const EncBatchDev& b, const HeaderDev& h,
         const bool rev = ck.interleaved && (rel & 1u);
         const u32 j0 = lo > off ? lo - off : 0, j1 = (off + n < hi ? off + n : hi) - off;
         if (mode == 0) {
-            const u8* q = t.text + line_start(t, 4 * rec + 3);
+            const u8* q = t.text + b.loc[i].w;
             if (rev) for (u32 j = j0 + lane; j < j1; j += 32) sm[off + j - lo] = q[rl - 1 - j];
             else for (u32 j = j0 + lane; j < j1; j += 32) sm[off + j - lo] = q[j];
         } else {
-            const u8* s = t.text + line_start(t, 4 * rec + 1);
+            const u8* s = t.text + b.loc[i].y;
             if (rev) { const int o = b.ov[i >> 1]; const u32 sh = o > 0 ? (u32)o : 0u; for (u32 j = j0 + lane; j < j1; j += 32) sm[off + j - lo] = complement_base(s[rl - 1 - (j + sh)]); }
             else for (u32 j = j0 + lane; j < j1; j += 32) sm[off + j - lo] = s[j];
         }
@@ -801,6 +801,8 @@ __global__ void __launch_bounds__(LAY_THREADS) k_layout(EncBatchDev b, HeaderDev
     }
     if (tid != 0) return;
     ck.qual_size = qual_size; ck.npos_size = npos_size;
+    if (!(ck.flags & RPQ_NAME1_SAME) || ((h.flags & RPQ_HAS_NAME2) && !(ck.flags & RPQ_NAME2_SAME)) || !(ck.flags & RPQ_STRAND_SAME))
+        atomicOr(b.err, INFOBIT_NEED_NAMES);
     /* column offsets in RfqChunk::write order (src/rfqchunk.cpp:230-312) */
     u32 o = 18u + ((h.flags & RPQ_ENCODE_N_POS) ? 4u : 0u);
     ck.off_readlen = o; o += ck.readlen_size;

@@ -14,9 +14,11 @@
 namespace rpq {
 
 constexpr int IDX_THREADS = 256;
-constexpr int IDX_CHUNKS = 4;                                /* 16-byte pieces per lane */
-constexpr int IDX_WARP_BYTES = 32 * 16 * IDX_CHUNKS;         /* 2 KiB per warp */
-constexpr int IDX_TILE = (IDX_THREADS / 32) * IDX_WARP_BYTES; /* 16 KiB per CTA */
+constexpr int IDX_CHUNKS = 4;                                /* 16-byte pieces per lane and round */
+constexpr int IDX_ROUNDS = 4;                                /* rounds per CTA */
+constexpr int IDX_WARP_BYTES = 32 * 16 * IDX_CHUNKS;         /* 2 KiB per warp and round */
+constexpr int IDX_ROUND_BYTES = (IDX_THREADS / 32) * IDX_WARP_BYTES;   /* 16 KiB */
+constexpr int IDX_TILE = IDX_ROUNDS * IDX_ROUND_BYTES;       /* 64 KiB per CTA */
 
 struct IndexCounters {
     u32 ticket;     /* dynamic tile id */
@@ -40,89 +42,115 @@ __device__ __forceinline__ u32 nl_mask16(uint4 v, u8 c) {
     return pack(m0) | (pack(m1) << 4) | (pack(m2) << 8) | (pack(m3) << 12);
 }
 
-/* One pass over the text: positions of every '\n', in order, via a chained (decoupled look-back) scan over 16 KiB tiles. */
+/*
+ * One pass over the text: positions of every '\n', in order.  A CTA takes a 64 KiB tile (4 rounds of 16 KiB, uint4 loads),
+ * keeps the newline masks in registers, publishes its count and gets its rank base from a chained scan over tiles with a
+ * warp-wide decoupled look-back (32 predecessors per probe), then writes the positions.
+ */
 __global__ void __launch_bounds__(IDX_THREADS) k_index_lines(const u8* __restrict__ text, u64 len, u32* __restrict__ nl, u32 nl_cap,
                                                             u64* tile_state, IndexCounters* ctr) {
     __shared__ u32 s_tile;
-    __shared__ u32 s_warp_tot[IDX_THREADS / 32];
+    __shared__ u32 s_tot[IDX_ROUNDS][IDX_THREADS / 32];
     __shared__ u32 s_prefix;
     __shared__ u32 s_cr, s_crlf;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { s_tile = atomicAdd(&ctr->ticket, 1u); s_cr = 0; s_crlf = 0; }
     __syncthreads();
     const u32 tile = s_tile;
-    const u64 wbase = (u64)tile * IDX_TILE + (u64)warp * IDX_WARP_BYTES;
+    const u64 tbase = (u64)tile * IDX_TILE;
 
-    u32 nlm[IDX_CHUNKS];
-    u32 cnt[IDX_CHUNKS];
+    u32 nlm[IDX_ROUNDS][IDX_CHUNKS / 2];       /* two 16-bit masks per register */
+    u32 exc[IDX_ROUNDS][IDX_CHUNKS / 2];       /* two 16-bit in-warp exclusive offsets per register */
     u32 ncr = 0, ncrlf = 0;
 #pragma unroll
-    for (int k = 0; k < IDX_CHUNKS; k++) {
-        const u64 p = wbase + (u64)k * 512 + (u64)lane * 16;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        u32 valid = 0xFFFFu;
-        if (p + 16 <= len) v = *reinterpret_cast<const uint4*>(text + p);
-        else if (p < len) {
-            u32 w[4] = {0, 0, 0, 0};
-            const int n = (int)(len - p);
-            for (int i = 0; i < n; i++) w[i >> 2] |= (u32)text[p + i] << (8 * (i & 3));
-            v = make_uint4(w[0], w[1], w[2], w[3]);
-            valid = (1u << n) - 1u;
-        } else valid = 0;
-        const u32 m = nl_mask16(v, '\n') & valid;
-        const u32 c = nl_mask16(v, '\r') & valid;
-        u32 pair = m & (c << 1);
-        if ((m & 1u) && p > 0 && text[p - 1] == '\r') pair |= 1u;
-        nlm[k] = m; cnt[k] = (u32)__popc(m);
-        ncr += (u32)__popc(c); ncrlf += (u32)__popc(pair);
+    for (int r = 0; r < IDX_ROUNDS; r++) {
+        const u64 wbase = tbase + (u64)r * IDX_ROUND_BYTES + (u64)warp * IDX_WARP_BYTES;
+        u32 wtot = 0;
+#pragma unroll
+        for (int k = 0; k < IDX_CHUNKS; k++) {
+            const u64 p = wbase + (u64)k * 512 + (u64)lane * 16;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            u32 valid = 0xFFFFu;
+            if (p + 16 <= len) v = *reinterpret_cast<const uint4*>(text + p);
+            else if (p < len) {
+                u32 w[4] = {0, 0, 0, 0};
+                const int n = (int)(len - p);
+                for (int i = 0; i < n; i++) w[i >> 2] |= (u32)text[p + i] << (8 * (i & 3));
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+                valid = (1u << n) - 1u;
+            } else valid = 0;
+            const u32 m = nl_mask16(v, '\n') & valid;
+            const u32 c = nl_mask16(v, '\r') & valid;
+            u32 pair = m & (c << 1);
+            if ((m & 1u) && p > 0 && text[p - 1] == '\r') pair |= 1u;
+            ncr += (u32)__popc(c); ncrlf += (u32)__popc(pair);
+            u32 t; const u32 ex = wtot + warp_excl_scan((u32)__popc(m), lane, t); wtot += t;
+            if (k & 1) { nlm[r][k >> 1] |= m << 16; exc[r][k >> 1] |= ex << 16; } else { nlm[r][k >> 1] = m; exc[r][k >> 1] = ex; }
+        }
+        if (lane == 0) s_tot[r][warp] = wtot;
     }
-    /* order inside the warp's 2 KiB is (k, lane) */
-    u32 excl[IDX_CHUNKS];
-    u32 wtot = 0;
-#pragma unroll
-    for (int k = 0; k < IDX_CHUNKS; k++) { u32 t; excl[k] = wtot + warp_excl_scan(cnt[k], lane, t); wtot += t; }
     ncr = warp_sum(ncr); ncrlf = warp_sum(ncrlf);
-    if (lane == 0) { s_warp_tot[warp] = wtot; if (ncr) atomicAdd(&s_cr, ncr); if (ncrlf) atomicAdd(&s_crlf, ncrlf); }
+    if (lane == 0) { if (ncr) atomicAdd(&s_cr, ncr); if (ncrlf) atomicAdd(&s_crlf, ncrlf); }
     __syncthreads();
-    u32 wpre = 0, btot = 0;
+    u32 btot = 0;
 #pragma unroll
-    for (int w = 0; w < IDX_THREADS / 32; w++) { u32 t = s_warp_tot[w]; if (w < warp) wpre += t; btot += t; }
+    for (int r = 0; r < IDX_ROUNDS; r++)
+#pragma unroll
+        for (int w = 0; w < IDX_THREADS / 32; w++) btot += s_tot[r][w];
 
-    if (tid == 0) {
+    if (warp == 0) {
         volatile u64* st = tile_state;
         u32 prefix = 0;
         if (tile > 0) {
-            st[tile] = TS_AGG | btot;
-            __threadfence();
-            int j = (int)tile - 1;
+            if (lane == 0) { st[tile] = TS_AGG | btot; __threadfence(); }
+            int j = (int)tile - 1;                       /* newest predecessor not yet accounted for */
             for (;;) {
-                u64 s = st[j];
-                if ((s & TS_MASK) == 0) { RPQ_SPIN_HINT(); continue; }
-                prefix += (u32)s;
-                if ((s & TS_MASK) == TS_PREFIX) break;
-                j--;
+                const int idx = j - lane;
+                u64 s = idx >= 0 ? st[idx] : TS_PREFIX;   /* before tile 0: an empty prefix */
+                const u32 unset = __ballot_sync(0xffffffffu, (s & TS_MASK) == 0);
+                const u32 pre = __ballot_sync(0xffffffffu, (s & TS_MASK) == TS_PREFIX);
+                /* usable lanes: those before the first unset one, up to and including the first prefix */
+                const int first_unset = unset ? __ffs((int)unset) - 1 : 32;
+                const int first_pre = pre ? __ffs((int)pre) - 1 : 32;
+                const int upto = first_pre < first_unset ? first_pre + 1 : first_unset;   /* lanes [0, upto) are summed */
+                u32 v = lane < upto ? (u32)s : 0u;
+                prefix += warp_sum(v);
+                if (first_pre < first_unset) break;
+                j -= upto;
+                if (upto == 0) RPQ_SPIN_HINT();
             }
         }
-        __threadfence();
-        st[tile] = TS_PREFIX | (u64)(prefix + btot);
-        s_prefix = prefix;
-        if (s_cr) atomicAdd(&ctr->n_cr, s_cr);
-        if (s_crlf) atomicAdd(&ctr->n_crlf, s_crlf);
-        if ((u64)(tile + 1) * IDX_TILE >= len) ctr->n_nl = prefix + btot;     /* the last tile knows the total */
+        if (lane == 0) {
+            __threadfence();
+            st[tile] = TS_PREFIX | (u64)(prefix + btot);
+            s_prefix = prefix;
+            if (s_cr) atomicAdd(&ctr->n_cr, s_cr);
+            if (s_crlf) atomicAdd(&ctr->n_crlf, s_crlf);
+            if ((u64)(tile + 1) * IDX_TILE >= len) ctr->n_nl = prefix + btot;     /* the last tile knows the total */
+        }
     }
     __syncthreads();
-    const u32 base = s_prefix + wpre;
+    u32 base = s_prefix;
 #pragma unroll
-    for (int k = 0; k < IDX_CHUNKS; k++) {
-        u32 m = nlm[k];
-        u32 o = base + excl[k];
-        const u32 p = (u32)(wbase + (u64)k * 512 + (u64)lane * 16);
-        while (m) {
-            const int b = __ffs((int)m) - 1;
-            m &= m - 1;
-            if (o < nl_cap) nl[o] = p + (u32)b;
-            o++;
+    for (int r = 0; r < IDX_ROUNDS; r++) {
+        u32 wpre = 0;
+#pragma unroll
+        for (int w = 0; w < IDX_THREADS / 32; w++) { const u32 t = s_tot[r][w]; if (w < warp) wpre += t; }
+        const u64 wbase = tbase + (u64)r * IDX_ROUND_BYTES + (u64)warp * IDX_WARP_BYTES;
+#pragma unroll
+        for (int k = 0; k < IDX_CHUNKS; k++) {
+            u32 m = (nlm[r][k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+            u32 o = base + wpre + ((exc[r][k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
+            const u32 p = (u32)(wbase + (u64)k * 512 + (u64)lane * 16);
+            while (m) {
+                const int bb = __ffs((int)m) - 1;
+                m &= m - 1;
+                if (o < nl_cap) nl[o] = p + (u32)bb;
+                o++;
+            }
         }
+#pragma unroll
+        for (int w = 0; w < IDX_THREADS / 32; w++) base += s_tot[r][w];
     }
 }
 
@@ -148,6 +176,7 @@ struct UnitStats {
     u32 first_read_len;   /* first unit with a read > 65535 bases */
     u32 min_bases, max_bases;
     u32 max_read;         /* longest single read */
+    u32 max_head;         /* most bytes from the start of a name line to the start of the quality line */
     u32 n_chunks;         /* written by k_cut */
     u32 units_in_chunks;  /* units covered by the emitted chunks */
 };
@@ -158,7 +187,7 @@ __global__ void k_unit_lengths(EncBatchDev b, u32 n_units, u32* __restrict__ rle
     const u32 per = b.is_pe ? 2u : 1u;
     u32 bases = 0;
     bool empty = false, badq = false, badn = false, badl = false;
-    u32 longest = 0;
+    u32 longest = 0, head = 0;
     for (u32 k = 0; k < per; k++) {
         const u32 i = u * per + k;
         u32 f, rec; read_locus(b, i, f, rec);
@@ -171,6 +200,12 @@ __global__ void k_unit_lengths(EncBatchDev b, u32 n_units, u32* __restrict__ rle
         if (ln[0] > 255 || ln[2] > 255) badn = true;
         if (ln[1] > 65535) badl = true;
         rlen[i] = ln[1];
+        {
+            uint4 lc;
+            lc.x = line_start(t, 4 * rec); lc.y = line_start(t, 4 * rec + 1); lc.z = line_start(t, 4 * rec + 2); lc.w = line_start(t, 4 * rec + 3);
+            b.loc[i] = lc;
+            head = lc.w - lc.x > head ? lc.w - lc.x : head;
+        }
         longest = ln[1] > longest ? ln[1] : longest;
         bases += ln[1];
     }
@@ -182,6 +217,7 @@ __global__ void k_unit_lengths(EncBatchDev b, u32 n_units, u32* __restrict__ rle
     atomicMin(&st->min_bases, bases);
     atomicMax(&st->max_bases, bases);
     atomicMax(&st->max_read, longest);
+    atomicMax(&st->max_head, head);
 }
 
 /*

