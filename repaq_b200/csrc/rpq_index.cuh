@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(IDX_THREADS) k_index_lines(const u8* __restric
             int j = (int)tile - 1;                       /* newest predecessor not yet accounted for */
             for (;;) {
                 const int idx = j - lane;
-                u64 s = idx >= 0 ? st[idx] : TS_PREFIX;   /* before tile 0: an empty prefix */
+                u64 s = 2ull << 62;                       /* before tile 0: an empty prefix (TS_PREFIX | 0) */
+                if (idx >= 0) s = st[idx];
                 const u32 unset = __ballot_sync(0xffffffffu, (s & TS_MASK) == 0);
                 const u32 pre = __ballot_sync(0xffffffffu, (s & TS_MASK) == TS_PREFIX);
                 /* usable lanes: those before the first unset one, up to and including the first prefix */
