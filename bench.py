@@ -314,13 +314,15 @@ def main():
     rfq_b = state["rfq_bytes"]
     qual_b = seq_b = n_reads * 150
     # algorithmic bytes per launch of each kernel (DESIGN.md "Kernels"): what it must read + write once
+    head_b = fastq_bytes - qual_b - n_reads                                     # name + sequence + strand lines
     alg = {
-        "k_index_lines": fastq_bytes + 4 * 4 * n_reads,
-        "k_meta": (fastq_bytes - qual_b - 2 * n_reads) + 16 * n_reads,          # names + sequences + strands in, metadata out
-        "k_streams": qual_b + 0.6 * rfq_b,
-        "k_emit": seq_b + seq_b / 4,
+        "k_index_lines": fastq_bytes + 4 * 4 * n_reads,                          # text in, line index out
+        "k_unit_lengths": (16 + 16 + 4 + 4) * n_reads,                           # line index in, record index + lengths out
+        "k_meta": head_b + 16 * n_reads, "k_meta2": head_b + (16 + 16 + 3 * 44 / 2) * n_reads,   # heads in, metadata + packed reads out
+        "k_streams": qual_b + 0.6 * rfq_b, "k_streams2": qual_b + 0.6 * rfq_b,   # qualities in, tokens out
+        "k_emit": seq_b + seq_b / 4, "k_emit2": 44 * n_reads + seq_b / 4,        # packed reads in, 2-bit stream out
         "k_gather": 1.2 * rfq_b,
-        "k_dec_format": rfq_b + qual_b + fastq_bytes,
+        "k_dec_format": rfq_b + qual_b + fastq_bytes, "k_dec_format2": rfq_b + qual_b + fastq_bytes,   # columns + plane in, text out
         "k_dec_streams": 0.6 * rfq_b + 0.1 * qual_b,
     }
     kern_total = sum(ms for _, ms in prof.values())
@@ -353,10 +355,14 @@ def main():
         barrier()
         t_e = time.perf_counter()
         h2d = d2h = 0
+        parts = dict(enc_h2d_ms=0.0, enc_kernels_ms=0.0, enc_d2h_ms=0.0, dec_h2d_ms=0.0, dec_kernels_ms=0.0, dec_d2h_ms=0.0)
         for _ in range(args.steps):
             eo, do, se, sd = step_host()
             h2d += se.h2d_bytes + sd.h2d_bytes
             d2h += se.d2h_bytes + sd.d2h_bytes
+            for k, v in (("enc_h2d_ms", se.ms_h2d), ("enc_kernels_ms", se.ms_kernels), ("enc_d2h_ms", se.ms_d2h),
+                         ("dec_h2d_ms", sd.ms_h2d), ("dec_kernels_ms", sd.ms_kernels), ("dec_d2h_ms", sd.ms_d2h)):
+                parts[k] += v / args.steps
         barrier()
         e_ms = 1e3 * (time.perf_counter() - t_e)
         # result check on the host copies
@@ -367,7 +373,7 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e_ms = float(te[0])
         e2e = dict(value=job_bytes * args.steps / 1e9 / (e_ms / 1e3), unit=UNIT, h2d_bytes_per_step=int(h2d // args.steps), d2h_bytes_per_step=int(d2h // args.steps),
-                   ms_per_step=e_ms / args.steps, timing="host wall clock around the C-ABI calls (they return after the D2H completed), max over ranks")
+                   ms_per_step=e_ms / args.steps, breakdown_ms_per_step={k: round(v, 3) for k, v in parts.items()}, timing="host wall clock around the C-ABI calls (they return after the D2H completed), max over ranks")
         del h1, h2
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload

@@ -1,0 +1,171 @@
+/*
+ * repaq_b200_cli - host C++ driver with the reference's command line for the two modes on the hot path
+ * (`repaq -c` / `repaq -d`, reference src/main.cpp:31-49, src/repaq.cpp:262-413,530-759) on top of the C ABI.
+ * File-level rules kept from the reference: header written first (src/repaq.cpp:554-557), Q13 NO_LINE_BREAK thresholds
+ * (src/fastqreader.cpp:31-46), trailing-newline trimming on decode (src/repaq.cpp:300-328, 375-413).
+ * Not implemented here: .gz input/output, the xz pipe, --compare / -v / -f (outside the tier's scope).
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "repaq_b200.h"
+
+static void error_exit(const std::string& msg) { fprintf(stderr, "ERROR: %s\n", msg.c_str()); exit(-1); }   /* src/util.h:246-249 */
+
+static bool ends_with(const std::string& s, const std::string& suf) { return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0; }
+
+static std::vector<char> slurp(const std::string& path) {
+    FILE* f = path == "/dev/stdin" ? stdin : fopen(path.c_str(), "rb");
+    if (!f) error_exit("Failed to open file: " + path);
+    std::vector<char> b;
+    size_t cap = 1 << 26, n = 0;
+    b.resize(cap);
+    for (;;) {
+        size_t got = fread(b.data() + n, 1, cap - n, f);
+        n += got;
+        if (got == 0) break;
+        if (n == cap) { cap *= 2; b.resize(cap); }
+    }
+    if (f != stdin) fclose(f);
+    b.resize(n);
+    return b;
+}
+static void spill(const std::string& path, const void* p, size_t n, bool append) {
+    FILE* f = path == "/dev/stdout" ? stdout : fopen(path.c_str(), append ? "ab" : "wb");
+    if (!f) error_exit("Failed to open file: " + path);
+    if (n && fwrite(p, 1, n, f) != n) error_exit("Failed to write file: " + path);
+    if (f != stdout) fclose(f);
+}
+
+/* Q13: the reader raises hasNoLineBreakAtEnd when it loads a SHORT 1 MiB buffer that does not end in '\n' */
+static void nobreak_rule(const std::vector<char>& f, uint64_t& from, bool& tail) {
+    const uint64_t MiB = 1ull << 20, n = f.size();
+    const bool nl = n && f[n - 1] == '\n';
+    if (n % MiB == 0) { from = nl ? UINT64_MAX : n; tail = true; }
+    else { from = nl ? UINT64_MAX : (n / MiB) * MiB; tail = false; }
+}
+
+struct Opt { std::string in1, in2, out1, out2; bool compress = false, decompress = false, interleaved = false, to_stdout = false, from_stdin = false; int k = 1000; int device = 0; };
+
+static int do_compress(const Opt& o) {
+    std::vector<char> r1 = slurp(o.in1), r2;
+    const bool two = !o.in2.empty();
+    if (two) r2 = slurp(o.in2);
+    const uint32_t chunk_bases = (uint32_t)(o.k < 100 ? 100 : o.k) * 1000u;        /* src/main.cpp:69 */
+    char err[768];
+    rpq_header h;
+    if (rpq_make_header(r1.data(), r1.size(), two ? r2.data() : NULL, r2.size(), o.interleaved, chunk_bases, &h, err, sizeof err)) error_exit(err);
+    uint8_t hb[17 + 128];
+    const size_t hn = rpq_header_write(&h, hb, sizeof hb);
+    spill(o.out1, hb, hn, false);
+    rpq_ctx* ctx = NULL;
+    if (rpq_create(o.device, &ctx)) error_exit("no CUDA device: repaq_b200 has no CPU fallback");
+    if (rpq_set_header(ctx, &h)) error_exit(rpq_last_error(ctx));
+    uint64_t from1, from2 = UINT64_MAX; bool t1, t2 = false;
+    nobreak_rule(r1, from1, t1);
+    if (two) nobreak_rule(r2, from2, t2); else if (o.interleaved) { from2 = from1; t2 = t1; }
+    const uint64_t WIN = 3ull << 30;                       /* < 4 GiB of text per file and call */
+    uint64_t a = 0, b = 0;
+    for (;;) {
+        rpq_encode_in in; memset(&in, 0, sizeof in);
+        const uint64_t n1 = r1.size() - a < WIN ? r1.size() - a : WIN, n2 = two ? (r2.size() - b < WIN ? r2.size() - b : WIN) : 0;
+        in.r1 = r1.data() + a; in.r1_len = n1; in.r2 = two ? r2.data() + b : NULL; in.r2_len = n2;
+        in.mem = RPQ_MEM_HOST; in.out_mem = RPQ_MEM_HOST; in.interleaved = o.interleaved; in.chunk_bases = chunk_bases;
+        in.final = (a + n1 == r1.size()) && (!two || b + n2 == r2.size());
+        in.nobreak_from[0] = from1 == UINT64_MAX ? UINT64_MAX : (from1 > a ? from1 - a : 0);
+        in.nobreak_from[1] = from2 == UINT64_MAX ? UINT64_MAX : (two ? (from2 > b ? from2 - b : 0) : in.nobreak_from[0]);
+        in.tail_flags = (uint16_t)((t1 ? RPQ_NO_LINE_BREAK_AT_END : 0) | (t2 ? RPQ_NO_LINE_BREAK_AT_END_R2 : 0));
+        rpq_encode_out res;
+        if (rpq_encode(ctx, &in, &res)) error_exit(rpq_last_error(ctx));
+        spill(o.out1, res.data, res.bytes, true);
+        if (in.final) break;
+        if (res.r1_consumed == 0) error_exit("a chunk does not fit the 3 GiB batch window; lower --chunk");
+        a += res.r1_consumed; b += res.r2_consumed;
+    }
+    rpq_destroy(ctx);
+    return 0;
+}
+
+static int do_decompress(const Opt& o) {
+    std::vector<char> rfq = slurp(o.in1);
+    char err[768]; rpq_header h; size_t used = 0;
+    if (rpq_header_read((const uint8_t*)rfq.data(), rfq.size(), &h, &used, err, sizeof err)) error_exit(err);
+    const bool pe = !o.out2.empty();
+    if (pe && !(h.flags & RPQ_PAIRED_END)) error_exit("The input RFQ file was encoded by single-end FASTQ, you should not specify <out2>");
+    rpq_ctx* ctx = NULL;
+    if (rpq_create(o.device, &ctx)) error_exit("no CUDA device: repaq_b200 has no CPU fallback");
+    if (rpq_set_header(ctx, &h)) error_exit(rpq_last_error(ctx));
+    rpq_decode_in in; memset(&in, 0, sizeof in);
+    in.data = (const uint8_t*)rfq.data() + used; in.bytes = rfq.size() - used; in.mem = RPQ_MEM_HOST; in.out_mem = RPQ_MEM_HOST; in.split_pairs = pe;
+    rpq_decode_out res;
+    if (rpq_decode(ctx, &in, &res)) error_exit(rpq_last_error(ctx));
+    if (!pe) {
+        /* Repaq::decompress: only a flagged LAST chunk loses its final newline */
+        uint64_t n = res.out1_bytes;
+        if (res.n_chunks && (res.chunks[res.n_chunks - 1].flags & RPQ_NO_LINE_BREAK_AT_END) && n) n--;
+        spill(o.out1, res.out1, n, false);
+    } else {
+        /* Repaq::decompressPE incl. its `continue` (src/repaq.cpp:395,405): after a flagged chunk that is not the last one,
+         * the rest of that chunk's output and the whole next chunk are never written */
+        spill(o.out1, NULL, 0, false); spill(o.out2, NULL, 0, false);
+        uint64_t a1 = 0, a2 = 0;
+        for (uint32_t i = 0; i < res.n_chunks; i++) {
+            const rpq_chunk_info& c = res.chunks[i];
+            const bool f1 = c.flags & RPQ_NO_LINE_BREAK_AT_END, f2 = c.flags & RPQ_NO_LINE_BREAK_AT_END_R2, last = i + 1 == res.n_chunks;
+            bool skip_next = false;
+            if (f1) { if (last) spill(o.out1, res.out1 + a1, c.out1_bytes ? c.out1_bytes - 1 : 0, true); else { spill(o.out1, res.out1 + a1, c.out1_bytes, true); skip_next = true; } }
+            else spill(o.out1, res.out1 + a1, c.out1_bytes, true);
+            if (!skip_next) {
+                if (f2) { if (last) spill(o.out2, res.out2 + a2, c.out2_bytes ? c.out2_bytes - 1 : 0, true); else { spill(o.out2, res.out2 + a2, c.out2_bytes, true); skip_next = true; } }
+                else spill(o.out2, res.out2 + a2, c.out2_bytes, true);
+            }
+            a1 += c.out1_bytes; a2 += c.out2_bytes;
+            if (skip_next && i + 1 < res.n_chunks) { i++; a1 += res.chunks[i].out1_bytes; a2 += res.chunks[i].out2_bytes; }
+        }
+    }
+    rpq_destroy(ctx);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc == 1) { fprintf(stderr, "repaq_b200: repack FASTQ to a smaller binary file (.rfq) on a B200\nversion 0.5.1 (algorithm 2)\n"); return 0; }
+    if (argc == 2 && strcmp(argv[1], "--version") == 0) { printf("repaq 0.5.1\n"); return 0; }
+    Opt o;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto val = [&](const char* lng) -> std::string {
+            std::string pre = std::string("--") + lng + "=";
+            if (a.compare(0, pre.size(), pre) == 0) return a.substr(pre.size());
+            if (i + 1 >= argc) error_exit("option needs value: " + a);
+            return argv[++i];
+        };
+        if (a == "-i" || a.compare(0, 6, "--in1=") == 0 || a == "--in1") o.in1 = val("in1");
+        else if (a == "-I" || a.compare(0, 6, "--in2=") == 0 || a == "--in2") o.in2 = val("in2");
+        else if (a == "-o" || a.compare(0, 7, "--out1=") == 0 || a == "--out1") o.out1 = val("out1");
+        else if (a == "-O" || a.compare(0, 7, "--out2=") == 0 || a == "--out2") o.out2 = val("out2");
+        else if (a == "-k" || a.compare(0, 8, "--chunk=") == 0 || a == "--chunk") o.k = atoi(val("chunk").c_str());
+        else if (a == "-c" || a == "--compress") o.compress = true;
+        else if (a == "-d" || a == "--decompress") o.decompress = true;
+        else if (a == "--interleaved_in") o.interleaved = true;
+        else if (a == "--stdout") o.to_stdout = true;
+        else if (a == "--stdin") o.from_stdin = true;
+        else if (a.compare(0, 9, "--device=") == 0) o.device = atoi(a.c_str() + 9);
+        else error_exit("unsupported option for the B200 driver: " + a);
+    }
+    if (o.compress && o.decompress) error_exit("repaq can run in compress/decompress/compare mode, you can only choose any one mode.");
+    if (!o.decompress) o.compress = true;                                   /* compress is the default mode */
+    if (o.in1.empty()) { if (o.from_stdin) o.in1 = "/dev/stdin"; else error_exit("Please specify input file by <in1>, or enable --stdin if you want to read STDIN"); }
+    if (o.out1.empty()) { if (o.to_stdout) o.out1 = "/dev/stdout"; else error_exit("Please specify output file by <out1>, or enable --stdout if you want to read STDIN"); }
+    if (ends_with(o.in1, ".gz") || ends_with(o.in2, ".gz") || ends_with(o.out1, ".gz") || ends_with(o.in1, ".xz") || ends_with(o.out1, ".xz"))
+        error_exit("gz / xz streams are outside this driver (use zcat / xz pipes with --stdin / --stdout)");
+    const long long cs = (long long)(o.k < 100 ? 100 : o.k) * 1000;
+    if (cs > 500000000) error_exit("chunk size cannot be greater than 500,000 kb");
+    if (o.compress) { if (!o.out2.empty()) error_exit("In compress mode, only one RFQ output file is allowed, but you specified <out2>"); return do_compress(o); }
+    if (!o.in2.empty()) error_exit("In decompress mode, only one RFQ input file is allowed, but you specified <in2>");
+    return do_decompress(o);
+}

@@ -1,0 +1,63 @@
+"""The C++ command-line driver (repaq_b200/csrc/cli/main.cpp): `repaq -c` / `repaq -d` compatible invocations.
+On the CPU the driver is linked against the emulation build of the kernels (tests/emu); on the GPU box the real
+binary repaq_b200/repaq_b200_cli is used."""
+import json
+import os
+import subprocess
+
+import pytest
+
+from tests.conftest import ROOT, golden_rfq
+from tests.golden.cases import build_cases
+
+EMU_CLI = os.path.join(ROOT, "tests", "emu", "repaq_emu_cli")
+GPU_CLI = os.path.join(ROOT, "repaq_b200", "repaq_b200_cli")
+MAN = json.load(open(os.path.join(ROOT, "tests", "golden", "manifest.json")))
+CASES = {c["name"]: c for c in build_cases()}
+NAMES = ["kat_se", "kat_pe", "nova_se_k100", "nova_pe_k1000", "bgi_se_k100", "nova_pe_nonl_k100", "nova_pe_nonl_r2only_k100", "nova_se_nonl_k100",
+         "nova_interleaved_in_k100", "pe_demoted_lastpair_k100", "nova_pe_crlf_k100"]
+
+
+def run_cli(cli, tmp_path, name):
+    import hashlib
+    c, m = CASES[name], MAN[name]
+    p1 = tmp_path / "a.fq"
+    p1.write_bytes(c["r1"])
+    cmd = [cli, "-c", "-i", str(p1), "-o", str(tmp_path / "o.rfq"), "-k", str(c["k"])]
+    if c["r2"] is not None:
+        p2 = tmp_path / "b.fq"
+        p2.write_bytes(c["r2"])
+        cmd += ["-I", str(p2)]
+    if c["interleaved"]:
+        cmd += ["--interleaved_in"]
+    subprocess.check_call(cmd)
+    assert (tmp_path / "o.rfq").read_bytes() == golden_rfq(name)
+    subprocess.check_call([cli, "-d", "-i", str(tmp_path / "o.rfq"), "-o", str(tmp_path / "d.fq")])
+    d = (tmp_path / "d.fq").read_bytes()
+    assert (len(d), hashlib.sha256(d).hexdigest()) == (m["dec_len"], m["dec_sha256"])
+    if "dec1_sha256" in m:
+        subprocess.check_call([cli, "-d", "-i", str(tmp_path / "o.rfq"), "-o", str(tmp_path / "d1.fq"), "-O", str(tmp_path / "d2.fq")])
+        d1, d2 = (tmp_path / "d1.fq").read_bytes(), (tmp_path / "d2.fq").read_bytes()
+        assert (len(d1), hashlib.sha256(d1).hexdigest()) == (m["dec1_len"], m["dec1_sha256"])
+        assert (len(d2), hashlib.sha256(d2).hexdigest()) == (m["dec2_len"], m["dec2_sha256"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_cli_emulated(tmp_path, name):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
+    run_cli(EMU_CLI, tmp_path, name)
+
+
+def test_cli_error_strings(tmp_path):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
+    p = subprocess.run([EMU_CLI, "-d", "-i", str(tmp_path / "missing.rfq"), "-o", str(tmp_path / "x.fq")], capture_output=True)
+    assert p.returncode != 0 and b"Failed to open file" in p.stderr
+    (tmp_path / "bad.rfq").write_bytes(b"RFQ0.4.0\x01" + bytes(30))
+    p = subprocess.run([EMU_CLI, "-d", "-i", str(tmp_path / "bad.rfq"), "-o", str(tmp_path / "x.fq")], capture_output=True)
+    assert p.returncode != 0 and b"different version of repaq" in p.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_cli_gpu(tmp_path, name):
+    run_cli(GPU_CLI, tmp_path, name)
