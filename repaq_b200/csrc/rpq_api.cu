@@ -11,9 +11,12 @@
 #include "rpq_index.cuh"
 #include "rpq_encode.cuh"
 #include "rpq_streams2.cuh"
+#include "rpq_streams3.cuh"
 #include "rpq_meta2.cuh"
+#include "rpq_meta3.cuh"
 #include "rpq_decode.cuh"
 #include "rpq_decode2.cuh"
+#include "rpq_decode3.cuh"
 #include "rpq_host.h"
 
 using namespace rpq;
@@ -136,8 +139,9 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     { const char* e = getenv("RPQ_DEBUG_FORCE_V1"); c->force_v1 = e && e[0] == '1'; }
 #ifndef RPQ_EMU
     cudaFuncSetAttribute(k_streams2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_meta2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(k_dec_format2, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
+    cudaFuncSetAttribute(k_streams3, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_meta3, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_dec_format3, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
 #endif
     *out = c;
     return RPQ_OK;
@@ -337,14 +341,14 @@ extern "C" int rpq_encode(rpq_ctx* c, const rpq_encode_in* in, rpq_encode_out* o
         m2.pkw = ((us.max_read + 15u) / 16u + 1u) | 1u;
         size_t smem2 = 0;
         for (u32 P : {128u, 64u, 32u}) {
-            smem2 = 4ull * P * per * m2.slot_words + 4ull * P * per * m2.pkw + 4ull * P * m2.pkw;
+            const size_t nr = (size_t)P * per;
+            smem2 = 4 * nr * (m2.slot_words + m2.pkw) + 16 * nr + 4 * nr + ((nr + 3) & ~(size_t)3) + 4 * (size_t)P + 64;
             if (smem2 <= 160u * 1024u && !c->force_v1) { m2.units_per_cta = P; v2 = true; break; }
         }
         if (v2) {
-            if (!ensure(c, c->pk, 4ull * n_reads * m2.pkw + 64) || !ensure(c, c->pk_rc, 4ull * (n_reads / 2 + 1) * m2.pkw + 64))
-                return fail(c, RPQ_ERR_NOMEM, "out of device memory (packed reads)");
-            b.pk = c->pk.as<u32>(); b.pk_rc = c->pk_rc.as<u32>(); b.pkw = m2.pkw;
-            LAUNCH(c, k_meta2, (units + m2.units_per_cta - 1) / m2.units_per_cta, m2.units_per_cta, smem2, b, hd, units, m2);
+            if (!ensure(c, c->pk, 4ull * n_reads * m2.pkw + 64)) return fail(c, RPQ_ERR_NOMEM, "out of device memory (packed reads)");
+            b.pk = c->pk.as<u32>(); b.pk_rc = nullptr; b.pkw = m2.pkw;
+            LAUNCH(c, k_meta3, (units + m2.units_per_cta - 1) / m2.units_per_cta, m2.units_per_cta * per, smem2, b, hd, units, m2);
         } else {
             const int use_smem = pe && us.max_read <= (u32)META_SEQ_SMEM;     /* longer reads: the overlap search reads the text directly */
             LAUNCH(c, k_meta, (units + META_WARPS - 1) / META_WARPS, 32 * META_WARPS, use_smem ? META_WARPS * 2 * META_SEQ_SMEM : 0, b, hd, units, use_smem);
@@ -385,7 +389,8 @@ extern "C" int rpq_encode(rpq_ctx* c, const rpq_encode_in* in, rpq_encode_out* o
             j.n_spans = c->misc.as<u32>() + 20 + k;
             LAUNCH(c, k_span_plan, 1, 256, 0, b, (u32)k, c->span_first[k].as<u32>(), c->span_chunk[k].as<u32>(), span_cap, c->misc.as<u32>() + 20 + k);
             const size_t smem = ST_SPAN + 2 * ST_HALO + (size_t)j.nstreams * S2_THREADS * (sizeof(u32) + 3 * sizeof(u16));
-            LAUNCH(c, k_streams2, span_cap, S2_THREADS, smem, b, hd, j, c->span_chunk[k].as<u32>());
+            if (c->force_v1) LAUNCH(c, k_streams2, span_cap, S2_THREADS, smem, b, hd, j, c->span_chunk[k].as<u32>());
+            else LAUNCH(c, k_streams3, span_cap, S2_THREADS, smem, b, hd, j, c->span_chunk[k].as<u32>());
         }
         u32 ovf = 0;
         if (have_q || have_n) { if (int rc = read_back(c, c->misc.as<u32>() + 16, &ovf)) return fail(c, rc, "CUDA failure in k_streams"); }

@@ -144,131 +144,6 @@ __device__ inline int overlap_dir_packed(const u32* a, int la, const u32* p, int
     return 0;
 }
 
-__global__ void __launch_bounds__(128) k_meta2(EncBatchDev b, HeaderDev h, u32 n_units, Meta2Cfg cfg) {
-    RPQ_DYN_SMEM(dyn);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const u32 P = cfg.units_per_cta, per = b.is_pe ? 2u : 1u;
-    const u32 u0 = blockIdx.x * P;
-    const u32 n_here = n_units - u0 < P ? n_units - u0 : P;
-    u32* slots = reinterpret_cast<u32*>(dyn);                         /* [P*per][slot_words] */
-    u32* pkS = slots + (size_t)P * per * cfg.slot_words;              /* [P*per][pkw]   as stored */
-    u32* pkR = pkS + (size_t)P * per * cfg.pkw;                       /* [P][pkw]       revcomp(R2) */
-
-    /* ---- stage the record heads (warp per record) */
-    for (u32 r = warp; r < n_here * per; r += nwarps) {
-        const u32 i = u0 * per + r;
-        const uint4 lc = b.loc[i];
-        u32 f, rec; read_locus(b, i, f, rec);
-        const u8* text = b.t[f].text;
-        const u32 head = lc.w - lc.x;
-        const u32 a0 = lc.x & ~3u;
-        const u32 nw = ((lc.x & 3u) + head + 3u) >> 2;
-        const u32* src = reinterpret_cast<const u32*>(text + a0);
-        u32* dst = slots + (size_t)r * cfg.slot_words;
-        /* the last word may reach past the end of the text image by < 4 bytes: buffers are padded by the API */
-        for (u32 k = lane; k < nw && k < cfg.slot_words; k += 32) dst[k] = src[k];
-    }
-    __syncthreads();
-
-    const u32 u = u0 + tid;
-    if (tid < (int)n_here) {
-        const u32 i0 = u * per;
-        const u32 c = chunk_of_read(b, i0);
-        const u32 first = b.chunk_first[c];
-        const ReadMeta m0 = b.meta0[c];
-        const uint4 lc0 = b.loc[first];
-        u32 f0, rec0; read_locus(b, first, f0, rec0);
-        const u32 crlf0 = b.t[f0].crlf;
-        const u8* name0 = b.t[f0].text + lc0.x;
-        const u8* strand0 = b.t[f0].text + lc0.z;
-        const u32 rlen0 = lc0.z - lc0.y - 1u - crlf0;
-        const int n2len0 = (int)m0.name_len - (int)m0.name2_off;
-
-        u32 clear = 0;
-        ReadMeta mm[2];
-        bool eq0[2] = {true, true};
-        u32 seq_off[2] = {0, 0}; int rl[2] = {0, 0};
-        const u32* sw[2] = {nullptr, nullptr};
-        for (u32 k = 0; k < per; k++) {
-            const u32 i = i0 + k;
-            const uint4 lc = b.loc[i];
-            u32 f, rec; read_locus(b, i, f, rec);
-            const u32 crlf = b.t[f].crlf;
-            const u32* words = slots + (size_t)(tid * per + k) * cfg.slot_words;
-            const u8* bytes = reinterpret_cast<const u8*>(words) + (lc.x & 3u);
-            const int nlen = (int)(lc.y - lc.x - 1u - crlf);
-            const int rlen = (int)(lc.z - lc.y - 1u - crlf);
-            const int slen = (int)(lc.w - lc.z - 1u - crlf);
-            ReadMeta m = thread_tokenise(bytes, nlen < 256 ? nlen : 255);
-            m.strand_len = (u8)slen;
-            mm[k] = m;
-            b.meta[i] = m;
-            sw[k] = words; seq_off[k] = (lc.x & 3u) + (lc.y - lc.x); rl[k] = rlen;
-            if ((u32)rlen != rlen0) clear |= AB_READ_LEN;
-            if (m.name1_len != m0.name1_len) clear |= AB_N1LEN;
-            const int n2len = (int)m.name_len - (int)m.name2_off;
-            if (n2len != n2len0) clear |= AB_N2LEN;
-            if (m.strand_len != m0.strand_len) clear |= AB_SLEN;
-            if (m.lane != m0.lane) clear |= AB_LANE;
-            if (m.tile != m0.tile) clear |= AB_TILE;
-            if (m.name1_len != m0.name1_len || !bytes_equal(bytes, name0, m.name1_len)) clear |= AB_N1;
-            if (m.strand_len != m0.strand_len || !bytes_equal(bytes + (lc.z - lc.x), strand0, slen)) clear |= AB_STRAND;
-            eq0[k] = (n2len == n2len0) && bytes_equal(bytes + m.name2_off, name0 + m0.name2_off, n2len);
-            /* the read as it will be stored */
-            pack_forward(words, seq_off[k], rlen, pkS + (size_t)(tid * per + k) * cfg.pkw, (int)cfg.pkw);
-        }
-        ChunkDev& ck = b.chunks[c];
-        if (clear && (*(volatile u32*)&ck.and_bits & clear)) atomicAnd(&ck.and_bits, ~clear);
-        const u32 rel = i0 - first;
-        if (!b.is_pe) {
-            if (!eq0[0]) { if (rel & 1u) atomicMax(&ck.last_odd_neq, rel + 1); else if (!*(volatile u32*)&ck.even_neq) atomicOr(&ck.even_neq, 1u); }
-        } else {
-            if (!eq0[0] && !*(volatile u32*)&ck.even_neq) atomicOr(&ck.even_neq, 1u);
-            if (!eq0[1]) atomicMax(&ck.last_odd_neq, rel + 2);
-            if (h.support_interleaved) {
-                /* Q10: R1.name2 with the header's diff char substituted must equal R2.name2; lane/tile/x/y must agree */
-                const u8* n1 = reinterpret_cast<const u8*>(sw[0]) + (b.loc[i0].x & 3u) + mm[0].name2_off;
-                const u8* n2 = reinterpret_cast<const u8*>(sw[1]) + (b.loc[i0 + 1].x & 3u) + mm[1].name2_off;
-                const int l1 = (int)mm[0].name_len - (int)mm[0].name2_off, l2 = (int)mm[1].name_len - (int)mm[1].name2_off;
-                bool okA = l1 == l2;
-                for (int q = 0; okA && q < l1; q++) { u8 ch = n1[q]; if (h.name2_diff_char != 0 && q == (int)h.name2_diff_pos) ch = h.name2_diff_char; if (ch != n2[q]) okA = false; }
-                const bool okB = mm[0].lane == mm[1].lane && mm[0].tile == mm[1].tile && mm[0].x == mm[1].x && mm[0].y == mm[1].y;
-                if (!okA) atomicMin(&ck.fA, rel + 1);
-                if (!okB) atomicMin(&ck.fB, rel + 1);
-                int o = 0;
-                if (h.flags & RPQ_ENCODE_PE_BY_OVERLAP) {
-                    u32* A = pkS + (size_t)(tid * 2) * cfg.pkw;
-                    u32* R = pkR + (size_t)tid * cfg.pkw;
-                    pack_revcomp(sw[1], seq_off[1], rl[1], R, (int)cfg.pkw);
-                    const u8* s1 = reinterpret_cast<const u8*>(sw[0]) + seq_off[0];
-                    const u8* s2 = reinterpret_cast<const u8*>(sw[1]) + seq_off[1];
-                    const int len1 = rl[0], len2 = rl[1];
-                    /* forward: r1[len1-o+i] == rc2[i]; backward: rc2[len2-o+i] == r1[i]   (rc2[i] = comp(r2[len2-1-i])) */
-                    auto vf = [&](int oo) { for (int q = 0; q < oo; q++) if (s1[len1 - oo + q] != complement_base(s2[len2 - 1 - q])) return false; return true; };
-                    auto vb = [&](int oo) { for (int q = 0; q < oo; q++) if (complement_base(s2[oo - 1 - q]) != s1[q]) return false; return true; };
-                    o = overlap_dir_packed(A, len1, R, len2, (int)cfg.pkw, vf);
-                    if (!o) o = -overlap_dir_packed(R, len2, A, len1, (int)cfg.pkw, vb);
-                    if (o + (int)h.overlap_shift > 127) o = 0;
-                    if (o + (int)h.overlap_shift < -127) o = 0;
-                }
-                b.ov[u] = (short)o;
-            }
-        }
-    }
-    __syncthreads();
-    /* ---- packed reads to global memory, coalesced (shared and global layouts are both [read][pkw]) */
-    {
-        const u32 nw = n_here * per * cfg.pkw;
-        u32* g = b.pk + (size_t)u0 * per * cfg.pkw;
-        for (u32 k = tid; k < nw; k += blockDim.x) g[k] = pkS[k];
-        if (b.is_pe && h.support_interleaved && (h.flags & RPQ_ENCODE_PE_BY_OVERLAP)) {
-            const u32 nr = n_here * cfg.pkw;
-            u32* gr = b.pk_rc + (size_t)u0 * cfg.pkw;
-            for (u32 k = tid; k < nr; k += blockDim.x) gr[k] = pkR[k];
-        }
-    }
-}
-
 }  // namespace rpq
 
 namespace rpq {
@@ -310,18 +185,30 @@ __global__ void __launch_bounds__(256) k_emit2(EncBatchDev b, HeaderDev h, u8* o
     const u32 kept = kept_bases(b, h, il, i, rel);
     if (kept == 0) return;
     const u32 pkw = b.pkw;
-    auto source = [&](u32 ii, u32 rr, u32& shift) -> const u32* {
-        shift = 0;
-        if (il && (rr & 1u)) { const int ov = (h.flags & RPQ_ENCODE_PE_BY_OVERLAP) ? (int)b.ov[ii >> 1] : 0; shift = ov > 0 ? (u32)ov : 0u; return b.pk_rc + (size_t)(ii >> 1) * pkw; }
-        return b.pk + (size_t)ii * pkw;
+    /* 16 kept bases of read ii (chunk-relative rr) from kept-base index j0.  In a file whose header supports interleaving the
+     * odd reads are packed as revcomp (k_meta3); a chunk that lost the interleaved form (Q10) needs them forward: from the text. */
+    const bool rc_file = b.is_pe && h.support_interleaved;
+    auto window = [&](u32 ii, u32 rr, u32 j0) -> u32 {
+        if (il && (rr & 1u)) {
+            const int ov = (h.flags & RPQ_ENCODE_PE_BY_OVERLAP) ? (int)b.ov[ii >> 1] : 0;
+            return packed_window(b.pk + (size_t)ii * pkw, j0 + (ov > 0 ? (u32)ov : 0u), pkw);
+        }
+        if (rc_file && (rr & 1u)) {
+            u32 f, rec; read_locus(b, ii, f, rec);
+            const u8* sq = b.t[f].text + b.loc[ii].y;
+            const u32 rl2 = b.rlen[ii];
+            u32 w = 0;
+            for (u32 k = 0; k < 16u && j0 + k < rl2; k++) w |= base_code(sq[j0 + k]) << (2 * k);
+            return w;
+        }
+        return packed_window(b.pk + (size_t)ii * pkw, j0, pkw);
     };
-    u32 shift; const u32* src = source(i, rel, shift);
     u8* col = o + ck.off_seq;
     const u32 w0 = (so + 15u) >> 4, w1 = (so + kept - 1u) >> 4;
     for (u32 W = w0; W <= w1; W++) {
         const u32 p0 = 16u * W;
         u32 have = so + kept - p0; if (have > 16u) have = 16u;                  /* own bases in this word */
-        u32 word = packed_window(src, p0 - so + shift, pkw);
+        u32 word = window(i, rel, p0 - so);
         if (have < 16u) {
             word &= (1u << (2 * have)) - 1u;
             /* pull from the following reads that still have kept bases */
@@ -330,9 +217,8 @@ __global__ void __launch_bounds__(256) k_emit2(EncBatchDev b, HeaderDev h, u8* o
                 const u32 i2 = ck.first + r2;
                 const u32 k2 = kept_bases(b, h, il, i2, r2);
                 if (k2) {
-                    u32 sh2; const u32* s2 = source(i2, r2, sh2);
                     u32 take = 16u - filled; if (take > k2) take = k2;
-                    u32 w2 = packed_window(s2, sh2, pkw);
+                    u32 w2 = window(i2, r2, 0u);
                     if (take < 16u) w2 &= (1u << (2 * take)) - 1u;
                     word |= w2 << (2 * filled);
                     filled += take;

@@ -1,0 +1,263 @@
+/*
+ * rpq_meta3.cuh - k_meta3: per-read metadata, third generation.  Same staging and outputs as k_meta2 (rpq_meta2.cuh) but the
+ * CTA re-maps its threads per phase so that twice as many threads share the same shared-memory footprint, and the overlap
+ * search does three instructions per candidate:
+ *
+ *   stage   warp per record: name + sequence + strand lines -> fixed slots (word copies, source byte phase kept)
+ *   A       thread per READ : FastqMeta::parse (reference src/fastqmeta.cpp:22-80), comparisons with the chunk's first read
+ *                             (src/rfqcodec.cpp:225-234)
+ *   A2      thread per PAIR : the PE consistency test (src/rfqcodec.cpp:233-270, Q10)
+ *   B       thread per READ : 2-bit packing as stored (src/rfqcodec.cpp:593-604); an odd read of a file whose header supports
+ *                             interleaving is packed as revcomp (src/read.cpp:77-115), which is what both the overlap search
+ *                             and the stored stream need; "clean" = only A/C/G/T(/acgt for R2) characters
+ *   C       thread per (PAIR, DIRECTION): RfqCodec::overlap (src/rfqcodec.cpp:1391-1438) on packed words, 16 candidate shifts
+ *                             per pair of words; a packed match of two clean reads is exact, otherwise the bytes are compared
+ *   D       thread per PAIR : forward beats backward, +-127 clamp (src/rfqcodec.cpp:378-383); packed reads to HBM, coalesced
+ *
+ * v2 ran all phases in one thread per pair: 18.75 % occupancy, 28 % issue utilisation (profiles/r01_v2_ncu_full_k_meta2.csv).
+ */
+#pragma once
+#include "rpq_meta2.cuh"
+
+namespace rpq {
+
+/* code_fwd / code_rc words plus the "is a plain base" test; returns packed 2-bit codes of 4 bytes and clears `clean` otherwise */
+__device__ __forceinline__ u32 codes_fwd_clean(u32 w, u32 valid_mask, bool& clean) {
+    const u32 a = __vcmpeq4(w, 0x41414141u), t = __vcmpeq4(w, 0x54545454u), c = __vcmpeq4(w, 0x43434343u), g = __vcmpeq4(w, 0x47474747u);
+    if (((a | t | c | g) & valid_mask) != valid_mask) clean = false;
+    return (a & 0x01010101u) | (t & 0x02020202u) | (c & 0x03030303u);
+}
+__device__ __forceinline__ u32 codes_rc_clean(u32 w, u32 valid_mask, bool& clean) {
+    const u32 l = w | 0x20202020u;
+    const u32 a = __vcmpeq4(l, 0x61616161u), t = __vcmpeq4(l, 0x74747474u), c = __vcmpeq4(l, 0x63636363u), g = __vcmpeq4(l, 0x67676767u);
+    if (((a | t | c | g) & valid_mask) != valid_mask) clean = false;
+    return (a & 0x02020202u) | (t & 0x01010101u) | (g & 0x03030303u);
+}
+
+__device__ inline bool pack_forward_c(const u32* words, u32 off, int len, u32* dst, int pkw) {
+    bool clean = true;
+    for (int j = 0; j < pkw; j++) {
+        u32 acc = 0;
+        const int base = j * 16;
+        if (base < len) {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const int p = base + 4 * g;
+                if (p >= len) break;
+                const int left = len - p;
+                const u32 vm = left >= 4 ? 0xFFFFFFFFu : ((1u << (8 * left)) - 1u);
+                const u32 c = codes_fwd_clean(ld4(words, off + (u32)p), vm, clean) & vm;
+                acc |= squeeze4(c) << (8 * g);
+            }
+        }
+        dst[j] = acc;
+    }
+    return clean;
+}
+__device__ inline bool pack_revcomp_c(const u32* words, u32 off, int len, u32* dst, int pkw) {
+    bool clean = true;
+    for (int j = 0; j < pkw; j++) {
+        u32 acc = 0;
+        const int base = j * 16;
+        if (base < len) {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const int k = base + 4 * g;
+                if (k >= len) break;
+                const int left = len - k;
+                u32 w;
+                if (left >= 4) w = __byte_perm(ld4(words, off + (u32)(len - 4 - k)), 0, 0x0123);
+                else { w = 0; for (int q = 0; q < left; q++) w |= (u32)reinterpret_cast<const u8*>(words)[off + (u32)(len - 1 - k - q)] << (8 * q); }
+                const u32 vm = left >= 4 ? 0xFFFFFFFFu : ((1u << (8 * left)) - 1u);
+                const u32 c = codes_rc_clean(w, vm, clean) & vm;
+                acc |= squeeze4(c) << (8 * g);
+            }
+        }
+        dst[j] = acc;
+    }
+    return clean;
+}
+
+/* do the packed sequences agree on o bases: a from base s, p from base 0 */
+__device__ __forceinline__ bool packed_equal(const u32* a, int s, const u32* p, int o, int pkw) {
+    for (int k = 0; k < o; k += 16) {
+        const int s2 = s + k;
+        const u32 w2 = (u32)s2 >> 4, sh2 = ((u32)s2 & 15u) * 2u;
+        const u32 win = __funnelshift_r(a[w2], (int)(w2 + 1) < pkw ? a[w2 + 1] : 0u, sh2);
+        const int rem = o - k;
+        const u32 m = rem >= 16 ? 0xFFFFFFFFu : ((1u << (2 * rem)) - 1u);
+        if (((win ^ p[k >> 4]) & m) != 0) return false;
+    }
+    return true;
+}
+
+/* smallest o in [12, min(la, lp)] with a[la-o+i] == p[i] (i < o); `exact(o)` confirms a packed match when a read is not clean */
+template <class V>
+__device__ inline int overlap_search(const u32* a, int la, const u32* p, int lp, int pkw, bool packed_is_exact, const V& exact) {
+    const int minlen = la < lp ? la : lp;
+    if (minlen < 12) return 0;
+    const u32 pat = p[0];
+    auto confirm = [&](int o) -> bool { return packed_equal(a, la - o, p, o, pkw) && (packed_is_exact || exact(o)); };
+    /* o = 12..15: masked window */
+    for (int o = 12; o <= 15 && o <= minlen; o++) {
+        const int s = la - o;
+        const u32 wi = (u32)s >> 4, sh = ((u32)s & 15u) * 2u;
+        const u32 win = __funnelshift_r(a[wi], (int)(wi + 1) < pkw ? a[wi + 1] : 0u, sh);
+        if ((((win ^ pat) & ((1u << (2 * o)) - 1u)) == 0) && confirm(o)) return o;
+    }
+    if (minlen < 16) return 0;
+    /* o >= 16: window start s from la-16 down to la-minlen, a full 16-base compare per shift */
+    const int s_hi = la - 16, s_lo = la - minlen;
+    for (int wi = s_hi >> 4; wi >= (s_lo >> 4); wi--) {
+        const u32 lo = a[wi], hi = wi + 1 < pkw ? a[wi + 1] : 0u;
+        u32 hits = 0;
+#pragma unroll
+        for (int sh = 0; sh < 16; sh++) hits |= (u32)(__funnelshift_r(lo, hi, 2 * sh) == pat) << sh;
+        /* restrict to [s_lo, s_hi] */
+        const int base = wi << 4;
+        if (base + 15 > s_hi) hits &= (2u << (s_hi - base)) - 1u;
+        if (base < s_lo) hits &= ~((1u << (s_lo - base)) - 1u);
+        while (hits) {
+            const int sh = 31 - __clz((int)hits);              /* largest start first = smallest o first */
+            hits &= ~(1u << sh);
+            const int o = la - (base + sh);
+            if (confirm(o)) return o;
+        }
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) k_meta3(EncBatchDev b, HeaderDev h, u32 n_units, Meta2Cfg cfg) {
+    RPQ_DYN_SMEM(dyn);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const u32 P = cfg.units_per_cta, per = b.is_pe ? 2u : 1u;
+    const u32 u0 = blockIdx.x * P;
+    const u32 n_here = n_units - u0 < P ? n_units - u0 : P;
+    const u32 n_reads_here = n_here * per;
+    u32* slots = reinterpret_cast<u32*>(dyn);                         /* [P*per][slot_words] */
+    u32* pkS = slots + (size_t)P * per * cfg.slot_words;              /* [P*per][pkw] */
+    ReadMeta* s_meta = reinterpret_cast<ReadMeta*>(pkS + (size_t)P * per * cfg.pkw);   /* [P*per] */
+    u32* s_seq = reinterpret_cast<u32*>(s_meta + (size_t)P * per);    /* [P*per] byte offset of the sequence inside the slot | rlen << 16 */
+    u8* s_flag = reinterpret_cast<u8*>(s_seq + (size_t)P * per);      /* [P*per] bit0 name2 == read0.name2, bit1 clean */
+    short* s_ov = reinterpret_cast<short*>(s_flag + (((size_t)P * per + 3) & ~(size_t)3));   /* [P*2] per direction */
+    const bool rc_odd = b.is_pe && h.support_interleaved;
+
+    for (u32 r = warp; r < n_reads_here; r += nwarps) {
+        const u32 i = u0 * per + r;
+        const uint4 lc = b.loc[i];
+        u32 f, rec; read_locus(b, i, f, rec);
+        const u8* text = b.t[f].text;
+        const u32 head = lc.w - lc.x;
+        const u32 a0 = lc.x & ~3u;
+        const u32 nw = ((lc.x & 3u) + head + 3u) >> 2;
+        const u32* src = reinterpret_cast<const u32*>(text + a0);
+        u32* dst = slots + (size_t)r * cfg.slot_words;
+        for (u32 k = lane; k < nw && k < cfg.slot_words; k += 32) dst[k] = src[k];
+    }
+    __syncthreads();
+
+    /* ---- A: thread per read */
+    if ((u32)tid < n_reads_here) {
+        const u32 r = tid, i = u0 * per + r;
+        const u32 c = chunk_of_read(b, i);
+        const u32 first = b.chunk_first[c];
+        const ReadMeta m0 = b.meta0[c];
+        const uint4 lc0 = b.loc[first];
+        u32 f0, rec0; read_locus(b, first, f0, rec0);
+        const u8* name0 = b.t[f0].text + lc0.x;
+        const u8* strand0 = b.t[f0].text + lc0.z;
+        const u32 rlen0 = lc0.z - lc0.y - 1u - b.t[f0].crlf;
+        const int n2len0 = (int)m0.name_len - (int)m0.name2_off;
+        const uint4 lc = b.loc[i];
+        u32 f, rec; read_locus(b, i, f, rec);
+        const u32 crlf = b.t[f].crlf;
+        const u32* words = slots + (size_t)r * cfg.slot_words;
+        const u8* bytes = reinterpret_cast<const u8*>(words) + (lc.x & 3u);
+        const int nlen = (int)(lc.y - lc.x - 1u - crlf);
+        const int rlen = (int)(lc.z - lc.y - 1u - crlf);
+        const int slen = (int)(lc.w - lc.z - 1u - crlf);
+        ReadMeta m = thread_tokenise(bytes, nlen < 256 ? nlen : 255);
+        m.strand_len = (u8)slen;
+        b.meta[i] = m;
+        s_meta[r] = m;
+        s_seq[r] = ((lc.x & 3u) + (lc.y - lc.x)) | ((u32)rlen << 16);
+        u32 clear = 0;
+        if ((u32)rlen != rlen0) clear |= AB_READ_LEN;
+        if (m.name1_len != m0.name1_len) clear |= AB_N1LEN;
+        const int n2len = (int)m.name_len - (int)m.name2_off;
+        if (n2len != n2len0) clear |= AB_N2LEN;
+        if (m.strand_len != m0.strand_len) clear |= AB_SLEN;
+        if (m.lane != m0.lane) clear |= AB_LANE;
+        if (m.tile != m0.tile) clear |= AB_TILE;
+        if (m.name1_len != m0.name1_len || !bytes_equal(bytes, name0, m.name1_len)) clear |= AB_N1;
+        if (m.strand_len != m0.strand_len || !bytes_equal(bytes + (lc.z - lc.x), strand0, slen)) clear |= AB_STRAND;
+        const bool eq0 = (n2len == n2len0) && bytes_equal(bytes + m.name2_off, name0 + m0.name2_off, n2len);
+        ChunkDev& ck = b.chunks[c];
+        if (clear && (*(volatile u32*)&ck.and_bits & clear)) atomicAnd(&ck.and_bits, ~clear);
+        const u32 rel = i - first;
+        if (!eq0) { if (rel & 1u) atomicMax(&ck.last_odd_neq, rel + 1); else if (!*(volatile u32*)&ck.even_neq) atomicOr(&ck.even_neq, 1u); }
+        /* ---- B: the read as it will be stored */
+        const u32 so = s_seq[r] & 0xFFFFu;
+        bool clean;
+        if (rc_odd && (r & 1u)) clean = pack_revcomp_c(words, so, rlen, pkS + (size_t)r * cfg.pkw, (int)cfg.pkw);
+        else clean = pack_forward_c(words, so, rlen, pkS + (size_t)r * cfg.pkw, (int)cfg.pkw);
+        s_flag[r] = (u8)((eq0 ? 1u : 0u) | (clean ? 2u : 0u));
+    }
+    __syncthreads();
+    if (rc_odd) {
+        /* ---- A2: thread per pair (Q10) */
+        if ((u32)tid < n_here) {
+            const u32 u = u0 + tid, i0 = u * 2;
+            const u32 c = chunk_of_read(b, i0);
+            ChunkDev& ck = b.chunks[c];
+            const u32 rel = i0 - b.chunk_first[c];
+            const ReadMeta ma = s_meta[2 * tid], mb = s_meta[2 * tid + 1];
+            const u8* n1 = reinterpret_cast<const u8*>(slots + (size_t)(2 * tid) * cfg.slot_words) + (b.loc[i0].x & 3u) + ma.name2_off;
+            const u8* n2 = reinterpret_cast<const u8*>(slots + (size_t)(2 * tid + 1) * cfg.slot_words) + (b.loc[i0 + 1].x & 3u) + mb.name2_off;
+            const int l1 = (int)ma.name_len - (int)ma.name2_off, l2 = (int)mb.name_len - (int)mb.name2_off;
+            bool okA = l1 == l2;
+            for (int q = 0; okA && q < l1; q++) { u8 ch = n1[q]; if (h.name2_diff_char != 0 && q == (int)h.name2_diff_pos) ch = h.name2_diff_char; if (ch != n2[q]) okA = false; }
+            const bool okB = ma.lane == mb.lane && ma.tile == mb.tile && ma.x == mb.x && ma.y == mb.y;
+            if (!okA) atomicMin(&ck.fA, rel + 1);
+            if (!okB) atomicMin(&ck.fB, rel + 1);
+        }
+        /* ---- C: thread per (pair, direction) */
+        if ((h.flags & RPQ_ENCODE_PE_BY_OVERLAP) && (u32)tid < 2 * n_here) {
+            const u32 pair = tid >> 1, dir = tid & 1u;
+            const u32* A = pkS + (size_t)(2 * pair) * cfg.pkw;          /* r1 as stored */
+            const u32* R = pkS + (size_t)(2 * pair + 1) * cfg.pkw;      /* revcomp(r2) */
+            const u32 sa = s_seq[2 * pair], sb = s_seq[2 * pair + 1];
+            const int len1 = (int)(sa >> 16), len2 = (int)(sb >> 16);
+            const u8* s1 = reinterpret_cast<const u8*>(slots + (size_t)(2 * pair) * cfg.slot_words) + (sa & 0xFFFFu);
+            const u8* s2 = reinterpret_cast<const u8*>(slots + (size_t)(2 * pair + 1) * cfg.slot_words) + (sb & 0xFFFFu);
+            const bool exact_packed = (s_flag[2 * pair] & 2u) && (s_flag[2 * pair + 1] & 2u);
+            int o;
+            if (dir == 0) {
+                auto vf = [&](int oo) { for (int q = 0; q < oo; q++) if (s1[len1 - oo + q] != complement_base(s2[len2 - 1 - q])) return false; return true; };
+                o = overlap_search(A, len1, R, len2, (int)cfg.pkw, exact_packed, vf);
+            } else {
+                auto vb = [&](int oo) { for (int q = 0; q < oo; q++) if (complement_base(s2[oo - 1 - q]) != s1[q]) return false; return true; };
+                o = overlap_search(R, len2, A, len1, (int)cfg.pkw, exact_packed, vb);
+            }
+            s_ov[tid] = (short)o;
+        }
+        __syncthreads();
+        if ((u32)tid < n_here) {
+            int o = 0;
+            if (h.flags & RPQ_ENCODE_PE_BY_OVERLAP) {
+                o = s_ov[2 * tid] ? (int)s_ov[2 * tid] : -(int)s_ov[2 * tid + 1];
+                if (o + (int)h.overlap_shift > 127) o = 0;
+                if (o + (int)h.overlap_shift < -127) o = 0;
+            }
+            b.ov[u0 + tid] = (short)o;
+        }
+    }
+    /* ---- D: packed reads to global memory, coalesced */
+    {
+        const u32 nw = n_reads_here * cfg.pkw;
+        u32* g = b.pk + (size_t)u0 * per * cfg.pkw;
+        for (u32 k = tid; k < nw; k += blockDim.x) g[k] = pkS[k];
+    }
+}
+
+}  // namespace rpq

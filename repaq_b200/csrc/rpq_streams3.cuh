@@ -1,0 +1,242 @@
+/*
+ * rpq_streams3.cuh - k_streams3: the position-stream coder (reference src/rfqcodec.cpp:625-765 and :420-426), third
+ * generation.  Same contract as k_streams2 (S2Tables / SpanDir / slots) but the work is organised around RUNS:
+ *
+ *   a thread owns 64 consecutive positions and reduces them to two 64-bit masks with SIMD byte compares:
+ *       NM  position does not hold the major quality (mode 1: position holds 'N')
+ *       EQ  position holds the same byte as the position before it
+ *   a run of a stream value is then "lowest set NM bit + the EQ bits that follow"; every lane of a warp handles its k-th
+ *   run in the same iteration (convergent), and both passes (count, write) replay the masks from registers.
+ *   Staging of the quality bytes is word based (funnel shift / byte reverse), not byte based.
+ *
+ * v2 classified byte by byte inside a divergent loop: 1.72 G warp instructions for 180 M positions at 6.7 active threads
+ * per instruction (profiles/r01_v2_ncu_full_k_streams2.csv).
+ */
+#pragma once
+#include "rpq_streams2.cuh"
+
+namespace rpq {
+
+__device__ __forceinline__ u32 pack4(u32 m) { m &= 0x01010101u; return (m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xFu; }
+__device__ __forceinline__ int eq_run(u64 eq, int k) { if (k >= 64) return 0; const u64 t = ~(eq >> k); return t ? (__ffsll((long long)t) - 1) : (64 - k); }
+
+/* quality bytes of the chunk's positions [lo, hi) into sm[pos - lo]; lo is a multiple of 4; word based */
+__device__ inline void stage_quality_words(const EncBatchDev& b, const ChunkDev& ck, u32 lo, u32 hi, u8* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (hi <= lo) return;
+    const u32* offs = b.qualoff;
+    u32 a = 0, z = ck.count;
+    while (z - a > 1) { const u32 mid = (a + z) >> 1; if (offs[ck.first + mid] <= lo) a = mid; else z = mid; }
+    u32* smw = reinterpret_cast<u32*>(sm);
+    for (u32 rel = a + warp; rel < ck.count; rel += nwarps) {
+        const u32 i = ck.first + rel;
+        const u32 off = offs[i];
+        if (off >= hi) break;
+        const u32 rl = b.rlen[i];
+        if (off + rl <= lo) continue;
+        u32 f, rec; read_locus(b, i, f, rec);
+        const u8* q = b.t[f].text + b.loc[i].w;
+        const bool rev = ck.interleaved && (rel & 1u);
+        const u32 d0 = (off > lo ? off : lo) - lo, d1 = (off + rl < hi ? off + rl : hi) - lo;      /* shared range [d0, d1) */
+        const u32 w0 = (d0 + 3u) & ~3u, w1 = d1 & ~3u;
+        auto src = [&](u32 x) -> u8 { const u32 j = x + lo - off; return rev ? q[rl - 1 - j] : q[j]; };
+        if (w0 >= w1) { for (u32 x = d0 + lane; x < d1; x += 32) sm[x] = src(x); continue; }
+        if ((u32)lane < w0 - d0) sm[d0 + lane] = src(d0 + lane);
+        if ((u32)lane < d1 - w1) sm[w1 + lane] = src(w1 + lane);
+        for (u32 x = w0 + 4u * lane; x < w1; x += 128u) {
+            const u32 j = x + lo - off;                       /* source index of the word's first byte */
+            const u8* g = rev ? q + (rl - 4u - j) : q + j;
+            const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
+            const u32* al = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
+            const u32 sh = (u32)(ga & 3u) * 8u;
+            u32 w = al[0];
+            if (sh) w = __funnelshift_r(w, al[1], sh);
+            if (rev) w = __byte_perm(w, 0, 0x0123);
+            smw[x >> 2] = w;
+        }
+    }
+}
+
+struct RunCtx {
+    const u8* sm; u32 sm_lo, n, lo, s, e;
+    const u8* lut; u32 mode, nstreams; int tid;
+};
+
+/* replay the runs of one 64-position segment; WRITE: emit token bytes, else count them */
+template <bool WRITE>
+__device__ inline void s3_runs(const RunCtx& R, u64 nm, const u64 eq, const S2Tables& T, u8* slot, const EncBatchDev& b, const ChunkDev& ck) {
+    auto at = [&](u32 p) -> u8 { return p >= R.sm_lo ? R.sm[p - R.sm_lo] : stream_byte_slow(b, ck, R.mode, p); };
+    const u32 exc_stream = R.nstreams - 1;
+    while (nm) {
+        const int i = __ffsll((long long)nm) - 1;
+        const u32 p = R.s + (u32)i;
+        const u8 v = R.sm[p - R.sm_lo];
+        int lin = 1 + eq_run(eq, i + 1);                       /* positions of the run inside the 64-bit window */
+        if ((u32)i + (u32)lin > R.e - R.s) lin = (int)(R.e - R.s) - i;
+        nm &= ~((lin >= 64 ? ~0ull : ((1ull << lin) - 1ull)) << i);
+        const u8 cls = R.mode == 0 ? R.lut[v] : (u8)0;
+        if (cls == LUT_EXC) {
+            /* every position of the run inside the segment is an exception record {q, u32 LE pos} */
+            const u32 idx = exc_stream * S2_THREADS + R.tid;
+            u32 off = T.cnt[idx];
+            for (u32 q = p; q < p + (u32)lin; q++) {
+                if (WRITE) { u8* o = slot + off; o[0] = v; o[1] = (u8)q; o[2] = (u8)(q >> 8); o[3] = (u8)(q >> 16); o[4] = (u8)(q >> 24); }
+                off += 5;
+            }
+            T.cnt[idx] = off;
+            continue;
+        }
+        if (cls == LUT_SKIP) continue;                          /* only when the major quality is not a stream: never set in NM */
+        const u32 idx = (u32)cls * S2_THREADS + R.tid;
+        /* run end, as far as the tokens headed in this segment need it: at most e + 32 */
+        u32 r_end = p + (u32)lin;
+        if (r_end == R.e) { const u32 lim = R.e + 32u < R.n ? R.e + 32u : R.n; while (r_end < lim && at(r_end) == v) r_end++; }
+        const bool crossing = i == 0 && (eq & 1ull);
+        u32 off = T.cnt[idx];
+        u32 head;
+        if (crossing) {
+            u32 p0 = p - 1; while (p0 > 0 && at(p0 - 1) == v) p0--;
+            const u32 s0 = p0 == 0 ? 2u : 1u;
+            head = p0 + s0;
+            if (head < p) head += ((p - head + 31u) / 32u) * 32u;
+        } else {
+            /* distance token at the run start */
+            const u32 lastrel = T.last[idx];
+            u32 dm1 = 0; bool emit = true;
+            if (lastrel != S2_NONE) dm1 = p - (R.lo + lastrel) - 1u;
+            else if (p == 0) dm1 = 0;
+            else {
+                const u32 f = T.first[idx];
+                if (WRITE && (f & S2_RESOLVED)) dm1 = T.fdist[idx];
+                else { emit = false; if (!WRITE) T.first[idx] = (u16)(p - R.lo); }
+            }
+            if (emit) {
+                if (dm1 < 128u) { if (WRITE) slot[off] = (u8)dm1; off += 1; }
+                else if (dm1 < (1u << 14)) { if (WRITE) { slot[off] = (u8)(0x80u | (dm1 >> 8)); slot[off + 1] = (u8)dm1; } off += 2; }
+                else { if (WRITE) { slot[off] = (u8)(0xE0u | (dm1 >> 24)); slot[off + 1] = (u8)(dm1 >> 16); slot[off + 2] = (u8)(dm1 >> 8); slot[off + 3] = (u8)dm1; } off += 4; }
+            }
+            if (p == 0 && r_end > 1 && 1u < R.e) { if (WRITE) slot[off] = 0x00; off += 1; }       /* Q16 */
+            head = p + (p == 0 ? 2u : 1u);
+        }
+        const u32 stop = r_end < R.e ? r_end : R.e;
+        for (; head < stop; head += 32u) {
+            const u32 len = r_end - head < 32u ? r_end - head : 32u;
+            if (WRITE) slot[off] = (u8)(0xC0u | (len - 1u));
+            off += 1;
+        }
+        T.cnt[idx] = off;
+        T.last[idx] = (u16)(stop - 1u - R.lo);
+    }
+}
+
+__global__ void __launch_bounds__(S2_THREADS) k_streams3(EncBatchDev b, HeaderDev h, StreamJob job, const u32* __restrict__ span_chunk) {
+    RPQ_DYN_SMEM(dyn);
+    __shared__ u8 s_lut[256];
+    __shared__ u32 s_total[MAX_BINS + 2];
+    __shared__ u32 s_base[MAX_BINS + 2];
+    __shared__ u64 s_slot;
+    __shared__ u32 s_bytes;
+    const u32 span = blockIdx.x;
+    if (span >= *job.n_spans) return;
+    const u32 c = span_chunk[span];
+    const ChunkDev& ck = b.chunks[c];
+    const u32 mode = job.mode;
+    const u32 n = mode ? ck.seq_kept : ck.total_len;
+    const u32 lo = (span - job.span_first[c]) * ST_SPAN;
+    const u32 hi = lo + ST_SPAN < n ? lo + ST_SPAN : n;
+    const u32 sm_lo = lo >= ST_HALO ? lo - ST_HALO : 0, sm_hi = hi + ST_HALO < n ? hi + ST_HALO : n;
+    const u32 nstreams = job.nstreams;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u8* sm = dyn;
+    S2Tables T;
+    T.cnt = reinterpret_cast<u32*>(dyn + ST_SPAN + 2 * ST_HALO);
+    T.first = reinterpret_cast<u16*>(T.cnt + nstreams * S2_THREADS);
+    T.last = T.first + nstreams * S2_THREADS;
+    T.fdist = T.last + nstreams * S2_THREADS;
+
+    s_lut[tid] = h.lut[tid];
+    for (u32 k = tid; k < nstreams * S2_THREADS; k += S2_THREADS) { T.cnt[k] = 0; T.first[k] = (u16)S2_NONE; T.last[k] = (u16)S2_NONE; T.fdist[k] = 0; }
+    for (u32 k = tid; k < 8; k += S2_THREADS) if (sm_hi - sm_lo + k < (u32)(ST_SPAN + 2 * ST_HALO)) sm[sm_hi - sm_lo + k] = mode == 0 ? h.major : (u8)0;
+    if (mode == 0) stage_quality_words(b, ck, sm_lo, sm_hi, sm);
+    else stage_positions(b, h, ck, mode, sm_lo, sm_hi, sm);
+    __syncthreads();
+
+    /* ---- masks of the thread's 64 positions */
+    const u32 s = lo + (u32)tid * S2_SEG;
+    const u32 e = s + S2_SEG < hi ? s + S2_SEG : hi;
+    u64 nm = 0, eq = 0;
+    if (s < hi) {
+        const u32* W = reinterpret_cast<const u32*>(sm + (s - sm_lo));
+        const bool major_is_stream = mode == 0 && s_lut[h.major] != LUT_SKIP;
+        const u32 mmmm = 0x01010101u * h.major;
+        u32 prevb = s > 0 ? (u32)sm[s - 1 - sm_lo] : 0x100u;
+#pragma unroll
+        for (int j = 0; j < S2_SEG / 4; j++) {
+            const u32 w = W[j];
+            const u32 shifted = (w << 8) | (prevb & 0xFFu);
+            u32 e4 = pack4(__vcmpeq4(w, shifted));
+            if (j == 0 && prevb > 0xFFu) e4 &= ~1u;
+            const u32 n4 = mode == 0 ? (major_is_stream ? 0xFu : pack4(__vcmpne4(w, mmmm))) : pack4(__vcmpeq4(w, 0x4E4E4E4Eu));
+            nm |= (u64)n4 << (4 * j); eq |= (u64)e4 << (4 * j);
+            prevb = w >> 24;
+        }
+        const u32 valid = e - s;
+        if (valid < 64u) nm &= (1ull << valid) - 1ull;
+    }
+    RunCtx R; R.sm = sm; R.sm_lo = sm_lo; R.n = n; R.lo = lo; R.s = s; R.e = e; R.lut = s_lut; R.mode = mode; R.nstreams = nstreams; R.tid = tid;
+    if (nm) s3_runs<false>(R, nm, eq, T, nullptr, b, ck);
+    __syncthreads();
+
+    /* per stream (a warp each): resolve first tokens against earlier segments of the span, exclusive scan of the byte counts */
+    for (u32 st = warp; st < nstreams; st += S2_THREADS / 32) {
+        const u32 base = st * S2_THREADS + lane * 8;
+        u32 lastv[8]; u32 lane_last = S2_NONE;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { lastv[k] = T.last[base + k]; if (lastv[k] != S2_NONE) lane_last = lastv[k]; }
+        u32 incl = lane_last;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d && incl == S2_NONE) incl = t; }
+        u32 prev = __shfl_up_sync(0xffffffffu, incl, 1); if (lane == 0) prev = S2_NONE;
+        u32 cntv[8]; u32 lane_sum = 0; u32 span_first = S2_NONE;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            u32 cv = T.cnt[base + k];
+            const u32 f = T.first[base + k];
+            if (f != S2_NONE) {
+                if (prev != S2_NONE) { const u32 dm1 = f - prev - 1u; cv += distance_len(dm1); T.first[base + k] = (u16)(f | S2_RESOLVED); T.fdist[base + k] = (u16)dm1; }
+                else span_first = f;
+            }
+            if (lastv[k] != S2_NONE) prev = lastv[k];
+            cntv[k] = cv; lane_sum += cv;
+        }
+        u32 tot; const u32 ex = warp_excl_scan(lane_sum, lane, tot);
+        u32 run = ex;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { T.cnt[base + k] = run; run += cntv[k]; }
+        const u32 sf = warp_min(span_first);
+        const u32 sl = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) {
+            s_total[st] = tot;
+            SpanDir d; d.bytes = tot; d.slot_off = 0; d.firstpos = sf == S2_NONE ? NONE32 : lo + sf; d.lastpos = sl == S2_NONE ? NONE32 : lo + sl;
+            d.dst = 0; d.first_tok = 0; d.first_len = 0; d.pad = 0;
+            job.dir[(size_t)span * nstreams + st] = d;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        u32 acc = 0;
+        for (u32 st = 0; st < nstreams; st++) { s_base[st] = acc; acc += s_total[st]; }
+        s_bytes = acc;
+        const u64 at = atomicAdd(job.slot_cursor, (u64)acc);
+        job.span_slot[span] = at;
+        if (at + acc > job.slot_cap) { atomicOr(job.overflow, 1u); s_slot = ~0ull; } else s_slot = at;
+    }
+    __syncthreads();
+    if (s_slot == ~0ull) return;
+    for (u32 st = tid; st < nstreams; st += S2_THREADS) job.dir[(size_t)span * nstreams + st].slot_off = s_base[st];
+    for (u32 k = tid; k < nstreams * S2_THREADS; k += S2_THREADS) { T.cnt[k] += s_base[k / S2_THREADS]; T.last[k] = (u16)S2_NONE; }
+    __syncthreads();
+    if (nm && s_bytes) s3_runs<true>(R, nm, eq, T, job.slots + s_slot, b, ck);
+}
+
+}  // namespace rpq
