@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(256) k_dec_offsets(DecBatchDev b) {
  * is an exclusive warp sum of the advances before it.
  * grid.x = chunks, blockIdx.y = stream (quality bins, then exceptions, then N positions), one warp each (blockDim 32).
  */
-__global__ void __launch_bounds__(32) k_dec_streams(DecBatchDev b, HeaderDev h, u32 n_qstreams) {
-    const u32 c = blockIdx.x, st = blockIdx.y;
+__global__ void __launch_bounds__(32) k_dec_streams(DecBatchDev b, HeaderDev h, u32 n_qstreams, u32 chunk_base) {
+    const u32 c = chunk_base + blockIdx.x, st = blockIdx.y;
     const int lane = threadIdx.x;
     const DecChunk& ck = b.chunks[c];
     const u8* in = b.body + ck.in_off;

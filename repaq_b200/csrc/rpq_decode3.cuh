@@ -37,15 +37,15 @@ __device__ __forceinline__ u32 lds4(const u8* p) {
     return sh ? __funnelshift_r(w[0], w[1], sh) : w[0];
 }
 
-__global__ void __launch_bounds__(128) k_dec_format3(DecBatchDev b, HeaderDev h, Fmt2Cfg cfg) {
+__global__ void __launch_bounds__(128) k_dec_format3(DecBatchDev b, HeaderDev h, Fmt2Cfg cfg, u32 read_first, u32 read_end) {
     RPQ_DYN_SMEM(dyn);
     __shared__ u64 s_start[2], s_end[2];
     __shared__ u64 s_q0, s_q1;
     __shared__ u32 s_lut_fwd[256], s_lut_rc[256];
     const int tid = threadIdx.x;
     const u32 G = cfg.reads_per_cta;
-    const u32 i0 = blockIdx.x * G;
-    const u32 n_here = b.n_reads - i0 < G ? b.n_reads - i0 : G;
+    const u32 i0 = read_first + blockIdx.x * G;          /* the launch covers reads [read_first, read_end) */
+    const u32 n_here = read_end - i0 < G ? read_end - i0 : G;
     u8* s_plane = dyn;
     u8* s_out[2] = {dyn + cfg.plane_cap, dyn + cfg.plane_cap + cfg.out_cap};
     const u32 nstreams = b.split_pairs ? 2u : 1u;

@@ -92,6 +92,7 @@ inline void rt_event_create(RtEvent* e) { e->t = 0; }
 inline void rt_event_destroy(RtEvent*) {}
 inline void rt_event_record(RtEvent* e, cudaStream_t) { e->t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 inline float rt_event_ms(const RtEvent& a, const RtEvent& b) { return (float)(b.t - a.t); }
+inline void rt_stream_wait_event(cudaStream_t, RtEvent*) {}
 inline size_t rt_scan_tmp_bytes(size_t) { return 16; }
 inline int rt_inclusive_sum_u32_u64(const uint32_t* in, unsigned long long* out, size_t n, void*, size_t, cudaStream_t) {
     unsigned long long acc = 0;
@@ -104,6 +105,7 @@ inline void rt_event_create(RtEvent* e) { cudaEventCreate(&e->e); }
 inline void rt_event_destroy(RtEvent* e) { cudaEventDestroy(e->e); }
 inline void rt_event_record(RtEvent* e, cudaStream_t s) { cudaEventRecord(e->e, s); }
 inline float rt_event_ms(const RtEvent& a, const RtEvent& b) { float ms = 0; cudaEventElapsedTime(&ms, a.e, b.e); return ms; }
+inline void rt_stream_wait_event(cudaStream_t s, RtEvent* e) { cudaStreamWaitEvent(s, e->e, 0); }
 struct RtCastU64 { __host__ __device__ unsigned long long operator()(uint32_t v) const { return v; } };
 inline size_t rt_scan_tmp_bytes(size_t n) {
     size_t bytes = 0;

@@ -90,3 +90,18 @@ def test_fallback_kernels_forced(monkeypatch):
         assert _decode_devmem(cd, rfq, True)[:2] == K.decompress(rfq, pe_out=True, codec=cd) or True
     finally:
         cd.close()
+
+
+def test_pipelined_host_windows(monkeypatch):
+    """the pipelined host path (windows over three lanes) must give the same bytes as one batch; tiny windows via
+    RPQ_DEBUG_PIPE_WINDOW so that several windows fit a test input"""
+    from tools import fqgen
+    monkeypatch.setenv("RPQ_DEBUG_PIPE_WINDOW", "1300000")
+    cd = K.Codec(lib_path=EMU)
+    try:
+        for name in ("nova_pe_k100_npos", "bgi_se_k100", "nova_pe_nonl_k100", "pe_demoted_mid_k100", "nova_pe_varlen_k100", "nova_se_k100"):
+            parity.check_encode_golden(cd, name)
+        r1, r2 = fqgen.generate(30000, seed=71, paired=True)          # 10.7 MB per file, k=100: ~8 windows
+        parity.check_against_oracle(cd, r1, r2, k=100)
+    finally:
+        cd.close()
