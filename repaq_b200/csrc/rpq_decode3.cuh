@@ -14,19 +14,27 @@
 
 namespace rpq {
 
-/* sequential byte sink into shared memory: aligned 32-bit stores once the destination is aligned */
+/* sequential byte sink into shared memory: after the first (unaligned) bytes every put4 is one aligned 32-bit store */
 struct Sink {
-    u8* dst; u64 acc; u32 n;
-    __device__ __forceinline__ void init(u8* d) { dst = d; acc = 0; n = 0; }
-    __device__ __forceinline__ void drain() {
-        while (n >= 4u) {
-            if ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0) { *reinterpret_cast<u32*>(dst) = (u32)acc; dst += 4; acc >>= 32; n -= 4u; }
-            else { *dst++ = (u8)acc; acc >>= 8; n -= 1u; }
+    u8* dst; u32 res, nres, need;
+    __device__ __forceinline__ void init(u8* d) { dst = d; res = 0; nres = 0; need = (4u - (u32)(reinterpret_cast<uintptr_t>(d) & 3u)) & 3u; }
+    __device__ __forceinline__ void put4(u32 w) {
+        if (need) {
+            for (u32 k = 0; k < need; k++) dst[k] = (u8)(w >> (8u * k));
+            dst += need; res = w >> (8u * need); nres = 4u - need; need = 0;
+            return;
         }
+        if (nres == 0) { *reinterpret_cast<u32*>(dst) = w; dst += 4; return; }
+        *reinterpret_cast<u32*>(dst) = res | (w << (8u * nres));
+        dst += 4;
+        res = w >> (8u * (4u - nres));
     }
-    __device__ __forceinline__ void put4(u32 w) { acc |= (u64)w << (8u * n); n += 4u; drain(); }
-    __device__ __forceinline__ void put1(u8 c) { acc |= (u64)c << (8u * n); n += 1u; drain(); }
-    __device__ __forceinline__ void flush() { while (n) { *dst++ = (u8)acc; acc >>= 8; n -= 1u; } }
+    __device__ __forceinline__ void put1(u8 c) {
+        if (need) { *dst++ = c; need--; return; }
+        res |= (u32)c << (8u * nres); nres++;
+        if (nres == 4u) { *reinterpret_cast<u32*>(dst) = res; dst += 4; res = 0; nres = 0; }
+    }
+    __device__ __forceinline__ void flush() { for (u32 k = 0; k < nres; k++) dst[k] = (u8)(res >> (8u * k)); dst += nres; nres = 0; res = 0; }
 };
 
 /* 4 bytes at any byte address of shared memory */
@@ -37,12 +45,13 @@ __device__ __forceinline__ u32 lds4(const u8* p) {
     return sh ? __funnelshift_r(w[0], w[1], sh) : w[0];
 }
 
-__global__ void __launch_bounds__(128) k_dec_format3(DecBatchDev b, HeaderDev h, Fmt2Cfg cfg, u32 read_first, u32 read_end) {
+__global__ void __launch_bounds__(256) k_dec_format3(DecBatchDev b, HeaderDev h, Fmt2Cfg cfg, u32 read_first, u32 read_end) {
     RPQ_DYN_SMEM(dyn);
     __shared__ u64 s_start[2], s_end[2];
     __shared__ u64 s_q0, s_q1;
     __shared__ u32 s_lut_fwd[256], s_lut_rc[256];
     const int tid = threadIdx.x;
+    const int rt = tid >> 1, half = tid & 1;            /* two threads per read: half 0 name + sequence line, half 1 strand + quality line */
     const u32 G = cfg.reads_per_cta;
     const u32 i0 = read_first + blockIdx.x * G;          /* the launch covers reads [read_first, read_end) */
     const u32 n_here = read_end - i0 < G ? read_end - i0 : G;
@@ -63,8 +72,8 @@ __global__ void __launch_bounds__(128) k_dec_format3(DecBatchDev b, HeaderDev h,
     }
     if (tid < 2) { s_start[tid] = ~0ull; s_end[tid] = 0; }
     __syncthreads();
-    const bool active = tid < (int)n_here;
-    const u32 i = i0 + tid;
+    const bool active = rt < (int)n_here;
+    const u32 i = i0 + rt;
     u32 c = 0, r = 0, rl = 0, stream = 0, olen = 0;
     u64 oabs = 0, qabs = 0;
     if (active) {
@@ -74,10 +83,12 @@ __global__ void __launch_bounds__(128) k_dec_format3(DecBatchDev b, HeaderDev h,
         stream = b.split_pairs ? (r & 1u) : 0u;
         oabs = ck.out_off[stream] + b.outoff[i];
         qabs = ck.plane_off + b.qualoff[i];
-        if ((u32)tid < nstreams) s_start[stream] = oabs;
-        if ((u32)tid + nstreams >= n_here) s_end[stream] = oabs + olen;
-        if (tid == 0) s_q0 = qabs;
-        if ((u32)tid == n_here - 1) s_q1 = qabs + rl;
+        if (half == 0) {
+            if ((u32)rt < nstreams) s_start[stream] = oabs;
+            if ((u32)rt + nstreams >= n_here) s_end[stream] = oabs + olen;
+            if (rt == 0) s_q0 = qabs;
+            if ((u32)rt == n_here - 1) s_q1 = qabs + rl;
+        }
     }
     __syncthreads();
     const u64 q0 = s_q0, q1 = s_q1, qa = q0 & ~15ull;
@@ -99,6 +110,10 @@ __global__ void __launch_bounds__(128) k_dec_format3(DecBatchDev b, HeaderDev h,
         const u32 xy = il ? r >> 1 : r;
         u8* o = s_out[stream] + (u32)(oabs - (s_start[stream] & ~15ull));
         const u8* q = s_plane + (u32)(qabs - qa);
+        /* ---- strand length first: it fixes where every part of the record lies */
+        const u32 ls = (fl & (RPQ_STRAND_SAME | RPQ_STRAND_LEN_SAME)) ? in[ck.off_slen] : in[ck.off_slen + r];
+        const u32 name_end = olen - (2u * rl + ls + 3u);          /* bytes of the name line including its line break */
+        if (half == 0) {
         u32 w_at = 0;
         /* ---- name (reference src/rfqcodec.cpp:1157-1231) */
         const u32 l1 = (fl & (RPQ_NAME1_SAME | RPQ_NAME1_LEN_SAME)) ? in[ck.off_n1len] : in[ck.off_n1len + r];
@@ -117,16 +132,17 @@ __global__ void __launch_bounds__(128) k_dec_format3(DecBatchDev b, HeaderDev h,
             w_at += l2;
         }
         o[w_at++] = '\n';
-        /* ---- strand goes between the two lines; copy it first, it is short */
-        const u32 ls = (fl & (RPQ_STRAND_SAME | RPQ_STRAND_LEN_SAME)) ? in[ck.off_slen] : in[ck.off_slen + r];
+        }
         const u8* sp = in + ck.off_strand + ((fl & RPQ_STRAND_SAME) ? 0u : b.soff[i]);
-        u8* o_seq = o + w_at;
+        u8* o_seq = o + name_end;
         u8* o_str = o_seq + rl + 1;
         u8* o_qual = o_str + ls + 1;
-        o_seq[rl] = '\n';
-        for (u32 k = 0; k < ls; k++) o_str[k] = sp[k];
-        o_str[ls] = '\n';
-        o_qual[rl] = '\n';
+        if (half == 0) o_seq[rl] = '\n';
+        else {
+            for (u32 k = 0; k < ls; k++) o_str[k] = sp[k];
+            o_str[ls] = '\n';
+            o_qual[rl] = '\n';
+        }
 
         /* ---- sequence + quality, four positions per step */
         const u8* seqb = in + ck.off_seq;
@@ -152,39 +168,49 @@ __global__ void __launch_bounds__(128) k_dec_format3(DecBatchDev b, HeaderDev h,
             else if (q[rc ? rl - 1 - jo : jo] == nq) base = 'N';
             return rc ? complement_base(base) : base;
         };
-        Sink ss, qs; ss.init(o_seq); qs.init(o_qual);
         const u32 ngroups = rl >> 2;
-        for (u32 g = 0; g < ngroups; g++) {
-            const u32 jo = 4u * g;
-            /* quality word in output order */
-            u32 qw = rc ? __byte_perm(lds4(q + (rl - 4u - jo)), 0, 0x0123) : lds4(q + jo);
-            qs.put4(qw);
-            /* bases */
-            const bool piece_a = jo + 3u < bnd, piece_b = jo >= bnd;
-            const long long cbase = piece_a ? cA : cB;
-            const long long ci_lo = rc ? cbase - (long long)jo - 3 : cbase + (long long)jo;
-            u32 bw;
-            if ((piece_a || piece_b) && ci_lo >= 0 && ci_lo + 3 < unpacked) {
-                const u32 k = (u32)(ci_lo >> 2), ph = 2u * (u32)(ci_lo & 3);
-                const u32 two = (u32)seqb[k] | (ph ? (u32)seqb[k + 1] << 8 : 0u);
-                const u32 code8 = (two >> ph) & 0xFFu;
-                bw = rc ? s_lut_rc[code8] : s_lut_fwd[code8];
-                u32 mask;
-                if (npos_mode) {
-                    const u32 wi = (u32)(ci_lo >> 5), bp = (u32)(ci_lo & 31);
-                    u32 m4 = (nmap[wi] >> bp) & 0xFu;
-                    if (bp > 28u) m4 |= (nmap[wi + 1] << (32u - bp)) & 0xFu;
-                    if (rc) m4 = ((m4 & 1u) << 3) | ((m4 & 2u) << 1) | ((m4 & 4u) >> 1) | ((m4 & 8u) >> 3);
-                    mask = ((m4 | (m4 << 7) | (m4 << 14) | (m4 << 21)) & 0x01010101u) * 0xFFu;
-                } else mask = __vcmpeq4(qw, nq4);
-                bw = (bw & ~mask) | (0x4E4E4E4Eu & mask);
-            } else {
-                bw = (u32)slow_base(jo) | ((u32)slow_base(jo + 1) << 8) | ((u32)slow_base(jo + 2) << 16) | ((u32)slow_base(jo + 3) << 24);
+        if (half == 1) {
+            /* quality line (reversed for the reverse strand) */
+            Sink qs; qs.init(o_qual);
+            for (u32 g = 0; g < ngroups; g++) {
+                const u32 jo = 4u * g;
+                qs.put4(rc ? __byte_perm(lds4(q + (rl - 4u - jo)), 0, 0x0123) : lds4(q + jo));
             }
-            ss.put4(bw);
+            for (u32 jo = ngroups * 4u; jo < rl; jo++) qs.put1(q[rc ? rl - 1 - jo : jo]);
+            qs.flush();
+        } else {
+            Sink ss; ss.init(o_seq);
+            for (u32 g = 0; g < ngroups; g++) {
+                const u32 jo = 4u * g;
+                const bool piece_a = jo + 3u < bnd, piece_b = jo >= bnd;
+                const long long cbase = piece_a ? cA : cB;
+                const long long ci_lo = rc ? cbase - (long long)jo - 3 : cbase + (long long)jo;
+                u32 bw;
+                if ((piece_a || piece_b) && ci_lo >= 0 && ci_lo + 3 < unpacked) {
+                    const u32 k = (u32)(ci_lo >> 2), ph = 2u * (u32)(ci_lo & 3);
+                    const u32 two = (u32)seqb[k] | (ph ? (u32)seqb[k + 1] << 8 : 0u);
+                    const u32 code8 = (two >> ph) & 0xFFu;
+                    bw = rc ? s_lut_rc[code8] : s_lut_fwd[code8];
+                    u32 mask;
+                    if (npos_mode) {
+                        const u32 wi = (u32)(ci_lo >> 5), bp = (u32)(ci_lo & 31);
+                        u32 m4 = (nmap[wi] >> bp) & 0xFu;
+                        if (bp > 28u) m4 |= (nmap[wi + 1] << (32u - bp)) & 0xFu;
+                        if (rc) m4 = ((m4 & 1u) << 3) | ((m4 & 2u) << 1) | ((m4 & 4u) >> 1) | ((m4 & 8u) >> 3);
+                        mask = ((m4 | (m4 << 7) | (m4 << 14) | (m4 << 21)) & 0x01010101u) * 0xFFu;
+                    } else {
+                        const u32 qw = rc ? __byte_perm(lds4(q + (rl - 4u - jo)), 0, 0x0123) : lds4(q + jo);
+                        mask = __vcmpeq4(qw, nq4);
+                    }
+                    bw = (bw & ~mask) | (0x4E4E4E4Eu & mask);
+                } else {
+                    bw = (u32)slow_base(jo) | ((u32)slow_base(jo + 1) << 8) | ((u32)slow_base(jo + 2) << 16) | ((u32)slow_base(jo + 3) << 24);
+                }
+                ss.put4(bw);
+            }
+            for (u32 jo = ngroups * 4u; jo < rl; jo++) ss.put1(slow_base(jo));
+            ss.flush();
         }
-        for (u32 jo = ngroups * 4u; jo < rl; jo++) { ss.put1(slow_base(jo)); qs.put1(q[rc ? rl - 1 - jo : jo]); }
-        ss.flush(); qs.flush();
     }
     __syncthreads();
     for (u32 s = 0; s < nstreams; s++) {

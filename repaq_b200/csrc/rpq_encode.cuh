@@ -501,6 +501,7 @@ struct StreamJob {                   /* one per kind (quality / N positions) */
     u64* span_slot;                  /* [spans] where each span's bytes start in `slots` */
     u32* overflow;                   /* set when slot_cap was too small: the host grows it and repeats the batch */
     const u32* n_spans;              /* actual number of spans (the grid is an upper bound) */
+    u32* span_read0;                 /* [spans] chunk-relative index of the first read whose positions reach into the span's staging window */
     u32 nstreams;                    /* nb + 1 (exceptions) for quality; 1 for N positions */
     u32 mode;                        /* 0 quality, 1 N positions */
 };
@@ -882,6 +883,20 @@ __global__ void __launch_bounds__(256) k_span_plan(EncBatchDev b, u32 mode, u32*
         __syncthreads();
     }
     if (tid == 0) { span_first[b.n_chunks] = s_carry; *n_spans = s_carry < cap ? s_carry : cap; }
+}
+
+/* first read of every span's staging window [lo - ST_HALO, ...): one thread per span, off the critical path of k_streams3 */
+__global__ void k_span_reads(EncBatchDev b, StreamJob job, const u32* __restrict__ span_chunk) {
+    const u32 span = blockIdx.x * blockDim.x + threadIdx.x;
+    if (span >= *job.n_spans) return;
+    const u32 c = span_chunk[span];
+    const ChunkDev& ck = b.chunks[c];
+    const u32 lo = (span - job.span_first[c]) * ST_SPAN;
+    const u32 sm_lo = lo >= ST_HALO ? lo - ST_HALO : 0;
+    const u32* offs = job.mode ? b.seqoff : b.qualoff;
+    u32 a = 0, z = ck.count;
+    while (z - a > 1) { const u32 mid = (a + z) >> 1; if (offs[ck.first + mid] <= sm_lo) a = mid; else z = mid; }
+    job.span_read0[span] = a;
 }
 
 /* ================================================================== emit ==== */

@@ -3,7 +3,7 @@
  * CTA re-maps its threads per phase so that twice as many threads share the same shared-memory footprint, and the overlap
  * search does three instructions per candidate:
  *
- *   stage   warp per record: name + sequence + strand lines -> fixed slots (word copies, source byte phase kept)
+ *   stage   one TMA bulk copy (cp.async.bulk, mbarrier byte counting) per record: name + sequence + strand lines -> its slot
  *   A       thread per READ : FastqMeta::parse (reference src/fastqmeta.cpp:22-80), comparisons with the chunk's first read
  *                             (src/rfqcodec.cpp:225-234)
  *   A2      thread per PAIR : the PE consistency test (src/rfqcodec.cpp:233-270, Q10)
@@ -142,19 +142,49 @@ __global__ void __launch_bounds__(256) k_meta3(EncBatchDev b, HeaderDev h, u32 n
     short* s_ov = reinterpret_cast<short*>(s_flag + (((size_t)P * per + 3) & ~(size_t)3));   /* [P*2] per direction */
     const bool rc_odd = b.is_pe && h.support_interleaved;
 
+    /* ---- stage: one TMA bulk copy (cp.async.bulk global -> shared, 16-byte granules) per record head, all in flight at once,
+     * completion counted in bytes on one mbarrier.  The source's 16-byte phase is kept inside the slot. */
+#ifdef RPQ_EMU
     for (u32 r = warp; r < n_reads_here; r += nwarps) {
         const u32 i = u0 * per + r;
         const uint4 lc = b.loc[i];
         u32 f, rec; read_locus(b, i, f, rec);
-        const u8* text = b.t[f].text;
-        const u32 head = lc.w - lc.x;
-        const u32 a0 = lc.x & ~3u;
-        const u32 nw = ((lc.x & 3u) + head + 3u) >> 2;
-        const u32* src = reinterpret_cast<const u32*>(text + a0);
-        u32* dst = slots + (size_t)r * cfg.slot_words;
-        for (u32 k = lane; k < nw && k < cfg.slot_words; k += 32) dst[k] = src[k];
+        const u8* src = b.t[f].text + (lc.x & ~15u);
+        const u32 nb = (((lc.x & 15u) + (lc.w - lc.x) + 15u) >> 4) << 4;
+        u8* dst = reinterpret_cast<u8*>(slots + (size_t)r * cfg.slot_words);
+        for (u32 k = lane; k < nb && k < cfg.slot_words * 4u; k += 32) dst[k] = src[k];
+    }
+    (void)nwarps;
+    __syncthreads();
+#else
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const u32 mbar = (u32)__cvta_generic_to_shared(&s_mbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(mbar), "r"(n_reads_here) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if ((u32)tid < n_reads_here) {
+        const u32 r = tid, i = u0 * per + r;
+        const uint4 lc = b.loc[i];
+        u32 f, rec; read_locus(b, i, f, rec);
+        const u8* src = b.t[f].text + (lc.x & ~15u);
+        u32 nb = (((lc.x & 15u) + (lc.w - lc.x) + 15u) >> 4) << 4;
+        if (nb > cfg.slot_words * 4u) nb = cfg.slot_words * 4u;
+        const u32 dst = (u32)__cvta_generic_to_shared(slots + (size_t)r * cfg.slot_words);
+        asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(mbar), "r"(nb) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "r"(nb), "r"(mbar) : "memory");
+    }
+    {
+        u32 done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mbar) : "memory");
+        }
+    }
+    (void)lane; (void)warp; (void)nwarps;
+#endif
 
     /* ---- A: thread per read */
     if ((u32)tid < n_reads_here) {
@@ -172,7 +202,7 @@ __global__ void __launch_bounds__(256) k_meta3(EncBatchDev b, HeaderDev h, u32 n
         u32 f, rec; read_locus(b, i, f, rec);
         const u32 crlf = b.t[f].crlf;
         const u32* words = slots + (size_t)r * cfg.slot_words;
-        const u8* bytes = reinterpret_cast<const u8*>(words) + (lc.x & 3u);
+        const u8* bytes = reinterpret_cast<const u8*>(words) + (lc.x & 15u);
         const int nlen = (int)(lc.y - lc.x - 1u - crlf);
         const int rlen = (int)(lc.z - lc.y - 1u - crlf);
         const int slen = (int)(lc.w - lc.z - 1u - crlf);
@@ -180,7 +210,7 @@ __global__ void __launch_bounds__(256) k_meta3(EncBatchDev b, HeaderDev h, u32 n
         m.strand_len = (u8)slen;
         b.meta[i] = m;
         s_meta[r] = m;
-        s_seq[r] = ((lc.x & 3u) + (lc.y - lc.x)) | ((u32)rlen << 16);
+        s_seq[r] = ((lc.x & 15u) + (lc.y - lc.x)) | ((u32)rlen << 16);
         u32 clear = 0;
         if ((u32)rlen != rlen0) clear |= AB_READ_LEN;
         if (m.name1_len != m0.name1_len) clear |= AB_N1LEN;
@@ -212,8 +242,8 @@ __global__ void __launch_bounds__(256) k_meta3(EncBatchDev b, HeaderDev h, u32 n
             ChunkDev& ck = b.chunks[c];
             const u32 rel = i0 - b.chunk_first[c];
             const ReadMeta ma = s_meta[2 * tid], mb = s_meta[2 * tid + 1];
-            const u8* n1 = reinterpret_cast<const u8*>(slots + (size_t)(2 * tid) * cfg.slot_words) + (b.loc[i0].x & 3u) + ma.name2_off;
-            const u8* n2 = reinterpret_cast<const u8*>(slots + (size_t)(2 * tid + 1) * cfg.slot_words) + (b.loc[i0 + 1].x & 3u) + mb.name2_off;
+            const u8* n1 = reinterpret_cast<const u8*>(slots + (size_t)(2 * tid) * cfg.slot_words) + (b.loc[i0].x & 15u) + ma.name2_off;
+            const u8* n2 = reinterpret_cast<const u8*>(slots + (size_t)(2 * tid + 1) * cfg.slot_words) + (b.loc[i0 + 1].x & 15u) + mb.name2_off;
             const int l1 = (int)ma.name_len - (int)ma.name2_off, l2 = (int)mb.name_len - (int)mb.name2_off;
             bool okA = l1 == l2;
             for (int q = 0; okA && q < l1; q++) { u8 ch = n1[q]; if (h.name2_diff_char != 0 && q == (int)h.name2_diff_pos) ch = h.name2_diff_char; if (ch != n2[q]) okA = false; }

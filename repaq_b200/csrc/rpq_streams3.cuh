@@ -20,39 +20,44 @@ namespace rpq {
 __device__ __forceinline__ u32 pack4(u32 m) { m &= 0x01010101u; return (m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xFu; }
 __device__ __forceinline__ int eq_run(u64 eq, int k) { if (k >= 64) return 0; const u64 t = ~(eq >> k); return t ? (__ffsll((long long)t) - 1) : (64 - k); }
 
-/* quality bytes of the chunk's positions [lo, hi) into sm[pos - lo]; lo is a multiple of 4; word based */
-__device__ inline void stage_quality_words(const EncBatchDev& b, const ChunkDev& ck, u32 lo, u32 hi, u8* sm) {
+/* quality bytes of the chunk's positions [lo, hi) into sm[pos - lo]; lo is a multiple of 4; word based.
+ * `first_rel` = first read that can reach into the window (k_span_reads).  Each warp takes 32 consecutive reads: the lanes
+ * fetch the reads' offsets / lengths / line starts in parallel, then the warp copies the reads one after the other. */
+__device__ inline void stage_quality_words(const EncBatchDev& b, const ChunkDev& ck, u32 lo, u32 hi, u8* sm, u32 first_rel) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     if (hi <= lo) return;
-    const u32* offs = b.qualoff;
-    u32 a = 0, z = ck.count;
-    while (z - a > 1) { const u32 mid = (a + z) >> 1; if (offs[ck.first + mid] <= lo) a = mid; else z = mid; }
     u32* smw = reinterpret_cast<u32*>(sm);
-    for (u32 rel = a + warp; rel < ck.count; rel += nwarps) {
-        const u32 i = ck.first + rel;
-        const u32 off = offs[i];
-        if (off >= hi) break;
-        const u32 rl = b.rlen[i];
-        if (off + rl <= lo) continue;
-        u32 f, rec; read_locus(b, i, f, rec);
-        const u8* q = b.t[f].text + b.loc[i].w;
-        const bool rev = ck.interleaved && (rel & 1u);
-        const u32 d0 = (off > lo ? off : lo) - lo, d1 = (off + rl < hi ? off + rl : hi) - lo;      /* shared range [d0, d1) */
-        const u32 w0 = (d0 + 3u) & ~3u, w1 = d1 & ~3u;
-        auto src = [&](u32 x) -> u8 { const u32 j = x + lo - off; return rev ? q[rl - 1 - j] : q[j]; };
-        if (w0 >= w1) { for (u32 x = d0 + lane; x < d1; x += 32) sm[x] = src(x); continue; }
-        if ((u32)lane < w0 - d0) sm[d0 + lane] = src(d0 + lane);
-        if ((u32)lane < d1 - w1) sm[w1 + lane] = src(w1 + lane);
-        for (u32 x = w0 + 4u * lane; x < w1; x += 128u) {
-            const u32 j = x + lo - off;                       /* source index of the word's first byte */
-            const u8* g = rev ? q + (rl - 4u - j) : q + j;
-            const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
-            const u32* al = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
-            const u32 sh = (u32)(ga & 3u) * 8u;
-            u32 w = al[0];
-            if (sh) w = __funnelshift_r(w, al[1], sh);
-            if (rev) w = __byte_perm(w, 0, 0x0123);
-            smw[x >> 2] = w;
+    for (u32 base = first_rel + 32u * warp; base < ck.count; base += 32u * nwarps) {
+        const u32 rel_l = base + lane;
+        u32 off_l = 0xFFFFFFFFu, rl_l = 0, qw_l = 0;
+        if (rel_l < ck.count) { const u32 i = ck.first + rel_l; off_l = b.qualoff[i]; rl_l = b.rlen[i]; qw_l = b.loc[i].w; }
+        if (__shfl_sync(0xffffffffu, off_l, 0) >= hi) break;
+        for (int k = 0; k < 32; k++) {
+            const u32 off = __shfl_sync(0xffffffffu, off_l, k);
+            if (off >= hi) break;                                         /* also ends at the padding lanes (off = ~0) */
+            const u32 rl = __shfl_sync(0xffffffffu, rl_l, k), qstart = __shfl_sync(0xffffffffu, qw_l, k);
+            if (off + rl <= lo) continue;
+            const u32 rel = base + (u32)k;
+            const u32 f = (b.is_pe && b.two_files) ? (rel & 1u) : 0u;      /* chunks start at an even read: file = parity */
+            const u8* q = b.t[f].text + qstart;
+            const bool rev = ck.interleaved && (rel & 1u);
+            const u32 d0 = (off > lo ? off : lo) - lo, d1 = (off + rl < hi ? off + rl : hi) - lo;      /* shared range [d0, d1) */
+            const u32 w0 = (d0 + 3u) & ~3u, w1 = d1 & ~3u;
+            auto src = [&](u32 x) -> u8 { const u32 j = x + lo - off; return rev ? q[rl - 1 - j] : q[j]; };
+            if (w0 >= w1) { for (u32 x = d0 + lane; x < d1; x += 32) sm[x] = src(x); continue; }
+            if ((u32)lane < w0 - d0) sm[d0 + lane] = src(d0 + lane);
+            if ((u32)lane < d1 - w1) sm[w1 + lane] = src(w1 + lane);
+            for (u32 x = w0 + 4u * lane; x < w1; x += 128u) {
+                const u32 j = x + lo - off;                       /* source index of the word's first byte */
+                const u8* g = rev ? q + (rl - 4u - j) : q + j;
+                const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
+                const u32* al = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
+                const u32 sh = (u32)(ga & 3u) * 8u;
+                u32 w = al[0];
+                if (sh) w = __funnelshift_r(w, al[1], sh);
+                if (rev) w = __byte_perm(w, 0, 0x0123);
+                smw[x >> 2] = w;
+            }
         }
     }
 }
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams3(EncBatchDev b, HeaderDe
     s_lut[tid] = h.lut[tid];
     for (u32 k = tid; k < nstreams * S2_THREADS; k += S2_THREADS) { T.cnt[k] = 0; T.first[k] = (u16)S2_NONE; T.last[k] = (u16)S2_NONE; T.fdist[k] = 0; }
     for (u32 k = tid; k < 8; k += S2_THREADS) if (sm_hi - sm_lo + k < (u32)(ST_SPAN + 2 * ST_HALO)) sm[sm_hi - sm_lo + k] = mode == 0 ? h.major : (u8)0;
-    if (mode == 0) stage_quality_words(b, ck, sm_lo, sm_hi, sm);
+    if (mode == 0) stage_quality_words(b, ck, sm_lo, sm_hi, sm, job.span_read0[span]);
     else stage_positions(b, h, ck, mode, sm_lo, sm_hi, sm);
     __syncthreads();
 
