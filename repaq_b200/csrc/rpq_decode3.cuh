@@ -51,8 +51,9 @@ __global__ void __launch_bounds__(256) k_dec_format3(DecBatchDev b, HeaderDev h,
     __shared__ u64 s_q0, s_q1;
     __shared__ u32 s_lut_fwd[256], s_lut_rc[256];
     const int tid = threadIdx.x;
-    const int rt = tid >> 1, half = tid & 1;            /* two threads per read: half 0 name + sequence line, half 1 strand + quality line */
     const u32 G = cfg.reads_per_cta;
+    /* two threads per read, in different warps (no divergence): threads [0,G) write name + sequence line, [G,2G) strand + quality line */
+    const int rt = tid < (int)G ? tid : tid - (int)G, half = tid < (int)G ? 0 : 1;
     const u32 i0 = read_first + blockIdx.x * G;          /* the launch covers reads [read_first, read_end) */
     const u32 n_here = read_end - i0 < G ? read_end - i0 : G;
     u8* s_plane = dyn;

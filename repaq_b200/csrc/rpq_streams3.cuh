@@ -21,14 +21,15 @@ __device__ __forceinline__ u32 pack4(u32 m) { m &= 0x01010101u; return (m | (m >
 __device__ __forceinline__ int eq_run(u64 eq, int k) { if (k >= 64) return 0; const u64 t = ~(eq >> k); return t ? (__ffsll((long long)t) - 1) : (64 - k); }
 
 /* quality bytes of the chunk's positions [lo, hi) into sm[pos - lo]; lo is a multiple of 4; word based.
- * `first_rel` = first read that can reach into the window (k_span_reads).  Each warp takes 32 consecutive reads: the lanes
- * fetch the reads' offsets / lengths / line starts in parallel, then the warp copies the reads one after the other. */
+ * `first_rel` = first read that can reach into the window (k_span_reads).  A warp takes every nwarps-th read; its lanes fetch
+ * the offsets / lengths / line starts of 32 of them in parallel, then the warp copies those reads one after the other. */
 __device__ inline void stage_quality_words(const EncBatchDev& b, const ChunkDev& ck, u32 lo, u32 hi, u8* sm, u32 first_rel) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     if (hi <= lo) return;
     u32* smw = reinterpret_cast<u32*>(sm);
-    for (u32 base = first_rel + 32u * warp; base < ck.count; base += 32u * nwarps) {
-        const u32 rel_l = base + lane;
+    /* warp w takes reads first_rel + w + nwarps*k (k = lane within a round of 32): neighbouring reads go to different warps */
+    for (u32 base = first_rel + (u32)warp; base < ck.count; base += 32u * nwarps) {
+        const u32 rel_l = base + (u32)lane * nwarps;
         u32 off_l = 0xFFFFFFFFu, rl_l = 0, qw_l = 0;
         if (rel_l < ck.count) { const u32 i = ck.first + rel_l; off_l = b.qualoff[i]; rl_l = b.rlen[i]; qw_l = b.loc[i].w; }
         if (__shfl_sync(0xffffffffu, off_l, 0) >= hi) break;
@@ -37,7 +38,7 @@ __device__ inline void stage_quality_words(const EncBatchDev& b, const ChunkDev&
             if (off >= hi) break;                                         /* also ends at the padding lanes (off = ~0) */
             const u32 rl = __shfl_sync(0xffffffffu, rl_l, k), qstart = __shfl_sync(0xffffffffu, qw_l, k);
             if (off + rl <= lo) continue;
-            const u32 rel = base + (u32)k;
+            const u32 rel = base + (u32)k * nwarps;
             const u32 f = (b.is_pe && b.two_files) ? (rel & 1u) : 0u;      /* chunks start at an even read: file = parity */
             const u8* q = b.t[f].text + qstart;
             const bool rev = ck.interleaved && (rel & 1u);
