@@ -324,6 +324,12 @@ def main():
         "k_gather": 1.2 * rfq_b,
         "k_dec_format": rfq_b + qual_b + fastq_bytes, "k_dec_format2": rfq_b + qual_b + fastq_bytes,   # columns + plane in, text out
         "k_dec_streams": 0.6 * rfq_b + 0.1 * qual_b,
+        # current generation
+        "k_meta3": head_b + (16 + 44) * n_reads,                                 # record heads in, ReadMeta + packed read out
+        "k_streams3": qual_b + 0.6 * rfq_b,                                      # qualities in, tokens out
+        "k_dec_format3": rfq_b + qual_b + fastq_bytes,                           # columns + quality plane in, text out
+        "k_dec_coords2": (1 + 8) * n_reads, "k_dec_reads": 48 * n_reads, "k_chunk_finish": 44 * n_reads,
+        "k_coords": 9 * n_reads,
     }
     kern_total = sum(ms for _, ms in prof.values())
     top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None

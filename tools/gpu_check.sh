@@ -4,6 +4,9 @@
 cd "$(dirname "$0")/.."
 MODE=${1:-full}
 mkdir -p gpurun_out
+# refuse to measure a stale library: the stamp is the hash of the sources the .so was built from (csrc/Makefile)
+WANT=$(cat $(ls repaq_b200/csrc/*.cu repaq_b200/csrc/*.cuh repaq_b200/csrc/*.h repaq_b200/csrc/*.inc repaq_b200/csrc/*.cpp include/repaq_b200.h | sort) | sha1sum | cut -c1-40)
+if [ "$WANT" != "$(cat repaq_b200/.build_stamp 2>/dev/null)" ]; then echo "STALE BUILD: librepaq_b200.so does not match the sources; run make -C repaq_b200/csrc"; exit 9; fi
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 nproc > gpurun_out/nproc.txt; free -g >> gpurun_out/nproc.txt
 if [ "$MODE" != "prof" ]; then
