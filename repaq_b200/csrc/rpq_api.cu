@@ -41,6 +41,7 @@ struct rpq_ctx {
     DevBuf loc, pk, pk_rc, text[2], nl[2], tile_state, counters, rlen, unit_bases, prefix, scan_tmp, ustats, chunk_first, chunks, meta, meta0, ov,
         seqoff, qualoff, n1off, n2off, soff, errbits, tmpx, tmpy, span_first[2], span_chunk[2], dir[2], slots[2], span_slot[2], span_read0[2], misc, out,
         d_in, d_desc, d_tmp[8], d_tmp2, out2;
+    u32 fmt_reads = 0;                     /* RPQ_DEBUG_FMT_READS=n: reads per formatter CTA (tuning experiments) */
     bool force_v1 = false;                 /* RPQ_DEBUG_FORCE_V1=1: take the long-read fallback kernels (test coverage) */
     bool no_pipeline = false;              /* RPQ_NO_PIPELINE=1: host batches are never cut into pipelined windows */
     uint64_t pipe_window = 0;              /* RPQ_DEBUG_PIPE_WINDOW=<bytes>: window size of the pipelined host path (tests) */
@@ -143,9 +144,11 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     memset(&c->stats, 0, sizeof c->stats);
     memset(&c->hdr, 0, sizeof c->hdr);
     { const char* e = getenv("RPQ_DEBUG_FORCE_V1"); c->force_v1 = e && e[0] == '1'; }
+    { const char* e = getenv("RPQ_DEBUG_FMT_READS"); c->fmt_reads = e ? (u32)atoi(e) : 0u; }
     { const char* e = getenv("RPQ_NO_PIPELINE"); c->no_pipeline = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_DEBUG_PIPE_WINDOW"); c->pipe_window = e ? strtoull(e, nullptr, 10) : 0; }
 #ifndef RPQ_EMU
+    cudaFuncSetAttribute(k_index_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, IDX_SMEM);
     cudaFuncSetAttribute(k_streams2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_streams3, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_meta3, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -237,7 +240,7 @@ int index_text(rpq_ctx* c, int f, const u8* d_text, u64 len, IndexCounters* hc) 
         IndexCounters* dc = c->counters.as<IndexCounters>() + f;
         rt_memset(c->tile_state.p, 0, sizeof(u64) * (tiles + 1), c->stream);
         rt_memset(dc, 0, sizeof(IndexCounters), c->stream);
-        LAUNCH(c, k_index_lines, tiles, IDX_THREADS, 0, d_text, len, c->nl[f].as<u32>(), (u32)cap, c->tile_state.as<u64>(), dc);
+        LAUNCH(c, k_index_lines, tiles, IDX_THREADS, IDX_SMEM, d_text, len, c->nl[f].as<u32>(), (u32)cap, c->tile_state.as<u64>(), dc);
         LAUNCH(c, k_index_finish, 1, 32, 0, d_text, len, c->nl[f].as<u32>(), (u32)cap, dc);
         if (int rc = read_back(c, dc, hc)) return rc;
         if ((size_t)hc->n_nl + 1 <= cap) return RPQ_OK;

@@ -138,6 +138,13 @@ __device__ __forceinline__ u32 chunk_of_read(const EncBatchDev& b, u32 i) {
 }
 
 /* ---------------------------------------------------------------- small warp helpers ---- */
+/* exact per-byte equality of two words, SIMD in a register: bit 7 of every byte of the result is set iff the bytes are equal
+ * (no carries between bytes: (x & 0x7f) + 0x7f <= 0xfe) */
+__device__ __forceinline__ u32 eq_bytes(u32 a, u32 b) {
+    const u32 x = a ^ b;
+    return ~((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x)) & 0x80808080u;
+}
+
 __device__ __forceinline__ u32 warp_excl_scan(u32 v, int lane, u32& total) {
     u32 inc = v;
 #pragma unroll

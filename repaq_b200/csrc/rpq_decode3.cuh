@@ -6,44 +6,14 @@
  *   - four bases come from one byte of the 2-bit column through a 256-entry lookup (forward, or reverse-complement:
  *     reference src/rfqcodec.cpp:833-853 and src/read.cpp:77-115 fused);
  *   - 'N' restoration is a SIMD compare of the quality word with the N quality (:1093-1100) or four bits of the N bitmap;
- *   - both lines are written through a small byte sink that emits aligned 32-bit shared stores.
+ *   - both lines are written destination-first: whole aligned 32-bit shared stores, the source phase hoisted out of the loop
+ *     (one PRMT per quality word, one funnel shift per sixteen bases).
  * v2 did all of this per base (~9 k thread instructions per read, profiles/r01_v2_ncu_full_k_dec_format2.csv).
  */
 #pragma once
 #include "rpq_decode2.cuh"
 
 namespace rpq {
-
-/* sequential byte sink into shared memory: after the first (unaligned) bytes every put4 is one aligned 32-bit store */
-struct Sink {
-    u8* dst; u32 res, nres, need;
-    __device__ __forceinline__ void init(u8* d) { dst = d; res = 0; nres = 0; need = (4u - (u32)(reinterpret_cast<uintptr_t>(d) & 3u)) & 3u; }
-    __device__ __forceinline__ void put4(u32 w) {
-        if (need) {
-            for (u32 k = 0; k < need; k++) dst[k] = (u8)(w >> (8u * k));
-            dst += need; res = w >> (8u * need); nres = 4u - need; need = 0;
-            return;
-        }
-        if (nres == 0) { *reinterpret_cast<u32*>(dst) = w; dst += 4; return; }
-        *reinterpret_cast<u32*>(dst) = res | (w << (8u * nres));
-        dst += 4;
-        res = w >> (8u * (4u - nres));
-    }
-    __device__ __forceinline__ void put1(u8 c) {
-        if (need) { *dst++ = c; need--; return; }
-        res |= (u32)c << (8u * nres); nres++;
-        if (nres == 4u) { *reinterpret_cast<u32*>(dst) = res; dst += 4; res = 0; nres = 0; }
-    }
-    __device__ __forceinline__ void flush() { for (u32 k = 0; k < nres; k++) dst[k] = (u8)(res >> (8u * k)); dst += nres; nres = 0; res = 0; }
-};
-
-/* 4 bytes at any byte address of shared memory */
-__device__ __forceinline__ u32 lds4(const u8* p) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const u32* w = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
-    const u32 sh = (u32)(a & 3u) * 8u;
-    return sh ? __funnelshift_r(w[0], w[1], sh) : w[0];
-}
 
 __global__ void __launch_bounds__(256) k_dec_format3(DecBatchDev b, HeaderDev h, Fmt2Cfg cfg, u32 read_first, u32 read_end) {
     RPQ_DYN_SMEM(dyn);
@@ -169,48 +139,101 @@ __global__ void __launch_bounds__(256) k_dec_format3(DecBatchDev b, HeaderDev h,
             else if (q[rc ? rl - 1 - jo : jo] == nq) base = 'N';
             return rc ? complement_base(base) : base;
         };
-        const u32 ngroups = rl >> 2;
+        /* Both lines are produced destination-first: up to three bytes until the output is word aligned, then whole aligned
+         * 32-bit words, then up to three bytes.  The source phase (plane byte offset, 2-bit phase) is constant along a line. */
+        const int d = rc ? -1 : 1;
         if (half == 1) {
-            /* quality line (reversed for the reverse strand) */
-            Sink qs; qs.init(o_qual);
-            for (u32 g = 0; g < ngroups; g++) {
-                const u32 jo = 4u * g;
-                qs.put4(rc ? __byte_perm(lds4(q + (rl - 4u - jo)), 0, 0x0123) : lds4(q + jo));
+            /* quality line: a byte-shifted (reverse strand: byte-reversed) copy out of the staged plane, one PRMT per word */
+            u32 need = (4u - (u32)(reinterpret_cast<uintptr_t>(o_qual) & 3u)) & 3u; if (need > rl) need = rl;
+            for (u32 jo = 0; jo < need; jo++) o_qual[jo] = q[rc ? rl - 1 - jo : jo];
+            const u32 nw = (rl - need) >> 2;
+            u32* dw = reinterpret_cast<u32*>(o_qual + need);
+            if (nw) {
+                const uintptr_t p0 = reinterpret_cast<uintptr_t>(rc ? q + (rl - 4u - need) : q + need);
+                const u32* w = reinterpret_cast<const u32*>(p0 & ~(uintptr_t)3);
+                const u32 sel = (rc ? 0x0123u : 0x3210u) + 0x1111u * (u32)(p0 & 3u);
+#pragma unroll 4
+                for (u32 m = 0; m < nw; m++) { dw[m] = __byte_perm(w[0], w[1], sel); w += d; }
             }
-            for (u32 jo = ngroups * 4u; jo < rl; jo++) qs.put1(q[rc ? rl - 1 - jo : jo]);
-            qs.flush();
+            for (u32 jo = need + 4u * nw; jo < rl; jo++) o_qual[jo] = q[rc ? rl - 1 - jo : jo];
         } else {
-            Sink ss; ss.init(o_seq);
-            for (u32 g = 0; g < ngroups; g++) {
-                const u32 jo = 4u * g;
-                const bool piece_a = jo + 3u < bnd, piece_b = jo >= bnd;
-                const long long cbase = piece_a ? cA : cB;
-                const long long ci_lo = rc ? cbase - (long long)jo - 3 : cbase + (long long)jo;
-                u32 bw;
-                if ((piece_a || piece_b) && ci_lo >= 0 && ci_lo + 3 < unpacked) {
-                    const u32 k = (u32)(ci_lo >> 2), ph = 2u * (u32)(ci_lo & 3);
-                    const u32 two = (u32)seqb[k] | (ph ? (u32)seqb[k + 1] << 8 : 0u);
-                    const u32 code8 = (two >> ph) & 0xFFu;
-                    bw = rc ? s_lut_rc[code8] : s_lut_fwd[code8];
-                    u32 mask;
-                    if (npos_mode) {
-                        const u32 wi = (u32)(ci_lo >> 5), bp = (u32)(ci_lo & 31);
-                        u32 m4 = (nmap[wi] >> bp) & 0xFu;
-                        if (bp > 28u) m4 |= (nmap[wi + 1] << (32u - bp)) & 0xFu;
-                        if (rc) m4 = ((m4 & 1u) << 3) | ((m4 & 2u) << 1) | ((m4 & 4u) >> 1) | ((m4 & 8u) >> 3);
-                        mask = ((m4 | (m4 << 7) | (m4 << 14) | (m4 << 21)) & 0x01010101u) * 0xFFu;
-                    } else {
-                        const u32 qw = rc ? __byte_perm(lds4(q + (rl - 4u - jo)), 0, 0x0123) : lds4(q + jo);
-                        mask = __vcmpeq4(qw, nq4);
-                    }
-                    bw = (bw & ~mask) | (0x4E4E4E4Eu & mask);
-                } else {
-                    bw = (u32)slow_base(jo) | ((u32)slow_base(jo + 1) << 8) | ((u32)slow_base(jo + 2) << 16) | ((u32)slow_base(jo + 3) << 24);
-                }
-                ss.put4(bw);
+            u32 need = (4u - (u32)(reinterpret_cast<uintptr_t>(o_seq) & 3u)) & 3u; if (need > rl) need = rl;
+            for (u32 jo = 0; jo < need; jo++) o_seq[jo] = slow_base(jo);
+            const u32 nw = (rl - need) >> 2;
+            u32* dw = reinterpret_cast<u32*>(o_seq + need);
+            /* compact positions a word may load codes for: inside the unpacked range, and not closer than 8 bytes to the end of the body */
+            long long lim = unpacked;
+            {
+                const long long avail = (long long)b.body_len - (long long)(ck.in_off + ck.off_seq);
+                const long long safe = avail > 8 ? 4 * (avail - 8) : 0;
+                if (lim > safe) lim = safe;
             }
-            for (u32 jo = ngroups * 4u; jo < rl; jo++) ss.put1(slow_base(jo));
-            ss.flush();
+            /* words [m0, m1) of the piece jo in [jlo, jhi) with compact base cb whose four positions can take the fast path */
+            auto range = [&](long long cb, long long jlo, long long jhi, u32& m0, u32& m1) {
+                long long a, z;                                    /* allowed first positions jo of a word: a <= jo <= z */
+                if (!rc) { a = -cb; z = lim - cb - 4; } else { a = cb - lim + 1; z = cb - 3; }
+                if (a < jlo) a = jlo;
+                if (z > jhi - 4) z = jhi - 4;
+                long long lo_m = a <= (long long)need ? 0 : (a - need + 3) >> 2;
+                long long hi_m = z < (long long)need ? 0 : ((z - need) >> 2) + 1;
+                if (hi_m > (long long)nw) hi_m = nw;
+                if (lo_m > hi_m) lo_m = hi_m;
+                m0 = (u32)lo_m; m1 = (u32)hi_m;
+            };
+            u32 a0, a1, b0, b1;
+            if (cA == cB) { range(cA, 0, rl, a0, a1); b0 = b1 = a1; }
+            else { range(cA, 0, bnd, a0, a1); range(cB, bnd, rl, b0, b1); if (b0 < a1) b0 = a1; if (b1 < b0) b1 = b0; }
+            auto slow_word = [&](u32 m) {
+                const u32 jo = need + 4u * m;
+                dw[m] = (u32)slow_base(jo) | ((u32)slow_base(jo + 1) << 8) | ((u32)slow_base(jo + 2) << 16) | ((u32)slow_base(jo + 3) << 24);
+            };
+            const u32* lut = rc ? s_lut_rc : s_lut_fwd;
+            /* sixteen bases per 32-bit load of the 2-bit column, four per table lookup; 'N' from a SIMD compare of the quality word */
+            auto fast_run = [&](u32 m0, u32 m1, long long cb) {
+                if (m0 >= m1) return;
+                const u32 jo0 = need + 4u * m0;
+                const uintptr_t p0 = reinterpret_cast<uintptr_t>(rc ? q + (rl - 4u - jo0) : q + jo0);
+                const u32* qw = reinterpret_cast<const u32*>(p0 & ~(uintptr_t)3);
+                const u32 qsel = (rc ? 0x0123u : 0x3210u) + 0x1111u * (u32)(p0 & 3u);
+                const long long ci0 = rc ? cb - (long long)jo0 - 15 : cb + (long long)jo0;     /* lowest compact index of the first 16 */
+                const uintptr_t ca = reinterpret_cast<uintptr_t>(seqb) + (uintptr_t)(ci0 >> 2);
+                const u32* cw = reinterpret_cast<const u32*>(ca & ~(uintptr_t)3);
+                const u32 sh = 8u * (u32)(ca & 3u) + 2u * (u32)(ci0 & 3);
+                for (u32 m = m0; m < m1; m += 4) {
+                    const u32 codes = __funnelshift_r(cw[0], cw[1], sh);
+                    cw += d;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        if (m + t < m1) {
+                            const u32 code8 = (codes >> (rc ? 24 - 8 * t : 8 * t)) & 0xFFu;
+                            u32 bw = lut[code8];
+                            if (npos_mode) {
+                                const u32 jo = need + 4u * (m + t);
+                                const long long ci_lo = rc ? cb - (long long)jo - 3 : cb + (long long)jo;
+                                const u32 wi = (u32)(ci_lo >> 5), bp = (u32)(ci_lo & 31);
+                                u32 m4 = (nmap[wi] >> bp) & 0xFu;
+                                if (bp > 28u) m4 |= (nmap[wi + 1] << (32u - bp)) & 0xFu;
+                                if (rc) m4 = ((m4 & 1u) << 3) | ((m4 & 2u) << 1) | ((m4 & 4u) >> 1) | ((m4 & 8u) >> 3);
+                                const u32 mask = ((m4 | (m4 << 7) | (m4 << 14) | (m4 << 21)) & 0x01010101u) * 0xFFu;
+                                bw = (bw & ~mask) | (0x4E4E4E4Eu & mask);
+                            } else {
+                                const u32 qv = __byte_perm(qw[0], qw[1], qsel);
+                                qw += d;
+                                const u32 fl7 = eq_bytes(qv, nq4);
+                                if (fl7) { const u32 mask = (fl7 >> 7) * 0xFFu; bw = (bw & ~mask) | (0x4E4E4E4Eu & mask); }
+                            }
+                            dw[m + t] = bw;
+                        }
+                    }
+                }
+            };
+            u32 m = 0;
+            for (; m < a0; m++) slow_word(m);
+            fast_run(a0, a1, cA); if (m < a1) m = a1;
+            for (; m < b0; m++) slow_word(m);
+            fast_run(b0, b1, cB); if (m < b1) m = b1;
+            for (; m < nw; m++) slow_word(m);
+            for (u32 jo = need + 4u * nw; jo < rl; jo++) o_seq[jo] = slow_base(jo);
         }
     }
     __syncthreads();

@@ -13,12 +13,12 @@
 
 namespace rpq {
 
-constexpr int IDX_THREADS = 256;
-constexpr int IDX_CHUNKS = 4;                                /* 16-byte pieces per lane and round */
-constexpr int IDX_ROUNDS = 4;                                /* rounds per CTA */
-constexpr int IDX_WARP_BYTES = 32 * 16 * IDX_CHUNKS;         /* 2 KiB per warp and round */
-constexpr int IDX_ROUND_BYTES = (IDX_THREADS / 32) * IDX_WARP_BYTES;   /* 16 KiB */
-constexpr int IDX_TILE = IDX_ROUNDS * IDX_ROUND_BYTES;       /* 64 KiB per CTA */
+constexpr int IDX_THREADS = 512;
+constexpr int IDX_ROW = 128;                                 /* bytes per thread: 8 pieces of 16 bytes */
+constexpr int IDX_PIECES = IDX_ROW / 16;
+constexpr int IDX_WARP_BYTES = 32 * IDX_ROW;                 /* 4 KiB per warp: one TMA bulk copy */
+constexpr int IDX_TILE = IDX_THREADS * IDX_ROW;              /* 64 KiB per CTA */
+constexpr int IDX_SMEM = IDX_TILE + IDX_THREADS * 16;        /* the tile + eight 16-bit newline masks per thread */
 
 struct IndexCounters {
     u32 ticket;     /* dynamic tile id */
@@ -34,69 +34,113 @@ struct IndexCounters {
 
 constexpr u64 TS_AGG = 1ull << 62, TS_PREFIX = 2ull << 62, TS_MASK = 3ull << 62;
 
-__device__ __forceinline__ u32 nl_mask16(uint4 v, u8 c) {
-    const u32 cc = 0x01010101u * c;
-    u32 m0 = __vcmpeq4(v.x, cc), m1 = __vcmpeq4(v.y, cc), m2 = __vcmpeq4(v.z, cc), m3 = __vcmpeq4(v.w, cc);
-    /* one bit per byte: take bit 0 of every byte lane and pack */
-    auto pack = [](u32 m) -> u32 { m &= 0x01010101u; return (m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xFu; };
-    return pack(m0) | (pack(m1) << 4) | (pack(m2) << 8) | (pack(m3) << 12);
+/* exact per-byte equality, SIMD in a register: bit 7 of every byte of the result is set iff that byte of v equals c.
+ * ((v ^ cccc) & 0x7f7f7f7f) + 0x7f7f7f7f carries into bit 7 iff the low seven bits differ; bit 7 itself must be clear in v
+ * (c < 0x80).  Three instructions per word, no carries between bytes. */
+__device__ __forceinline__ u32 eq_lowascii(u32 v, u32 cccc) {
+    const u32 t = ((v ^ cccc) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    return ~(t | v) & 0x80808080u;
+}
+/* bit 7 of every byte CLEAR iff that byte equals c (the complement of eq_lowascii before masking): lets four words be
+ * AND-ed together for an "any byte equals c" test */
+__device__ __forceinline__ u32 ne_lowascii(u32 v, u32 cccc) {
+    return (((v ^ cccc) & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v;
+}
+/* flags at bit 7 of the bytes of two words -> 8 consecutive bits in text order (lo word first) at bits 24..31.
+ * (lo >> 4 | hi) * (1 + 2^7 + 2^14 + 2^21): every partial product lands on a distinct bit, so there are no carries. */
+__device__ __forceinline__ u32 pack8(u32 lo, u32 hi) { return ((lo >> 4) | hi) * 0x00204081u; }
+__device__ __forceinline__ u32 mask16(u32 m0, u32 m1, u32 m2, u32 m3) {
+    return (pack8(m0, m1) >> 24) | ((pack8(m2, m3) >> 16) & 0xFF00u);
 }
 
 /*
- * One pass over the text: positions of every '\n', in order.  A CTA takes a 64 KiB tile (4 rounds of 16 KiB, uint4 loads),
- * keeps the newline masks in registers, publishes its count and gets its rank base from a chained scan over tiles with a
- * warp-wide decoupled look-back (32 predecessors per probe), then writes the positions.
+ * One pass over the text: positions of every '\n', in order.  A CTA takes a 64 KiB tile, brought into shared memory by one
+ * TMA bulk copy per warp (4 KiB); a thread owns 128 contiguous bytes (its pieces read in a lane-rotated order, so that the
+ * 128-bit shared loads of a quarter warp fall into eight different bank groups), turns them into eight exact 16-bit
+ * newline masks with SIMD-in-register compares, and counts.  One scan per CTA, then the chained scan over tiles with a
+ * warp-wide decoupled look-back (32 predecessors per probe) gives the rank base; every thread then writes its own
+ * positions.  '\r' is only tested for ("any in these 16 bytes"); files that have them take the exact path.
  */
-__global__ void __launch_bounds__(IDX_THREADS) k_index_lines(const u8* __restrict__ text, u64 len, u32* __restrict__ nl, u32 nl_cap,
-                                                            u64* tile_state, IndexCounters* ctr) {
+__global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines(const u8* __restrict__ text, u64 len, u32* __restrict__ nl, u32 nl_cap,
+                                                               u64* tile_state, IndexCounters* ctr) {
+    RPQ_DYN_SMEM(dyn);
     __shared__ u32 s_tile;
-    __shared__ u32 s_tot[IDX_ROUNDS][IDX_THREADS / 32];
+    __shared__ u32 s_wtot[IDX_THREADS / 32];
     __shared__ u32 s_prefix;
     __shared__ u32 s_cr, s_crlf;
+#ifndef RPQ_EMU
+    __shared__ __align__(8) unsigned long long s_mbar[IDX_THREADS / 32];
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { s_tile = atomicAdd(&ctr->ticket, 1u); s_cr = 0; s_crlf = 0; }
+#ifndef RPQ_EMU
+    if (tid < IDX_THREADS / 32) {
+        asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"((u32)__cvta_generic_to_shared(&s_mbar[tid])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#endif
     __syncthreads();
     const u32 tile = s_tile;
     const u64 tbase = (u64)tile * IDX_TILE;
+    u8* row = dyn + (size_t)tid * IDX_ROW;
+    unsigned short* my_masks = reinterpret_cast<unsigned short*>(dyn + IDX_TILE) + (size_t)tid * IDX_PIECES;
 
-    u32 nlm[IDX_ROUNDS][IDX_CHUNKS / 2];       /* two 16-bit masks per register */
-    u32 exc[IDX_ROUNDS][IDX_CHUNKS / 2];       /* two 16-bit in-warp exclusive offsets per register */
-    u32 ncr = 0, ncrlf = 0;
-#pragma unroll
-    for (int r = 0; r < IDX_ROUNDS; r++) {
-        const u64 wbase = tbase + (u64)r * IDX_ROUND_BYTES + (u64)warp * IDX_WARP_BYTES;
-        u32 wtot = 0;
-#pragma unroll
-        for (int k = 0; k < IDX_CHUNKS; k++) {
-            const u64 p = wbase + (u64)k * 512 + (u64)lane * 16;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            u32 valid = 0xFFFFu;
-            if (p + 16 <= len) v = *reinterpret_cast<const uint4*>(text + p);
-            else if (p < len) {
-                u32 w[4] = {0, 0, 0, 0};
-                const int n = (int)(len - p);
-                for (int i = 0; i < n; i++) w[i >> 2] |= (u32)text[p + i] << (8 * (i & 3));
-                v = make_uint4(w[0], w[1], w[2], w[3]);
-                valid = (1u << n) - 1u;
-            } else valid = 0;
-            const u32 m = nl_mask16(v, '\n') & valid;
-            const u32 c = nl_mask16(v, '\r') & valid;
-            u32 pair = m & (c << 1);
-            if ((m & 1u) && p > 0 && text[p - 1] == '\r') pair |= 1u;
-            ncr += (u32)__popc(c); ncrlf += (u32)__popc(pair);
-            u32 t; const u32 ex = wtot + warp_excl_scan((u32)__popc(m), lane, t); wtot += t;
-            if (k & 1) { nlm[r][k >> 1] |= m << 16; exc[r][k >> 1] |= ex << 16; } else { nlm[r][k >> 1] = m; exc[r][k >> 1] = ex; }
+    /* ---- stage */
+    const u64 wbase = tbase + (u64)warp * IDX_WARP_BYTES;
+    const u32 wbytes = wbase >= len ? 0u : (len - wbase >= IDX_WARP_BYTES ? (u32)IDX_WARP_BYTES : (u32)(((len - wbase) + 15) & ~15ull));
+#ifdef RPQ_EMU
+    for (u32 k = lane; k < wbytes; k += 32) { const u64 p = wbase + k; dyn[(size_t)warp * IDX_WARP_BYTES + k] = p < len ? text[p] : 0; }
+    __syncwarp();
+#else
+    if (wbytes) {
+        const u32 mbar = (u32)__cvta_generic_to_shared(&s_mbar[warp]);
+        if (lane == 0) {
+            const u32 dst = (u32)__cvta_generic_to_shared(dyn + (size_t)warp * IDX_WARP_BYTES);
+            asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(mbar), "r"(wbytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(text + wbase), "r"(wbytes), "r"(mbar) : "memory");
         }
-        if (lane == 0) s_tot[r][warp] = wtot;
+        u32 done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mbar) : "memory");
     }
+#endif
+    const u64 p0 = tbase + (u64)tid * IDX_ROW;                /* first byte of this thread's row */
+    const int lim = p0 >= len ? 0 : (len - p0 >= IDX_ROW ? IDX_ROW : (int)(len - p0));
+    if (lim < IDX_ROW) for (int i = lim; i < IDX_ROW; i++) row[i] = 0;     /* the end of the text: zeros match nothing */
+
+    /* ---- masks and counts */
+    u32 cnt = 0, ncr = 0, ncrlf = 0;
+#pragma unroll
+    for (int k = 0; k < IDX_PIECES; k++) {
+        const int kk = (k + lane) & (IDX_PIECES - 1);
+        const uint4 v = *reinterpret_cast<const uint4*>(row + 16 * kk);
+        const u32 m = mask16(eq_lowascii(v.x, 0x0A0A0A0Au), eq_lowascii(v.y, 0x0A0A0A0Au), eq_lowascii(v.z, 0x0A0A0A0Au), eq_lowascii(v.w, 0x0A0A0A0Au));
+        const u32 nocr = ne_lowascii(v.x, 0x0D0D0D0Du) & ne_lowascii(v.y, 0x0D0D0D0Du) & ne_lowascii(v.z, 0x0D0D0D0Du) & ne_lowascii(v.w, 0x0D0D0D0Du);
+        my_masks[kk] = (unsigned short)m;
+        cnt += (u32)__popc(m);
+        if (~nocr & 0x80808080u) {
+            const u32 c = mask16(eq_lowascii(v.x, 0x0D0D0D0Du), eq_lowascii(v.y, 0x0D0D0D0Du), eq_lowascii(v.z, 0x0D0D0D0Du), eq_lowascii(v.w, 0x0D0D0D0Du));
+            ncr += (u32)__popc(c);
+            ncrlf += (u32)__popc(m & (c << 1));
+        }
+        if (m & 1u) {                                        /* a newline at the first byte of a piece: look one byte back */
+            const u64 p = p0 + 16u * (u32)kk;
+            u8 prev = 0;
+            if (kk > 0 || lane > 0) prev = row[16 * kk - 1];  /* rows of a warp are contiguous in shared memory */
+            else if (p > 0) prev = text[p - 1];
+            if (prev == '\r') ncrlf++;
+        }
+    }
+    u32 wtot;
+    const u32 ex_in_warp = warp_excl_scan(cnt, lane, wtot);
     ncr = warp_sum(ncr); ncrlf = warp_sum(ncrlf);
-    if (lane == 0) { if (ncr) atomicAdd(&s_cr, ncr); if (ncrlf) atomicAdd(&s_crlf, ncrlf); }
+    if (lane == 0) { s_wtot[warp] = wtot; if (ncr) atomicAdd(&s_cr, ncr); if (ncrlf) atomicAdd(&s_crlf, ncrlf); }
     __syncthreads();
-    u32 btot = 0;
+    u32 btot = 0, wpre = 0;
 #pragma unroll
-    for (int r = 0; r < IDX_ROUNDS; r++)
-#pragma unroll
-        for (int w = 0; w < IDX_THREADS / 32; w++) btot += s_tot[r][w];
+    for (int w = 0; w < IDX_THREADS / 32; w++) { const u32 t = s_wtot[w]; btot += t; if (w < warp) wpre += t; }
 
     if (warp == 0) {
         volatile u64* st = tile_state;
@@ -131,27 +175,23 @@ __global__ void __launch_bounds__(IDX_THREADS) k_index_lines(const u8* __restric
         }
     }
     __syncthreads();
-    u32 base = s_prefix;
+
+    /* ---- positions: the eight masks of this thread, in text order */
+    if (cnt) {
+        u32 o = s_prefix + wpre + ex_in_warp;
+        const uint4 mm = *reinterpret_cast<const uint4*>(my_masks);
+        const u32 base = (u32)p0;
+        u32 w[4] = {mm.x, mm.y, mm.z, mm.w};
 #pragma unroll
-    for (int r = 0; r < IDX_ROUNDS; r++) {
-        u32 wpre = 0;
-#pragma unroll
-        for (int w = 0; w < IDX_THREADS / 32; w++) { const u32 t = s_tot[r][w]; if (w < warp) wpre += t; }
-        const u64 wbase = tbase + (u64)r * IDX_ROUND_BYTES + (u64)warp * IDX_WARP_BYTES;
-#pragma unroll
-        for (int k = 0; k < IDX_CHUNKS; k++) {
-            u32 m = (nlm[r][k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
-            u32 o = base + wpre + ((exc[r][k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
-            const u32 p = (u32)(wbase + (u64)k * 512 + (u64)lane * 16);
+        for (int q = 0; q < 4; q++) {
+            u32 m = w[q];
             while (m) {
                 const int bb = __ffs((int)m) - 1;
                 m &= m - 1;
-                if (o < nl_cap) nl[o] = p + (u32)bb;
+                if (o < nl_cap) nl[o] = base + 32u * q + (u32)bb;
                 o++;
             }
         }
-#pragma unroll
-        for (int w = 0; w < IDX_THREADS / 32; w++) base += s_tot[r][w];
     }
 }
 

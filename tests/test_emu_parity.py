@@ -54,6 +54,36 @@ def test_empty_and_ragged_inputs(codec):
         parity.check_against_oracle(codec, good + tail, roundtrip=False)
 
 
+@pytest.mark.parametrize("target", [128, 4096, 65536, 65536 + 4096, 131072])
+def test_crlf_across_indexer_boundaries(codec, target):
+    """k_index_lines: a "\r\n" whose '\n' is the first byte of a 16-byte piece / a thread's row / a warp's bulk copy / a
+    tile (the '\r' then lives in the previous one) must still count as a CRLF line end"""
+    import numpy as np
+    from tools import fqgen
+    body = bytes(fqgen.generate(700, seed=5, paired=False, flags=fqgen.CRLF)[0])
+    nls = np.flatnonzero(np.frombuffer(body, dtype=np.uint8) == 10)
+    done = 0
+    for want_nl in nls:
+        gap = target - int(want_nl)                 # bytes the prefix record must add
+        if gap < 15:
+            break
+        if gap > 700:
+            continue
+        name = b"@pad" if gap % 2 else b"@padd"
+        L = (gap - len(name) - 9) // 2
+        if L < 1:
+            continue
+        rec = name + b"\r\n" + b"A" * L + b"\r\n+\r\n" + b"F" * L + b"\r\n"
+        assert len(rec) == gap
+        text = rec + body
+        assert text[target] == 10 and text[target - 1] == 13
+        parity.check_against_oracle(codec, text, k=100, roundtrip=False)
+        done += 1
+        if done == 2:
+            break
+    assert done
+
+
 def _decode_devmem(codec, rfq, split):
     """decode with mem=RPQ_MEM_DEVICE in and out (under emulation 'device' memory is host memory): exercises the device
     chunk walk (k_dec_walk_fast + k_dec_describe, or the exact k_dec_walk)"""
