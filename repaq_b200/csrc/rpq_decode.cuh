@@ -275,47 +275,81 @@ __global__ void __launch_bounds__(32) k_dec_streams(DecBatchDev b, HeaderDev h, 
     u8* plane = b.plane + ck.plane_off;
     u32* nmap = b.nmap + ck.nmap_off;
     const u32 nmap_bits = ((ck.seq_kept + 31) / 32 + 1) * 32;
+    /* 128 stream bytes per step, four consecutive bytes per lane (aligned word loads, the next step's words already in
+     * flight).  Where the tokens of a lane start depends on how many payload bytes spill in from the lane before (0..3): every
+     * lane tabulates its exit spill for the four possible entries; most tables are constant, so the chain resolves in a round
+     * or two.  Each lane then decodes its (at most four) tokens; one warp scan of the per-lane advances places them. */
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(stream);
+    const u32* A = reinterpret_cast<const u32*>(sa & ~(uintptr_t)3);
+    const u32 sh = 8u * (u32)(sa & 3u);
+    const u32* Aend = reinterpret_cast<const u32*>((reinterpret_cast<uintptr_t>(b.body + b.body_len) + 3u) & ~(uintptr_t)3);
+    auto ldw = [&](u32 k) -> u32 { const u32* w = A + k; return w < Aend ? *w : 0u; };
     long long last = -1;
-    u32 skip = 0;                                         /* bytes at the start of the step that belong to the previous token */
-    for (u32 base = 0; base < slen; base += 32) {
-        const u32 p = base + lane;
-        const u32 b0 = p < slen ? stream[p] : 0u;
-        const bool valid = p < slen;
-        const u32 tlen = !(b0 & 0x80) ? 1u : !(b0 & 0x40) ? 2u : !(b0 & 0x20) ? 1u : 4u;
-        u32 multi = __ballot_sync(0xffffffffu, valid && tlen > 1);
-        const u32 is4 = __ballot_sync(0xffffffffu, valid && tlen == 4);
-        u32 skipped = skip >= 32 ? 0xffffffffu : ((1u << skip) - 1u);
-        u32 next_skip = skip > 32 ? skip - 32 : 0;
-        while (multi) {
-            const int i = __ffs((int)multi) - 1;
-            multi &= multi - 1;
-            if ((skipped >> i) & 1u) continue;
-            const u32 extra = ((is4 >> i) & 1u) ? 3u : 1u;
-            const u32 hi = (u32)i + extra;                  /* last payload position */
-            for (u32 k = (u32)i + 1; k <= hi && k < 32; k++) skipped |= 1u << k;
-            if (hi >= 32) next_skip = hi - 31;
+    u32 skip = 0;                                         /* payload bytes at the start of the step that belong to the previous token */
+    u32 cura = slen ? ldw((u32)lane) : 0u;
+    for (u32 base = 0; base < slen; base += 128) {
+        const u32 nexta = base + 128 < slen + 8 ? ldw((base >> 2) + 32u + (u32)lane) : 0u;
+        u32 a1 = __shfl_down_sync(0xffffffffu, cura, 1), a2 = __shfl_down_sync(0xffffffffu, cura, 2);
+        const u32 n0 = __shfl_sync(0xffffffffu, nexta, 0), n1 = __shfl_sync(0xffffffffu, nexta, 1);
+        if (lane == 31) { a1 = n0; a2 = n1; } else if (lane == 30) a2 = n0;
+        u64 B = (u64)__funnelshift_r(cura, a1, sh) | ((u64)__funnelshift_r(a1, a2, sh) << 32);
+        const u32 p0 = base + 4u * (u32)lane;
+        const u32 left = p0 < slen ? slen - p0 : 0u;       /* stream bytes from this lane's first byte on */
+        if (left < 8u) B = left ? B & ((1ull << (8u * left)) - 1ull) : 0ull;
+        const u32 nv = left < 4u ? left : 4u;
+        const u32 cur = (u32)B;
+        /* token length by first byte: 0xxxxxxx 1, 10xxxxxx 2, 110xxxxx 1, 111xxxxx 4 */
+        u32 L[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const u32 b0 = (cur >> (8 * k)) & 0xFFu; L[k] = !(b0 & 0x80u) ? 1u : !(b0 & 0x40u) ? 2u : !(b0 & 0x20u) ? 1u : 4u; }
+        /* exit spill if the first token of the lane starts at byte r */
+        const u32 e3 = L[3] - 1u;
+        const u32 e2 = L[2] == 1u ? e3 : L[2] - 2u;
+        const u32 e1 = L[1] == 1u ? e2 : (L[1] == 2u ? e3 : 1u);
+        const u32 e0 = L[0] == 1u ? e1 : (L[0] == 2u ? e2 : 0u);
+        const u32 f = e0 | (e1 << 2) | (e2 << 4) | (e3 << 6);
+        const bool is_const = f == e0 * 0x55u;
+        u32 r_in = lane == 0 ? skip : 4u;                    /* 4 = not known yet */
+        for (;;) {
+            const u32 mine = r_in < 4u ? (f >> (2u * r_in)) & 3u : (is_const ? e0 : 4u);
+            const u32 got = __shfl_up_sync(0xffffffffu, mine, 1);
+            if (r_in == 4u && lane > 0) r_in = got;
+            if (__ballot_sync(0xffffffffu, r_in == 4u) == 0u) break;
         }
-        const bool head = valid && !((skipped >> lane) & 1u);
-        /* advance of this token */
-        u32 adv = 0; u32 run = 0;
-        if (head) {
-            if (!(b0 & 0x80)) adv = b0 + 1;
-            else if (!(b0 & 0x40)) adv = (((b0 & 0x3F) << 8) | (p + 1 < slen ? stream[p + 1] : 0u)) + 1;
-            else if (!(b0 & 0x20)) { run = (b0 & 0x1F) + 1; adv = run; }
-            else adv = (((b0 & 0x1F) << 24) | ((u32)(p + 1 < slen ? stream[p + 1] : 0u) << 16) | ((u32)(p + 2 < slen ? stream[p + 2] : 0u) << 8) | (u32)(p + 3 < slen ? stream[p + 3] : 0u)) + 1;
+        skip = __shfl_sync(0xffffffffu, (f >> (2u * r_in)) & 3u, 31);
+        /* the lane's tokens */
+        u32 adv[4], run[4]; u32 lane_adv = 0; u32 next_head = r_in;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            adv[k] = 0; run[k] = 0;
+            if ((u32)k == next_head && (u32)k < nv) {
+                const u32 t = (u32)(B >> (8 * k));            /* the token's bytes, first byte lowest */
+                const u32 b0 = t & 0xFFu;
+                if (!(b0 & 0x80u)) adv[k] = b0 + 1u;
+                else if (!(b0 & 0x40u)) adv[k] = (((b0 & 0x3Fu) << 8) | ((t >> 8) & 0xFFu)) + 1u;
+                else if (!(b0 & 0x20u)) { run[k] = (b0 & 0x1Fu) + 1u; adv[k] = run[k]; }
+                else adv[k] = (((b0 & 0x1Fu) << 24) | (((t >> 8) & 0xFFu) << 16) | (((t >> 16) & 0xFFu) << 8) | ((t >> 24) & 0xFFu)) + 1u;
+                lane_adv += adv[k];
+                next_head = (u32)k + L[k];
+            }
         }
-        u32 tot; const u32 ex = warp_excl_scan(adv, lane, tot);
-        if (head) {
-            const long long endpos = last + (long long)ex + adv;       /* position of the token's last element */
-            const long long first = run ? endpos - run + 1 : endpos;
-            for (long long pos = first; pos <= endpos; pos++) {
-                if (pos < 0) continue;
-                if (is_npos) { if ((u64)pos < nmap_bits && (u64)pos < dst_len) atomicOr(&nmap[pos >> 5], 1u << (pos & 31)); }
-                else if ((u64)pos < dst_len) plane[pos] = q;
+        u32 tot; const u32 ex = warp_excl_scan(lane_adv, lane, tot);
+        long long acc = last + (long long)ex;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (adv[k]) {
+                const long long endpos = acc + (long long)adv[k];      /* position of the token's last element */
+                const long long first = run[k] ? endpos - run[k] + 1 : endpos;
+                for (long long pos = first; pos <= endpos; pos++) {
+                    if (pos < 0) continue;
+                    if (is_npos) { if ((u64)pos < nmap_bits && (u64)pos < dst_len) atomicOr(&nmap[pos >> 5], 1u << (pos & 31)); }
+                    else if ((u64)pos < dst_len) plane[pos] = q;
+                }
+                acc = endpos;
             }
         }
         last += tot;
-        skip = next_skip;
+        cura = nexta;
     }
 }
 

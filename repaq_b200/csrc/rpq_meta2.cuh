@@ -205,7 +205,31 @@ __global__ void __launch_bounds__(256) k_emit2(EncBatchDev b, HeaderDev h, u8* o
     };
     u8* col = o + ck.off_seq;
     const u32 w0 = (so + 15u) >> 4, w1 = (so + kept - 1u) >> 4;
-    for (u32 W = w0; W <= w1; W++) {
+    const bool col_aligned = (reinterpret_cast<uintptr_t>(col) & 3u) == 0;
+    auto store_word = [&](u32 W, u32 word) {
+        const u32 bo = 4u * W;
+        if (col_aligned && bo + 4u <= ck.seq_size) { *reinterpret_cast<u32*>(col + bo) = word; return; }
+        const u32 nbytes = ck.seq_size - bo < 4u ? ck.seq_size - bo : 4u;
+        for (u32 k = 0; k < nbytes; k++) col[bo + k] = (u8)(word >> (8 * k));
+    };
+    u32 W = w0;
+    /* words that lie entirely inside this read: a funnel shift of two neighbouring packed words, the loads a few words ahead */
+    if (w1 > w0 && !(rc_file && (rel & 1u) && !il)) {
+        const int ov = (il && (rel & 1u) && (h.flags & RPQ_ENCODE_PE_BY_OVERLAP)) ? (int)b.ov[i >> 1] : 0;
+        const u32 a = 16u * w0 - so + (ov > 0 ? (u32)ov : 0u);
+        const u32* src = b.pk + (size_t)i * pkw;
+        const u32 sh = (a & 15u) * 2u;
+        u32 k = a >> 4;
+        u32 lo = k < pkw ? src[k] : 0u;
+#pragma unroll 4
+        for (; W < w1; W++) {
+            k++;
+            const u32 hi = k < pkw ? src[k] : 0u;
+            store_word(W, __funnelshift_r(lo, hi, sh));
+            lo = hi;
+        }
+    }
+    for (; W <= w1; W++) {
         const u32 p0 = 16u * W;
         u32 have = so + kept - p0; if (have > 16u) have = 16u;                  /* own bases in this word */
         u32 word = window(i, rel, p0 - so);
@@ -226,9 +250,7 @@ __global__ void __launch_bounds__(256) k_emit2(EncBatchDev b, HeaderDev h, u8* o
                 r2++;
             }
         }
-        const u32 bo = 4u * W;
-        const u32 nbytes = ck.seq_size - bo < 4u ? ck.seq_size - bo : 4u;
-        for (u32 k = 0; k < nbytes; k++) col[bo + k] = (u8)(word >> (8 * k));
+        store_word(W, word);
     }
 }
 

@@ -21,17 +21,23 @@
 
 namespace rpq {
 
-/* code_fwd / code_rc words plus the "is a plain base" test; returns packed 2-bit codes of 4 bytes and clears `clean` otherwise */
+/* 2-bit codes of four bases by bit arithmetic on the ASCII codes (A 0x41, C 0x43, G 0x47, T 0x54: bits 2..1 tell them apart),
+ * checked by mapping the codes back through a 4-entry PRMT table and comparing with the input; a word holding anything else
+ * takes the exact compare path (codes_fwd / codes_rc: every other byte is code 0) and clears `clean`. */
 __device__ __forceinline__ u32 codes_fwd_clean(u32 w, u32 valid_mask, bool& clean) {
-    const u32 a = __vcmpeq4(w, 0x41414141u), t = __vcmpeq4(w, 0x54545454u), c = __vcmpeq4(w, 0x43434343u), g = __vcmpeq4(w, 0x47474747u);
-    if (((a | t | c | g) & valid_mask) != valid_mask) clean = false;
-    return (a & 0x01010101u) | (t & 0x02020202u) | (c & 0x03030303u);
+    u32 c = ((w ^ (w >> 1)) & 0x02020202u) | ((~w >> 2) & 0x01010101u);                /* G0 A1 T2 C3 */
+    const u32 t = c | (c >> 4);
+    const u32 expect = __byte_perm(0x43544147u, 0u, __byte_perm(t, 0u, 0x4420));       /* code -> "GATC" */
+    if ((expect ^ w) & valid_mask) { clean = false; c = codes_fwd(w); }
+    return c;
 }
 __device__ __forceinline__ u32 codes_rc_clean(u32 w, u32 valid_mask, bool& clean) {
     const u32 l = w | 0x20202020u;
-    const u32 a = __vcmpeq4(l, 0x61616161u), t = __vcmpeq4(l, 0x74747474u), c = __vcmpeq4(l, 0x63636363u), g = __vcmpeq4(l, 0x67676767u);
-    if (((a | t | c | g) & valid_mask) != valid_mask) clean = false;
-    return (a & 0x02020202u) | (t & 0x01010101u) | (g & 0x03030303u);
+    u32 c = (~(l ^ (l >> 1)) & 0x02020202u) | ((l >> 2) & 0x01010101u);                 /* code of the complement */
+    const u32 t = c | (c >> 4);
+    const u32 expect = __byte_perm(0x67617463u, 0u, __byte_perm(t, 0u, 0x4420));       /* code -> "ctag" */
+    if ((expect ^ l) & valid_mask) { clean = false; c = codes_rc(w); }
+    return c;
 }
 
 __device__ inline bool pack_forward_c(const u32* words, u32 off, int len, u32* dst, int pkw) {

@@ -68,11 +68,14 @@ struct RunCtx {
     const u8* lut; u32 mode, nstreams; int tid;
 };
 
-/* replay the runs of one 64-position segment; WRITE: emit token bytes, else count them */
+/* replay the runs of one 64-position segment.  WRITE: emit token bytes into the slot.  Otherwise count them and keep up to
+ * seven token bytes per (stream, thread) in `tok` (byte 7 = how many), so that the write pass is a plain copy; returns false
+ * when some stream of the thread did not fit (the thread then replays its runs with WRITE). */
 template <bool WRITE>
-__device__ inline void s3_runs(const RunCtx& R, u64 nm, const u64 eq, const S2Tables& T, u8* slot, const EncBatchDev& b, const ChunkDev& ck) {
+__device__ inline bool s3_runs(const RunCtx& R, u64 nm, const u64 eq, const S2Tables& T, u64* tok, u8* slot, const EncBatchDev& b, const ChunkDev& ck) {
     auto at = [&](u32 p) -> u8 { return p >= R.sm_lo ? R.sm[p - R.sm_lo] : stream_byte_slow(b, ck, R.mode, p); };
     const u32 exc_stream = R.nstreams - 1;
+    bool fits = true;
     while (nm) {
         const int i = __ffsll((long long)nm) - 1;
         const u32 p = R.s + (u32)i;
@@ -90,6 +93,7 @@ __device__ inline void s3_runs(const RunCtx& R, u64 nm, const u64 eq, const S2Ta
                 off += 5;
             }
             T.cnt[idx] = off;
+            fits = false;
             continue;
         }
         if (cls == LUT_SKIP) continue;                          /* only when the major quality is not a stream: never set in NM */
@@ -99,6 +103,14 @@ __device__ inline void s3_runs(const RunCtx& R, u64 nm, const u64 eq, const S2Ta
         if (r_end == R.e) { const u32 lim = R.e + 32u < R.n ? R.e + 32u : R.n; while (r_end < lim && at(r_end) == v) r_end++; }
         const bool crossing = i == 0 && (eq & 1ull);
         u32 off = T.cnt[idx];
+        u64 tk = 0; u32 tn = 0;
+        if (!WRITE) { const u64 w = tok[idx]; tn = (u32)(w >> 56); tk = w & 0x00FFFFFFFFFFFFFFull; }
+        auto put = [&](u32 byte) {
+            if (WRITE) slot[off] = (u8)byte;
+            else if (tn < 7u) { tk |= (u64)(byte & 0xFFu) << (8u * tn); tn++; }
+            else fits = false;
+            off++;
+        };
         u32 head;
         if (crossing) {
             u32 p0 = p - 1; while (p0 > 0 && at(p0 - 1) == v) p0--;
@@ -117,22 +129,23 @@ __device__ inline void s3_runs(const RunCtx& R, u64 nm, const u64 eq, const S2Ta
                 else { emit = false; if (!WRITE) T.first[idx] = (u16)(p - R.lo); }
             }
             if (emit) {
-                if (dm1 < 128u) { if (WRITE) slot[off] = (u8)dm1; off += 1; }
-                else if (dm1 < (1u << 14)) { if (WRITE) { slot[off] = (u8)(0x80u | (dm1 >> 8)); slot[off + 1] = (u8)dm1; } off += 2; }
-                else { if (WRITE) { slot[off] = (u8)(0xE0u | (dm1 >> 24)); slot[off + 1] = (u8)(dm1 >> 16); slot[off + 2] = (u8)(dm1 >> 8); slot[off + 3] = (u8)dm1; } off += 4; }
+                if (dm1 < 128u) put(dm1);
+                else if (dm1 < (1u << 14)) { put(0x80u | (dm1 >> 8)); put(dm1); }
+                else { put(0xE0u | (dm1 >> 24)); put(dm1 >> 16); put(dm1 >> 8); put(dm1); }
             }
-            if (p == 0 && r_end > 1 && 1u < R.e) { if (WRITE) slot[off] = 0x00; off += 1; }       /* Q16 */
+            if (p == 0 && r_end > 1 && 1u < R.e) put(0x00);       /* Q16 */
             head = p + (p == 0 ? 2u : 1u);
         }
         const u32 stop = r_end < R.e ? r_end : R.e;
         for (; head < stop; head += 32u) {
             const u32 len = r_end - head < 32u ? r_end - head : 32u;
-            if (WRITE) slot[off] = (u8)(0xC0u | (len - 1u));
-            off += 1;
+            put(0xC0u | (len - 1u));
         }
         T.cnt[idx] = off;
         T.last[idx] = (u16)(stop - 1u - R.lo);
+        if (!WRITE) tok[idx] = tk | ((u64)tn << 56);
     }
+    return fits;
 }
 
 __global__ void __launch_bounds__(S2_THREADS) k_streams3(EncBatchDev b, HeaderDev h, StreamJob job, const u32* __restrict__ span_chunk) {
@@ -155,13 +168,14 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams3(EncBatchDev b, HeaderDe
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     u8* sm = dyn;
     S2Tables T;
-    T.cnt = reinterpret_cast<u32*>(dyn + ST_SPAN + 2 * ST_HALO);
+    u64* tok = reinterpret_cast<u64*>(dyn + ST_SPAN + 2 * ST_HALO);        /* [nstreams][256] recorded token bytes */
+    T.cnt = reinterpret_cast<u32*>(tok + nstreams * S2_THREADS);
     T.first = reinterpret_cast<u16*>(T.cnt + nstreams * S2_THREADS);
     T.last = T.first + nstreams * S2_THREADS;
     T.fdist = T.last + nstreams * S2_THREADS;
 
     s_lut[tid] = h.lut[tid];
-    for (u32 k = tid; k < nstreams * S2_THREADS; k += S2_THREADS) { T.cnt[k] = 0; T.first[k] = (u16)S2_NONE; T.last[k] = (u16)S2_NONE; T.fdist[k] = 0; }
+    for (u32 k = tid; k < nstreams * S2_THREADS; k += S2_THREADS) { tok[k] = 0; T.cnt[k] = 0; T.first[k] = (u16)S2_NONE; T.last[k] = (u16)S2_NONE; T.fdist[k] = 0; }
     for (u32 k = tid; k < 8; k += S2_THREADS) if (sm_hi - sm_lo + k < (u32)(ST_SPAN + 2 * ST_HALO)) sm[sm_hi - sm_lo + k] = mode == 0 ? h.major : (u8)0;
     if (mode == 0) stage_quality_words(b, ck, sm_lo, sm_hi, sm, job.span_read0[span]);
     else stage_positions(b, h, ck, mode, sm_lo, sm_hi, sm);
@@ -175,22 +189,29 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams3(EncBatchDev b, HeaderDe
         const u32* W = reinterpret_cast<const u32*>(sm + (s - sm_lo));
         const bool major_is_stream = mode == 0 && s_lut[h.major] != LUT_SKIP;
         const u32 mmmm = 0x01010101u * h.major;
-        u32 prevb = s > 0 ? (u32)sm[s - 1 - sm_lo] : 0x100u;
+        /* eight positions per multiply: SIMD byte compares leave a flag in bit 7 of every byte, pack8f gathers the flags of two
+         * words into one byte in position order */
+        u32 prevw = s > 0 ? (u32)sm[s - 1 - sm_lo] << 24 : 0u;           /* the byte before the segment in the top byte */
+        u32 nmw[2] = {0, 0}, eqw[2] = {0, 0};
 #pragma unroll
-        for (int j = 0; j < S2_SEG / 4; j++) {
-            const u32 w = W[j];
-            const u32 shifted = (w << 8) | (prevb & 0xFFu);
-            u32 e4 = pack4(__vcmpeq4(w, shifted));
-            if (j == 0 && prevb > 0xFFu) e4 &= ~1u;
-            const u32 n4 = mode == 0 ? (major_is_stream ? 0xFu : pack4(__vcmpne4(w, mmmm))) : pack4(__vcmpeq4(w, 0x4E4E4E4Eu));
-            nm |= (u64)n4 << (4 * j); eq |= (u64)e4 << (4 * j);
-            prevb = w >> 24;
+        for (int j = 0; j < S2_SEG / 4; j += 2) {
+            const u32 w0 = W[j], w1 = W[j + 1];
+            const u32 e0 = eq_bytes(w0, __funnelshift_l(prevw, w0, 8)), e1 = eq_bytes(w1, __funnelshift_l(w0, w1, 8));
+            u32 n0, n1;
+            if (mode == 0) { n0 = major_is_stream ? 0x80808080u : eq_bytes(w0, mmmm) ^ 0x80808080u; n1 = major_is_stream ? 0x80808080u : eq_bytes(w1, mmmm) ^ 0x80808080u; }
+            else { n0 = eq_bytes(w0, 0x4E4E4E4Eu); n1 = eq_bytes(w1, 0x4E4E4E4Eu); }
+            const u32 eb = (((e0 >> 4) | e1) * 0x00204081u) >> 24, nb = (((n0 >> 4) | n1) * 0x00204081u) >> 24;
+            eqw[j >> 3] |= eb << (8 * ((j >> 1) & 3)); nmw[j >> 3] |= nb << (8 * ((j >> 1) & 3));
+            prevw = w1;
         }
+        if (s == 0) eqw[0] &= ~1u;                                       /* position 0 has no predecessor */
+        nm = (u64)nmw[0] | ((u64)nmw[1] << 32); eq = (u64)eqw[0] | ((u64)eqw[1] << 32);
         const u32 valid = e - s;
         if (valid < 64u) nm &= (1ull << valid) - 1ull;
     }
     RunCtx R; R.sm = sm; R.sm_lo = sm_lo; R.n = n; R.lo = lo; R.s = s; R.e = e; R.lut = s_lut; R.mode = mode; R.nstreams = nstreams; R.tid = tid;
-    if (nm) s3_runs<false>(R, nm, eq, T, nullptr, b, ck);
+    bool fits = true;
+    if (nm) fits = s3_runs<false>(R, nm, eq, T, tok, nullptr, b, ck);
     __syncthreads();
 
     /* per stream (a warp each): resolve first tokens against earlier segments of the span, exclusive scan of the byte counts */
@@ -242,7 +263,22 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams3(EncBatchDev b, HeaderDe
     for (u32 st = tid; st < nstreams; st += S2_THREADS) job.dir[(size_t)span * nstreams + st].slot_off = s_base[st];
     for (u32 k = tid; k < nstreams * S2_THREADS; k += S2_THREADS) { T.cnt[k] += s_base[k / S2_THREADS]; T.last[k] = (u16)S2_NONE; }
     __syncthreads();
-    if (nm && s_bytes) s3_runs<true>(R, nm, eq, T, job.slots + s_slot, b, ck);
+    if (!nm || !s_bytes) return;
+    u8* slot = job.slots + s_slot;
+    if (!fits) { s3_runs<true>(R, nm, eq, T, tok, slot, b, ck); return; }
+    /* the write pass of a thread whose tokens were recorded: a first distance token sized by the scan, then the recorded bytes */
+    for (u32 st = 0; st < nstreams; st++) {
+        const u32 idx = st * S2_THREADS + (u32)tid;
+        const u64 w = tok[idx];
+        const u32 tn = (u32)(w >> 56);
+        u8* o = slot + T.cnt[idx];
+        if (T.first[idx] & S2_RESOLVED) {
+            const u32 dm1 = T.fdist[idx];
+            if (dm1 < 128u) { o[0] = (u8)dm1; o += 1; }
+            else { o[0] = (u8)(0x80u | (dm1 >> 8)); o[1] = (u8)dm1; o += 2; }
+        }
+        for (u32 k = 0; k < tn; k++) o[k] = (u8)(w >> (8u * k));
+    }
 }
 
 }  // namespace rpq
