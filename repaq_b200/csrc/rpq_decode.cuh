@@ -243,11 +243,14 @@ __global__ void __launch_bounds__(256) k_dec_offsets(DecBatchDev b) {
  * Token length depends on the first byte only (0xxxxxxx:1  10xxxxxx:2  110xxxxx:1  111xxxxx:4), so the heads of a
  * step follow from its entry offset by visiting just the bytes that look like multi-byte heads; every head's position
  * is an exclusive warp sum of the advances before it.
- * grid.x = chunks, blockIdx.y = stream (quality bins, then exceptions, then N positions), one warp each (blockDim 32).
+ * A warp per (chunk, stream); DS_WARPS chunks per CTA (same stream index: similar lengths), blockIdx.y = stream (quality bins, then
+ * exceptions, then N positions).
  */
-__global__ void __launch_bounds__(32) k_dec_streams(DecBatchDev b, HeaderDev h, u32 n_qstreams, u32 chunk_base) {
-    const u32 c = chunk_base + blockIdx.x, st = blockIdx.y;
-    const int lane = threadIdx.x;
+constexpr int DS_WARPS = 4;
+__global__ void __launch_bounds__(32 * DS_WARPS) k_dec_streams(DecBatchDev b, HeaderDev h, u32 n_qstreams, u32 chunk_base, u32 chunk_end) {
+    const u32 c = chunk_base + blockIdx.x * DS_WARPS + (threadIdx.x >> 5), st = blockIdx.y;
+    if (c >= chunk_end) return;
+    const int lane = threadIdx.x & 31;
     const DecChunk& ck = b.chunks[c];
     const u8* in = b.body + ck.in_off;
     const u8* stream; u32 slen; u8 q; bool is_npos = false;
@@ -284,6 +287,7 @@ __global__ void __launch_bounds__(32) k_dec_streams(DecBatchDev b, HeaderDev h, 
     const u32 sh = 8u * (u32)(sa & 3u);
     const u32* Aend = reinterpret_cast<const u32*>((reinterpret_cast<uintptr_t>(b.body + b.body_len) + 3u) & ~(uintptr_t)3);
     auto ldw = [&](u32 k) -> u32 { const u32* w = A + k; return w < Aend ? *w : 0u; };
+    const u64 lim_pos = is_npos ? (nmap_bits < dst_len ? (u64)nmap_bits : (u64)dst_len) : (u64)dst_len;      /* positions >= this are ignored (Q20) */
     long long last = -1;
     u32 skip = 0;                                         /* payload bytes at the start of the step that belong to the previous token */
     u32 cura = slen ? ldw((u32)lane) : 0u;
@@ -339,13 +343,19 @@ __global__ void __launch_bounds__(32) k_dec_streams(DecBatchDev b, HeaderDev h, 
         for (int k = 0; k < 4; k++) {
             if (adv[k]) {
                 const long long endpos = acc + (long long)adv[k];      /* position of the token's last element */
-                const long long first = run[k] ? endpos - run[k] + 1 : endpos;
-                for (long long pos = first; pos <= endpos; pos++) {
-                    if (pos < 0) continue;
-                    if (is_npos) { if ((u64)pos < nmap_bits && (u64)pos < dst_len) atomicOr(&nmap[pos >> 5], 1u << (pos & 31)); }
-                    else if ((u64)pos < dst_len) plane[pos] = q;
-                }
                 acc = endpos;
+                long long first = run[k] ? endpos - run[k] + 1 : endpos;
+                if (first < 0) first = 0;
+                const long long lastp = endpos < (long long)lim_pos ? endpos : (long long)lim_pos - 1;
+                if (first <= lastp) {
+                    const u32 n = (u32)(lastp - first) + 1u;            /* 1..32 positions */
+                    if (is_npos) { for (u32 j = 0; j < n; j++) { const u64 pos = (u64)first + j; atomicOr(&nmap[pos >> 5], 1u << (pos & 31)); } }
+                    else {
+                        u8* d = plane + first;
+                        d[0] = q; if (n > 1) d[1] = q; if (n > 2) d[2] = q; if (n > 3) d[3] = q;
+                        for (u32 j = 4; j < n; j++) d[j] = q;
+                    }
+                }
             }
         }
         last += tot;

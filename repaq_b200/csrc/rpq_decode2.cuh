@@ -89,7 +89,10 @@ namespace rpq {
  *                   any mismatch makes the host fall back to the exact sequential walk (k_dec_walk).
  */
 __global__ void k_dec_walk_fast(const u8* body, u64 len, HeaderDev h, DecChunk* chunks, u32 cap, u32* n_out, u64* consumed) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    /* all 32 lanes follow the chain redundantly (broadcast loads); lane 0 records, and every lane warms L2 around the place
+     * the header after the next one is expected (chunks of one file are nearly the same size) */
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
     u64 at = 0; u32 n = 0, read_base = 0;
     const u32 head = 18u + ((h.flags & RPQ_ENCODE_N_POS) ? 4u : 0u);
     while (at + head <= len && n < cap) {
@@ -102,12 +105,20 @@ __global__ void k_dec_walk_fast(const u8* body, u64 len, HeaderDev h, DecChunk* 
         if (!(h.flags & RPQ_HAS_NAME2)) bytes -= (fl & RPQ_NAME2_LEN_SAME) ? 1 : reads;
         if (!(h.flags & RPQ_HAS_TILE)) bytes -= 2ll * ((fl & RPQ_TILE_SAME) ? 1 : xy);
         if (bytes < (long long)head || at + (u64)bytes > len) break;
-        DecChunk c; memset(&c, 0, sizeof c);
-        c.in_off = at; c.reads = reads; c.flags = fl; c.bytes = (u32)bytes; c.read_base = read_base;
-        chunks[n] = c;
+#ifndef RPQ_EMU
+        {
+            const long long pf = (long long)at + 2ll * bytes + ((long long)lane - 16) * 128;
+            if (pf >= 0 && (u64)pf + 128 <= len) asm volatile("prefetch.global.L2 [%0];" ::"l"(body + pf));
+        }
+#endif
+        if (lane == 0) {
+            DecChunk c; memset(&c, 0, sizeof c);
+            c.in_off = at; c.reads = reads; c.flags = fl; c.bytes = (u32)bytes; c.read_base = read_base;
+            chunks[n] = c;
+        }
         n++; read_base += reads; at += (u64)bytes;
     }
-    *n_out = n; *consumed = at;
+    if (lane == 0) { *n_out = n; *consumed = at; }
 }
 
 __global__ void __launch_bounds__(128) k_dec_describe(const u8* body, HeaderDev h, DecChunk* chunks, u32 n_chunks, u32* mismatch) {

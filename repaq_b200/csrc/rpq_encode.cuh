@@ -502,6 +502,8 @@ struct StreamJob {                   /* one per kind (quality / N positions) */
     u32* overflow;                   /* set when slot_cap was too small: the host grows it and repeats the batch */
     const u32* n_spans;              /* actual number of spans (the grid is an upper bound) */
     u32* span_read0;                 /* [spans] chunk-relative index of the first read whose positions reach into the span's staging window */
+    u32* redo_count;                 /* k_streams4: spans left to k_streams3 ... */
+    u32* redo_list;                  /* ... and which */
     u32 nstreams;                    /* nb + 1 (exceptions) for quality; 1 for N positions */
     u32 mode;                        /* 0 quality, 1 N positions */
 };

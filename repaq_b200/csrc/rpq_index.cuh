@@ -224,41 +224,51 @@ struct UnitStats {
 
 __global__ void k_unit_lengths(EncBatchDev b, u32 n_units, u32* __restrict__ rlen, u32* __restrict__ unit_bases, UnitStats* st) {
     const u32 u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n_units) return;
+    const bool live = u < n_units;
     const u32 per = b.is_pe ? 2u : 1u;
     u32 bases = 0;
     bool empty = false, badq = false, badn = false, badl = false;
     u32 longest = 0, head = 0;
-    for (u32 k = 0; k < per; k++) {
-        const u32 i = u * per + k;
-        u32 f, rec; read_locus(b, i, f, rec);
-        const TextDev& t = b.t[f];
-        u32 ln[4];
-#pragma unroll
-        for (u32 j = 0; j < 4; j++) { const u32 L = 4 * rec + j; ln[j] = line_end(t, L) - line_start(t, L); }
-        if (!ln[0] || !ln[1] || !ln[2] || !ln[3]) empty = true;
-        if (ln[1] != ln[3]) badq = true;
-        if (ln[0] > 255 || ln[2] > 255) badn = true;
-        if (ln[1] > 65535) badl = true;
-        rlen[i] = ln[1];
-        {
+    if (live) {
+        for (u32 k = 0; k < per; k++) {
+            const u32 i = u * per + k;
+            u32 f, rec; read_locus(b, i, f, rec);
+            const TextDev& t = b.t[f];
             uint4 lc;
             lc.x = line_start(t, 4 * rec); lc.y = line_start(t, 4 * rec + 1); lc.z = line_start(t, 4 * rec + 2); lc.w = line_start(t, 4 * rec + 3);
+            const u32 e3 = line_end(t, 4 * rec + 3);
+            /* a line ends where the next one starts, minus its break */
+            const u32 brk = 1u + t.crlf;
+            const u32 ln0 = lc.y - brk - lc.x, ln1 = lc.z - brk - lc.y, ln2 = lc.w - brk - lc.z, ln3 = e3 - lc.w;
+            if (!ln0 || !ln1 || !ln2 || !ln3) empty = true;
+            if (ln1 != ln3) badq = true;
+            if (ln0 > 255 || ln2 > 255) badn = true;
+            if (ln1 > 65535) badl = true;
+            rlen[i] = ln1;
             b.loc[i] = lc;
             head = lc.w - lc.x > head ? lc.w - lc.x : head;
+            longest = ln1 > longest ? ln1 : longest;
+            bases += ln1;
         }
-        longest = ln[1] > longest ? ln[1] : longest;
-        bases += ln[1];
+        unit_bases[u] = bases;
     }
-    unit_bases[u] = bases;
-    if (empty) atomicMin(&st->first_empty, u);
-    if (badq) atomicMin(&st->first_qual_len, u);
-    if (badn) atomicMin(&st->first_name_len, u);
-    if (badl) atomicMin(&st->first_read_len, u);
-    atomicMin(&st->min_bases, bases);
-    atomicMax(&st->max_bases, bases);
-    atomicMax(&st->max_read, longest);
-    atomicMax(&st->max_head, head);
+    /* one atomic per warp and statistic */
+    const u32 FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const u32 w_empty = __reduce_min_sync(FULL, empty ? u : 0xFFFFFFFFu), w_badq = __reduce_min_sync(FULL, badq ? u : 0xFFFFFFFFu);
+    const u32 w_badn = __reduce_min_sync(FULL, badn ? u : 0xFFFFFFFFu), w_badl = __reduce_min_sync(FULL, badl ? u : 0xFFFFFFFFu);
+    const u32 w_min = __reduce_min_sync(FULL, live ? bases : 0xFFFFFFFFu), w_max = __reduce_max_sync(FULL, bases);
+    const u32 w_long = __reduce_max_sync(FULL, longest), w_head = __reduce_max_sync(FULL, head);
+    if (lane == 0) {
+        if (w_empty != 0xFFFFFFFFu) atomicMin(&st->first_empty, w_empty);
+        if (w_badq != 0xFFFFFFFFu) atomicMin(&st->first_qual_len, w_badq);
+        if (w_badn != 0xFFFFFFFFu) atomicMin(&st->first_name_len, w_badn);
+        if (w_badl != 0xFFFFFFFFu) atomicMin(&st->first_read_len, w_badl);
+        if (w_min != 0xFFFFFFFFu) atomicMin(&st->min_bases, w_min);
+        atomicMax(&st->max_bases, w_max);
+        atomicMax(&st->max_read, w_long);
+        atomicMax(&st->max_head, w_head);
+    }
 }
 
 /*

@@ -63,6 +63,73 @@ __device__ inline void stage_quality_words(const EncBatchDev& b, const ChunkDev&
     }
 }
 
+/*
+ * Flat staging: the reads reaching into [lo, hi) go into a small table (offset of the first quality, start of the quality line);
+ * a thread then fills 16 bytes at a time: one binary search per 16 bytes, per word an unaligned 4-byte fetch (two aligned loads and a
+ * funnel shift, byte-reversed on the reverse strand).  Every lane works on every step, whatever the read lengths are
+ * (stage_quality_words gives a read to a warp: 150-base reads keep 38 of 64 lanes busy and pay ~60 instructions of per-read set-up).
+ * Returns false when the table is too small; the caller then uses stage_quality_words.
+ */
+constexpr int SQ_CAP = 383;                        /* reads per staged window the table can hold */
+__device__ inline bool stage_quality_flat(const EncBatchDev& b, const ChunkDev& ck, u32 lo, u32 hi, u8* sm, u32 first_rel, u32* s_off, u32* s_q, u32* s_n) {
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    if (hi <= lo) return true;
+    if (tid == 0) *s_n = 0;
+    __syncthreads();
+    for (u32 k = tid; k <= (u32)SQ_CAP; k += nthreads) {
+        const u32 rel = first_rel + k;
+        u32 off = ck.total_len, qs = 0;
+        if (rel < ck.count) { const u32 i = ck.first + rel; off = b.qualoff[i]; qs = b.loc[i].w; }
+        s_off[k] = off;
+        if (k < (u32)SQ_CAP) s_q[k] = qs;
+        if (rel < ck.count && off < hi) atomicMax(s_n, k + 1u);
+    }
+    __syncthreads();
+    const u32 n = *s_n;                                  /* reads 0..n-1 start below hi; s_off[n] >= hi is the end of the last one */
+    if (n > (u32)SQ_CAP) return false;
+    u32* smw = reinterpret_cast<u32*>(sm);
+    const bool pe_files = b.is_pe && b.two_files;
+    const u32 ngroups = (hi - lo + 15u) >> 4;
+    for (u32 g = tid; g < ngroups; g += nthreads) {
+        const u32 pos0 = lo + 16u * g;
+        u32 a = 0, z = n;                                /* largest r with s_off[r] <= pos0 */
+        while (z - a > 1u) { const u32 mid = (a + z) >> 1; if (s_off[mid] <= pos0) a = mid; else z = mid; }
+        u32 r = a;
+#pragma unroll
+        for (u32 w = 0; w < 4; w++) {
+            const u32 pos = pos0 + 4u * w;
+            if (pos >= hi) break;
+            u32 nxt = s_off[r + 1];
+            while (pos >= nxt) { r++; nxt = s_off[r + 1]; }
+            if (pos + 4u <= nxt && pos + 4u <= hi) {
+                const u32 off = s_off[r], rl = nxt - off, j = pos - off;
+                const u32 rel = first_rel + r;
+                const u8* q = b.t[pe_files ? (rel & 1u) : 0u].text + s_q[r];
+                const bool rev = ck.interleaved && (rel & 1u);
+                const uintptr_t ga = reinterpret_cast<uintptr_t>(rev ? q + (rl - 4u - j) : q + j);
+                const u32* al = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
+                const u32 sh = (u32)(ga & 3u) * 8u;
+                u32 v = al[0];
+                if (sh) v = __funnelshift_r(v, al[1], sh);
+                smw[(pos - lo) >> 2] = rev ? __byte_perm(v, 0, 0x0123) : v;
+            } else {
+                u32 r2 = r;
+                for (u32 bb = 0; bb < 4u; bb++) {
+                    const u32 pp = pos + bb;
+                    if (pp >= hi) break;
+                    while (pp >= s_off[r2 + 1]) r2++;
+                    const u32 off = s_off[r2], rl = s_off[r2 + 1] - off, j = pp - off;
+                    const u32 rel = first_rel + r2;
+                    const u8* q = b.t[pe_files ? (rel & 1u) : 0u].text + s_q[r2];
+                    const bool rev = ck.interleaved && (rel & 1u);
+                    sm[pp - lo] = rev ? q[rl - 1u - j] : q[j];
+                }
+            }
+        }
+    }
+    return true;
+}
+
 struct RunCtx {
     const u8* sm; u32 sm_lo, n, lo, s, e;
     const u8* lut; u32 mode, nstreams; int tid;
@@ -148,14 +215,14 @@ __device__ inline bool s3_runs(const RunCtx& R, u64 nm, const u64 eq, const S2Ta
     return fits;
 }
 
-__global__ void __launch_bounds__(S2_THREADS) k_streams3(EncBatchDev b, HeaderDev h, StreamJob job, const u32* __restrict__ span_chunk) {
+__global__ void __launch_bounds__(S2_THREADS) k_streams3(EncBatchDev b, HeaderDev h, StreamJob job, const u32* __restrict__ span_chunk, u32 from_redo_list) {
     RPQ_DYN_SMEM(dyn);
     __shared__ u8 s_lut[256];
     __shared__ u32 s_total[MAX_BINS + 2];
     __shared__ u32 s_base[MAX_BINS + 2];
     __shared__ u64 s_slot;
     __shared__ u32 s_bytes;
-    const u32 span = blockIdx.x;
+    const u32 span = from_redo_list ? job.redo_list[blockIdx.x] : blockIdx.x;     /* the spans k_streams4 passed on, or all of them */
     if (span >= *job.n_spans) return;
     const u32 c = span_chunk[span];
     const ChunkDev& ck = b.chunks[c];
@@ -177,8 +244,11 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams3(EncBatchDev b, HeaderDe
     s_lut[tid] = h.lut[tid];
     for (u32 k = tid; k < nstreams * S2_THREADS; k += S2_THREADS) { tok[k] = 0; T.cnt[k] = 0; T.first[k] = (u16)S2_NONE; T.last[k] = (u16)S2_NONE; T.fdist[k] = 0; }
     for (u32 k = tid; k < 8; k += S2_THREADS) if (sm_hi - sm_lo + k < (u32)(ST_SPAN + 2 * ST_HALO)) sm[sm_hi - sm_lo + k] = mode == 0 ? h.major : (u8)0;
-    if (mode == 0) stage_quality_words(b, ck, sm_lo, sm_hi, sm, job.span_read0[span]);
-    else stage_positions(b, h, ck, mode, sm_lo, sm_hi, sm);
+    if (mode == 0) {
+        u32* s_off = reinterpret_cast<u32*>(T.fdist + nstreams * S2_THREADS);      /* [SQ_CAP + 1] */
+        if (!stage_quality_flat(b, ck, sm_lo, sm_hi, sm, job.span_read0[span], s_off, s_off + SQ_CAP + 1, &s_bytes))
+            stage_quality_words(b, ck, sm_lo, sm_hi, sm, job.span_read0[span]);
+    } else stage_positions(b, h, ck, mode, sm_lo, sm_hi, sm);
     __syncthreads();
 
     /* ---- masks of the thread's 64 positions */

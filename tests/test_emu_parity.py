@@ -122,6 +122,46 @@ def test_fallback_kernels_forced(monkeypatch):
         cd.close()
 
 
+def test_stream_coder_generations(monkeypatch):
+    """RPQ_DEBUG_NO_STREAMS4=1: k_streams3 codes every span (it otherwise only sees the spans k_streams4 hands over); and inputs
+    built to need that hand-over inside otherwise ordinary chunks: runs of hundreds of equal non-major qualities, qualities the
+    header alphabet does not hold (exception records), a run over the first two positions (Q16)"""
+    import numpy as np
+    from tools import fqgen
+    monkeypatch.setenv("RPQ_DEBUG_NO_STREAMS4", "1")
+    cd = K.Codec(lib_path=EMU)
+    try:
+        for name in ("nova_pe_k1000", "nova_pe_k100_npos", "bgi_se_varlen_k100", "nova_se_late_quality"):
+            parity.check_encode_golden(cd, name)
+    finally:
+        cd.close()
+    monkeypatch.delenv("RPQ_DEBUG_NO_STREAMS4")
+    cd = K.Codec(lib_path=EMU)
+    try:
+        r1, r2 = fqgen.generate(2500, seed=77, paired=True)
+        for buf, seed in ((r1, 1), (r2, 2)):
+            rnd = np.random.RandomState(seed)
+            lines = bytes(buf).split(b"\n")
+            nrec = (len(lines) - 1) // 4
+            for rec in rnd.choice(np.arange(400, nrec), 60, replace=False):      # after the first chunk: the header alphabet is fixed
+                q = bytearray(lines[4 * rec + 3])
+                kind = rnd.randint(4)
+                if kind == 0: q[:] = b"#" * len(q)                                  # a run longer than a segment
+                elif kind == 1: q[10:140] = b"," * 130
+                elif kind == 2: q[5:9] = b"5678"                                     # not in the alphabet: exceptions
+                else: q[0:3] = b":::"
+                lines[4 * rec + 3] = bytes(q)
+            if seed == 1:
+                q = bytearray(lines[3]); q[0:2] = b",,"; lines[3] = bytes(q)          # Q16: positions 0 and 1 of the chunk
+                r1m = b"\n".join(lines)
+            else:
+                r2m = b"\n".join(lines)
+        parity.check_against_oracle(cd, r1m, r2m, k=100)
+        parity.check_against_oracle(cd, r1m, k=100)
+    finally:
+        cd.close()
+
+
 def test_pipelined_host_windows(monkeypatch):
     """the pipelined host path (windows over three lanes) must give the same bytes as one batch; tiny windows via
     RPQ_DEBUG_PIPE_WINDOW so that several windows fit a test input"""
@@ -135,3 +175,26 @@ def test_pipelined_host_windows(monkeypatch):
         parity.check_against_oracle(cd, r1, r2, k=100)
     finally:
         cd.close()
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_short_reads_many_per_span(codec, paired):
+    """reads of 3..40 bases: more reads reach into one 16 K-position span than the flat staging table of k_streams3 holds
+    (fallback to the warp-per-read staging), and runs / tokens cross read boundaries everywhere"""
+    import random
+    from tools import fqgen
+
+    def shorten(buf, seed):
+        rnd = random.Random(seed)
+        lines = bytes(buf).split(b"\n")
+        out = []
+        for k in range(0, len(lines) - 3, 4):
+            n = rnd.randint(3, 40)
+            out += [lines[k], lines[k + 1][:n], lines[k + 2], lines[k + 3][:n]]
+        return b"\n".join(out) + b"\n"
+
+    r = fqgen.generate(6000, seed=11, paired=paired)
+    if paired:
+        parity.check_against_oracle(codec, shorten(r[0], 1), shorten(r[1], 2), k=100)
+    else:
+        parity.check_against_oracle(codec, shorten(r[0], 1), k=100)
