@@ -247,8 +247,32 @@ __global__ void __launch_bounds__(256) k_dec_offsets(DecBatchDev b) {
  * exceptions, then N positions).
  */
 constexpr int DS_WARPS = 4;
-__global__ void __launch_bounds__(32 * DS_WARPS) k_dec_streams(DecBatchDev b, HeaderDev h, u32 n_qstreams, u32 chunk_base, u32 chunk_end) {
-    const u32 c = chunk_base + blockIdx.x * DS_WARPS + (threadIdx.x >> 5), st = blockIdx.y;
+/* stream indices by decreasing length in chunk `c0`: the CTAs of the longest stream are scheduled first (no long tail) */
+__global__ void k_dec_stream_order(DecBatchDev b, HeaderDev h, u32 c0, u32 n_qstreams, u32 n_streams, u32* __restrict__ order) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const DecChunk& ck = b.chunks[c0];
+    const u8* qcol = b.body + ck.in_off + ck.off_qual;
+    u32 len[MAX_BINS + 3];
+    u64 sum = 4ull * h.nb;
+    for (u32 st = 0; st < n_streams; st++) {
+        u32 l = 0;
+        if (st < n_qstreams) {
+            if (!(h.flags & RPQ_DONT_ENCODE_QUAL) && 4ull * h.nb <= ck.qual_size) {
+                if (st < h.nb) { l = ld32(qcol + 4 * st); sum += l; }
+                else l = ck.qual_size > sum ? (u32)(ck.qual_size - sum) : 0u;
+            }
+        } else l = ck.npos_size;
+        len[st] = l;
+    }
+    for (u32 st = 0; st < n_streams; st++) {
+        u32 rank = 0;
+        for (u32 o = 0; o < n_streams; o++) if (len[o] > len[st] || (len[o] == len[st] && o < st)) rank++;
+        order[rank] = st;
+    }
+}
+
+__global__ void __launch_bounds__(32 * DS_WARPS) k_dec_streams(DecBatchDev b, HeaderDev h, u32 n_qstreams, u32 chunk_base, u32 chunk_end, const u32* __restrict__ order) {
+    const u32 c = chunk_base + blockIdx.x * DS_WARPS + (threadIdx.x >> 5), st = order[blockIdx.y];
     if (c >= chunk_end) return;
     const int lane = threadIdx.x & 31;
     const DecChunk& ck = b.chunks[c];
@@ -353,7 +377,13 @@ __global__ void __launch_bounds__(32 * DS_WARPS) k_dec_streams(DecBatchDev b, He
                     else {
                         u8* d = plane + first;
                         d[0] = q; if (n > 1) d[1] = q; if (n > 2) d[2] = q; if (n > 3) d[3] = q;
-                        for (u32 j = 4; j < n; j++) d[j] = q;
+                        if (n > 4u) {                                  /* the rest of a long run: bytes up to a word boundary, words, bytes */
+                            u8* w = d + 4; u8* const we = d + n;
+                            while (w < we && (reinterpret_cast<uintptr_t>(w) & 3u)) *w++ = q;
+                            const u32 q4 = 0x01010101u * q;
+                            for (; w + 4 <= we; w += 4) *reinterpret_cast<u32*>(w) = q4;
+                            while (w < we) *w++ = q;
+                        }
                     }
                 }
             }

@@ -66,8 +66,9 @@ __global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines(const u8* __rest
     RPQ_DYN_SMEM(dyn);
     __shared__ u32 s_tile;
     __shared__ u32 s_wtot[IDX_THREADS / 32];
-    __shared__ u32 s_prefix;
+    __shared__ u32 s_un[IDX_THREADS / 32], s_pr[IDX_THREADS / 32], s_sum;
     __shared__ u32 s_cr, s_crlf;
+    u32 s_prefix_reg = 0;
 #ifndef RPQ_EMU
     __shared__ __align__(8) unsigned long long s_mbar[IDX_THREADS / 32];
 #endif
@@ -142,43 +143,56 @@ __global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines(const u8* __rest
 #pragma unroll
     for (int w = 0; w < IDX_THREADS / 32; w++) { const u32 t = s_wtot[w]; btot += t; if (w < warp) wpre += t; }
 
-    if (warp == 0) {
+    /* ---- rank base: chained scan over tiles, decoupled look-back with the WHOLE CTA probing (512 predecessors per round).
+     * The CTAs in flight are all in about the same phase, so a tile usually has to sum the aggregates of every tile that is in
+     * flight before it meets a finished prefix; a single warp needed ~14 probe rounds for that, which was most of a tile's time. */
+    {
         volatile u64* st = tile_state;
+        if (tid == 0 && tile > 0) { st[tile] = TS_AGG | btot; __threadfence(); }
         u32 prefix = 0;
         if (tile > 0) {
-            if (lane == 0) { st[tile] = TS_AGG | btot; __threadfence(); }
-            int j = (int)tile - 1;                       /* newest predecessor not yet accounted for */
+            int j = (int)tile - 1;                           /* newest predecessor not yet accounted for */
             for (;;) {
-                const int idx = j - lane;
-                u64 s = 2ull << 62;                       /* before tile 0: an empty prefix (TS_PREFIX | 0) */
-                if (idx >= 0) s = st[idx];
-                const u32 unset = __ballot_sync(0xffffffffu, (s & TS_MASK) == 0);
-                const u32 pre = __ballot_sync(0xffffffffu, (s & TS_MASK) == TS_PREFIX);
-                /* usable lanes: those before the first unset one, up to and including the first prefix */
-                const int first_unset = unset ? __ffs((int)unset) - 1 : 32;
-                const int first_pre = pre ? __ffs((int)pre) - 1 : 32;
-                const int upto = first_pre < first_unset ? first_pre + 1 : first_unset;   /* lanes [0, upto) are summed */
-                u32 v = lane < upto ? (u32)s : 0u;
-                prefix += warp_sum(v);
+                const int idx = j - tid;
+                u64 sv = 2ull << 62;                          /* before tile 0: an empty prefix (TS_PREFIX | 0) */
+                if (idx >= 0) sv = st[idx];
+                const u32 unset = __ballot_sync(0xffffffffu, (sv & TS_MASK) == 0);
+                const u32 pre = __ballot_sync(0xffffffffu, (sv & TS_MASK) == TS_PREFIX);
+                if (lane == 0) { s_un[warp] = unset; s_pr[warp] = pre; }
+                if (tid == 0) s_sum = 0;
+                __syncthreads();
+                int first_unset = IDX_THREADS, first_pre = IDX_THREADS;
+#pragma unroll
+                for (int w = IDX_THREADS / 32 - 1; w >= 0; w--) {
+                    const u32 u = s_un[w], q = s_pr[w];
+                    if (u) first_unset = 32 * w + __ffs((int)u) - 1;
+                    if (q) first_pre = 32 * w + __ffs((int)q) - 1;
+                }
+                /* usable predecessors: those before the first unset one, up to and including the first prefix */
+                const int upto = first_pre < first_unset ? first_pre + 1 : first_unset;
+                const u32 v = warp_sum(tid < upto ? (u32)sv : 0u);
+                if (lane == 0 && v) atomicAdd(&s_sum, v);
+                __syncthreads();
+                prefix += s_sum;
                 if (first_pre < first_unset) break;
                 j -= upto;
                 if (upto == 0) RPQ_SPIN_HINT();
+                __syncthreads();
             }
         }
-        if (lane == 0) {
+        if (tid == 0) {
             __threadfence();
             st[tile] = TS_PREFIX | (u64)(prefix + btot);
-            s_prefix = prefix;
             if (s_cr) atomicAdd(&ctr->n_cr, s_cr);
             if (s_crlf) atomicAdd(&ctr->n_crlf, s_crlf);
             if ((u64)(tile + 1) * IDX_TILE >= len) ctr->n_nl = prefix + btot;     /* the last tile knows the total */
         }
+        s_prefix_reg = prefix;
     }
-    __syncthreads();
 
     /* ---- positions: the eight masks of this thread, in text order */
     if (cnt) {
-        u32 o = s_prefix + wpre + ex_in_warp;
+        u32 o = s_prefix_reg + wpre + ex_in_warp;
         const uint4 mm = *reinterpret_cast<const uint4*>(my_masks);
         const u32 base = (u32)p0;
         u32 w[4] = {mm.x, mm.y, mm.z, mm.w};

@@ -89,42 +89,57 @@ __device__ inline bool stage_quality_flat(const EncBatchDev& b, const ChunkDev& 
     if (n > (u32)SQ_CAP) return false;
     u32* smw = reinterpret_cast<u32*>(sm);
     const bool pe_files = b.is_pe && b.two_files;
+    const bool il = ck.interleaved != 0;
+    /* pass 1: the words that lie inside one read.  The read of a group's first position is guessed from the mean read length
+     * (exact when all reads are equally long) and corrected by stepping. */
     const u32 ngroups = (hi - lo + 15u) >> 4;
+    const u32 off0 = s_off[0];
+    const float per_pos = n ? (float)n / (float)(s_off[n] - off0) : 0.f;
     for (u32 g = tid; g < ngroups; g += nthreads) {
         const u32 pos0 = lo + 16u * g;
-        u32 a = 0, z = n;                                /* largest r with s_off[r] <= pos0 */
-        while (z - a > 1u) { const u32 mid = (a + z) >> 1; if (s_off[mid] <= pos0) a = mid; else z = mid; }
-        u32 r = a;
+        u32 r = (u32)((float)(pos0 - off0) * per_pos);
+        if (r >= n) r = n - 1u;
+        while (s_off[r] > pos0) r--;
+        u32 nxt = s_off[r + 1];
+        while (pos0 >= nxt) { r++; nxt = s_off[r + 1]; }
+        u32 off = s_off[r];
+        const u8* q = b.t[pe_files ? ((first_rel + r) & 1u) : 0u].text + s_q[r];
+        bool rev = il && ((first_rel + r) & 1u);
 #pragma unroll
         for (u32 w = 0; w < 4; w++) {
             const u32 pos = pos0 + 4u * w;
-            if (pos >= hi) break;
-            u32 nxt = s_off[r + 1];
-            while (pos >= nxt) { r++; nxt = s_off[r + 1]; }
-            if (pos + 4u <= nxt && pos + 4u <= hi) {
-                const u32 off = s_off[r], rl = nxt - off, j = pos - off;
-                const u32 rel = first_rel + r;
-                const u8* q = b.t[pe_files ? (rel & 1u) : 0u].text + s_q[r];
-                const bool rev = ck.interleaved && (rel & 1u);
-                const uintptr_t ga = reinterpret_cast<uintptr_t>(rev ? q + (rl - 4u - j) : q + j);
+            if (pos + 4u > hi) break;                              /* the last, partial word: pass 2 */
+            if (pos >= nxt) {
+                do { r++; nxt = s_off[r + 1]; } while (pos >= nxt);
+                off = s_off[r];
+                q = b.t[pe_files ? ((first_rel + r) & 1u) : 0u].text + s_q[r];
+                rev = il && ((first_rel + r) & 1u);
+            }
+            if (pos + 4u <= nxt) {
+                const u32 j = pos - off;
+                const uintptr_t ga = reinterpret_cast<uintptr_t>(rev ? q + ((nxt - off) - 4u - j) : q + j);
                 const u32* al = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
                 const u32 sh = (u32)(ga & 3u) * 8u;
                 u32 v = al[0];
                 if (sh) v = __funnelshift_r(v, al[1], sh);
                 smw[(pos - lo) >> 2] = rev ? __byte_perm(v, 0, 0x0123) : v;
-            } else {
-                u32 r2 = r;
-                for (u32 bb = 0; bb < 4u; bb++) {
-                    const u32 pp = pos + bb;
-                    if (pp >= hi) break;
-                    while (pp >= s_off[r2 + 1]) r2++;
-                    const u32 off = s_off[r2], rl = s_off[r2 + 1] - off, j = pp - off;
-                    const u32 rel = first_rel + r2;
-                    const u8* q = b.t[pe_files ? (rel & 1u) : 0u].text + s_q[r2];
-                    const bool rev = ck.interleaved && (rel & 1u);
-                    sm[pp - lo] = rev ? q[rl - 1u - j] : q[j];
-                }
             }
+        }
+    }
+    /* pass 2: the words that hold the end of a read (bytes of two or more reads), and the partial word at hi: a thread each */
+    for (u32 r = tid; r <= n; r += nthreads) {
+        const u32 bnd = r < n ? s_off[r + 1] : hi;                 /* end of read r; r == n: the end of the window */
+        if (r < n && bnd >= hi) continue;                          /* beyond the window (the window's end is r == n's) */
+        const u32 wpos = bnd & ~3u;
+        if (wpos == bnd || wpos < lo) continue;
+        u32 r2 = r < n ? r : n - 1u;
+        for (u32 pp = wpos; pp < wpos + 4u && pp < hi; pp++) {
+            while (r2 > 0 && s_off[r2] > pp) r2--;
+            while (pp >= s_off[r2 + 1]) r2++;
+            const u32 off = s_off[r2], rl = s_off[r2 + 1] - off, j = pp - off;
+            const u32 rel = first_rel + r2;
+            const u8* q = b.t[pe_files ? (rel & 1u) : 0u].text + s_q[r2];
+            sm[pp - lo] = (il && (rel & 1u)) ? q[rl - 1u - j] : q[j];
         }
     }
     return true;

@@ -216,17 +216,25 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams4(EncBatchDev b, HeaderDe
         if (valid) roff[k] = (unsigned short)myoff;
     }
     __syncthreads();
-    /* ---- P2: block offsets per stream, directory, slot */
-    for (u32 st = tid; st < nstreams; st += S2_THREADS) {
+    /* ---- P2: block offsets per stream (a warp per stream, a lane per block), directory, slot */
+    for (u32 st = warp; st < nstreams; st += S2_THREADS / 32) {
         u32 acc = 0;
-        for (u32 j = 0; j < nblocks; j++) { const u32 t = t_bytes[j * nstreams + st]; t_bytes[j * nstreams + st] = (unsigned short)acc; acc += t; }
-        const u32 kl = s_total[st];
-        u32 lastpos = NONE32;
-        if (kl != RL_NONE && !(st == exc_stream && mode == 0)) { const u32 r_end = lo + rend[kl]; lastpos = (r_end < hi ? r_end : hi) - 1u; }
-        s_total[st] = acc;
-        SpanDir d; d.bytes = acc; d.slot_off = 0; d.firstpos = s_first[st]; d.lastpos = lastpos;
-        d.dst = 0; d.first_tok = 0; d.first_len = 0; d.pad = 0;
-        job.dir[(size_t)span * nstreams + st] = d;
+        for (u32 j0 = 0; j0 < nblocks; j0 += 32) {
+            const u32 j = j0 + (u32)lane;
+            const u32 t = j < nblocks ? (u32)t_bytes[j * nstreams + st] : 0u;
+            u32 tot; const u32 exs = warp_excl_scan(t, lane, tot);
+            if (j < nblocks) t_bytes[j * nstreams + st] = (unsigned short)(acc + exs);
+            acc += tot;
+        }
+        if (lane == 0) {
+            const u32 kl = s_total[st];
+            u32 lastpos = NONE32;
+            if (kl != RL_NONE && !(st == exc_stream && mode == 0)) { const u32 r_end = lo + rend[kl]; lastpos = (r_end < hi ? r_end : hi) - 1u; }
+            s_total[st] = acc;
+            SpanDir d; d.bytes = acc; d.slot_off = 0; d.firstpos = s_first[st]; d.lastpos = lastpos;
+            d.dst = 0; d.first_tok = 0; d.first_len = 0; d.pad = 0;
+            job.dir[(size_t)span * nstreams + st] = d;
+        }
     }
     __syncthreads();
     if (tid == 0) {
