@@ -245,7 +245,7 @@ int index_text(rpq_ctx* c, int f, const u8* d_text, u64 len, IndexCounters* hc) 
         IndexCounters* dc = c->counters.as<IndexCounters>() + f;
         rt_memset(c->tile_state.p, 0, sizeof(u64) * (tiles + 1), c->stream);
         rt_memset(dc, 0, sizeof(IndexCounters), c->stream);
-        LAUNCH(c, k_index_lines, tiles, IDX_THREADS, IDX_SMEM, d_text, len, c->nl[f].as<u32>(), (u32)cap, c->tile_state.as<u64>(), dc);
+        LAUNCH(c, k_index_lines, std::min<u32>(tiles, 3u * (u32)rt_sm_count()), IDX_THREADS, IDX_SMEM, d_text, len, c->nl[f].as<u32>(), (u32)cap, c->tile_state.as<u64>(), dc, tiles);
         LAUNCH(c, k_index_finish, 1, 32, 0, d_text, len, c->nl[f].as<u32>(), (u32)cap, dc);
         if (int rc = read_back(c, dc, hc)) return rc;
         if ((size_t)hc->n_nl + 1 <= cap) return RPQ_OK;

@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(256) k_dec_format3(DecBatchDev b, HeaderDev h,
     __shared__ u32 s_lut_fwd[256], s_lut_rc[256];
     const int tid = threadIdx.x;
     const u32 G = cfg.reads_per_cta;
-    /* two threads per read, in different warps (no divergence): threads [0,G) write name + sequence line, [G,2G) strand + quality line */
+    /* two threads per read, in different warps (no divergence): threads [0,G) write the sequence line, [G,2G) the name, strand and
+     * quality lines (about the same number of instructions each) */
     const int rt = tid < (int)G ? tid : tid - (int)G, half = tid < (int)G ? 0 : 1;
     const u32 i0 = read_first + blockIdx.x * G;          /* the launch covers reads [read_first, read_end) */
     const u32 n_here = read_end - i0 < G ? read_end - i0 : G;
@@ -63,13 +64,36 @@ __global__ void __launch_bounds__(256) k_dec_format3(DecBatchDev b, HeaderDev h,
     }
     __syncthreads();
     const u64 q0 = s_q0, q1 = s_q1, qa = q0 & ~15ull;
+    /* the CTA's slice of the quality plane: one TMA bulk copy, awaited only where a thread first needs the plane (the name lines
+     * are formatted while it is in flight) */
+    const u32 plane_bytes = (u32)((q1 - qa + 15) >> 4) << 4;
+#ifdef RPQ_EMU
     {
-        const u32 nvec = (u32)((q1 - qa + 15) >> 4);
         const uint4* src = reinterpret_cast<const uint4*>(b.plane + qa);
         uint4* dst = reinterpret_cast<uint4*>(s_plane);
-        for (u32 k = tid; k < nvec; k += blockDim.x) dst[k] = src[k];
+        for (u32 k = tid; k < plane_bytes / 16u; k += blockDim.x) dst[k] = src[k];
     }
     __syncthreads();
+    auto plane_ready = [&]() {};
+#else
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const u32 mbar = (u32)__cvta_generic_to_shared(&s_mbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (plane_bytes) {
+            asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(mbar), "r"(plane_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((u32)__cvta_generic_to_shared(s_plane)), "l"(b.plane + qa), "r"(plane_bytes), "r"(mbar) : "memory");
+        } else asm volatile("mbarrier.arrive.shared.b64 _, [%0];" ::"r"(mbar) : "memory");
+    }
+    __syncthreads();                                           /* the barrier object is initialised for everybody */
+    auto plane_ready = [&]() {
+        u32 done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar) : "memory");
+    };
+#endif
 
     if (active) {
         const DecChunk& ck = b.chunks[c];
@@ -84,7 +108,7 @@ __global__ void __launch_bounds__(256) k_dec_format3(DecBatchDev b, HeaderDev h,
         /* ---- strand length first: it fixes where every part of the record lies */
         const u32 ls = (fl & (RPQ_STRAND_SAME | RPQ_STRAND_LEN_SAME)) ? in[ck.off_slen] : in[ck.off_slen + r];
         const u32 name_end = olen - (2u * rl + ls + 3u);          /* bytes of the name line including its line break */
-        if (half == 0) {
+        if (half == 1) {
         u32 w_at = 0;
         /* ---- name (reference src/rfqcodec.cpp:1157-1231) */
         const u32 l1 = (fl & (RPQ_NAME1_SAME | RPQ_NAME1_LEN_SAME)) ? in[ck.off_n1len] : in[ck.off_n1len + r];
@@ -115,6 +139,7 @@ __global__ void __launch_bounds__(256) k_dec_format3(DecBatchDev b, HeaderDev h,
             o_qual[rl] = '\n';
         }
 
+        plane_ready();
         /* ---- sequence + quality, four positions per step */
         const u8* seqb = in + ck.off_seq;
         const u32* nmap = b.nmap + ck.nmap_off;

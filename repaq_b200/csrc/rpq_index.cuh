@@ -18,7 +18,7 @@ constexpr int IDX_ROW = 128;                                 /* bytes per thread
 constexpr int IDX_PIECES = IDX_ROW / 16;
 constexpr int IDX_WARP_BYTES = 32 * IDX_ROW;                 /* 4 KiB per warp: one TMA bulk copy */
 constexpr int IDX_TILE = IDX_THREADS * IDX_ROW;              /* 64 KiB per CTA */
-constexpr int IDX_SMEM = IDX_TILE + IDX_THREADS * 16;        /* the tile + eight 16-bit newline masks per thread */
+constexpr int IDX_SMEM = IDX_TILE;                            /* the tile */
 
 struct IndexCounters {
     u32 ticket;     /* dynamic tile id */
@@ -54,158 +54,164 @@ __device__ __forceinline__ u32 mask16(u32 m0, u32 m1, u32 m2, u32 m3) {
 }
 
 /*
- * One pass over the text: positions of every '\n', in order.  A CTA takes a 64 KiB tile, brought into shared memory by one
- * TMA bulk copy per warp (4 KiB); a thread owns 128 contiguous bytes (its pieces read in a lane-rotated order, so that the
- * 128-bit shared loads of a quarter warp fall into eight different bank groups), turns them into eight exact 16-bit
- * newline masks with SIMD-in-register compares, and counts.  One scan per CTA, then the chained scan over tiles with a
- * warp-wide decoupled look-back (32 predecessors per probe) gives the rank base; every thread then writes its own
- * positions.  '\r' is only tested for ("any in these 16 bytes"); files that have them take the exact path.
+ * One pass over the text: positions of every '\n', in order.  Persistent CTAs take 64 KiB tiles by ticket.  A tile is brought into
+ * shared memory by one TMA bulk copy per warp (4 KiB); a thread owns 128 contiguous bytes (its pieces read in a lane-rotated
+ * order, so that the 128-bit shared loads of a quarter warp fall into eight different bank groups), turns them into eight exact
+ * 16-bit newline masks (kept in two 64-bit registers) with SIMD-in-register compares, and counts.  The tile's count is published
+ * at once; its rank base - the chained scan over tiles with a decoupled look-back, the whole CTA probing 512 predecessors per
+ * round - is only resolved one tile LATER, after the next tile's copy has been started, and then the positions are written:
+ * by then the predecessors (which were all in the same phase) have published their counts, so nobody waits on the chain.
+ * '\r' is only tested for ("any in these 16 bytes"); files that have them take the exact path.
  */
 __global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines(const u8* __restrict__ text, u64 len, u32* __restrict__ nl, u32 nl_cap,
-                                                               u64* tile_state, IndexCounters* ctr) {
+                                                               u64* tile_state, IndexCounters* ctr, u32 n_tiles) {
     RPQ_DYN_SMEM(dyn);
     __shared__ u32 s_tile;
     __shared__ u32 s_wtot[IDX_THREADS / 32];
     __shared__ u32 s_un[IDX_THREADS / 32], s_pr[IDX_THREADS / 32], s_sum;
     __shared__ u32 s_cr, s_crlf;
-    u32 s_prefix_reg = 0;
 #ifndef RPQ_EMU
     __shared__ __align__(8) unsigned long long s_mbar[IDX_THREADS / 32];
 #endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_tile = atomicAdd(&ctr->ticket, 1u); s_cr = 0; s_crlf = 0; }
+    if (tid == 0) { s_cr = 0; s_crlf = 0; }
 #ifndef RPQ_EMU
     if (tid < IDX_THREADS / 32) {
         asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"((u32)__cvta_generic_to_shared(&s_mbar[tid])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    u32 parity = 0;
 #endif
-    __syncthreads();
-    const u32 tile = s_tile;
-    const u64 tbase = (u64)tile * IDX_TILE;
     u8* row = dyn + (size_t)tid * IDX_ROW;
-    unsigned short* my_masks = reinterpret_cast<unsigned short*>(dyn + IDX_TILE) + (size_t)tid * IDX_PIECES;
+    volatile u64* st = tile_state;
 
-    /* ---- stage */
-    const u64 wbase = tbase + (u64)warp * IDX_WARP_BYTES;
-    const u32 wbytes = wbase >= len ? 0u : (len - wbase >= IDX_WARP_BYTES ? (u32)IDX_WARP_BYTES : (u32)(((len - wbase) + 15) & ~15ull));
+    /* the tile whose positions are still to be written */
+    bool pending = false;
+    u32 p_tile = 0, p_off = 0, p_btot = 0, p_base = 0;
+    u64 p_lo = 0, p_hi = 0;
+
+    for (;;) {
+        __syncthreads();                                       /* everybody is done with the tile buffer (and with s_tile, s_wtot) */
+        if (tid == 0) s_tile = atomicAdd(&ctr->ticket, 1u);
+        __syncthreads();
+        const u32 tile = s_tile;
+        const bool have = tile < n_tiles;
+        const u64 tbase = (u64)tile * IDX_TILE;
+        const u64 wbase = tbase + (u64)warp * IDX_WARP_BYTES;
+        const u32 wbytes = (!have || wbase >= len) ? 0u : (len - wbase >= IDX_WARP_BYTES ? (u32)IDX_WARP_BYTES : (u32)(((len - wbase) + 15) & ~15ull));
+        /* ---- start the copy of the next tile */
 #ifdef RPQ_EMU
-    for (u32 k = lane; k < wbytes; k += 32) { const u64 p = wbase + k; dyn[(size_t)warp * IDX_WARP_BYTES + k] = p < len ? text[p] : 0; }
-    __syncwarp();
+        for (u32 k = lane; k < wbytes; k += 32) { const u64 p = wbase + k; dyn[(size_t)warp * IDX_WARP_BYTES + k] = p < len ? text[p] : 0; }
+        __syncwarp();
 #else
-    if (wbytes) {
         const u32 mbar = (u32)__cvta_generic_to_shared(&s_mbar[warp]);
-        if (lane == 0) {
+        if (wbytes && lane == 0) {
             const u32 dst = (u32)__cvta_generic_to_shared(dyn + (size_t)warp * IDX_WARP_BYTES);
             asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(mbar), "r"(wbytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(dst), "l"(text + wbase), "r"(wbytes), "r"(mbar) : "memory");
         }
-        u32 done = 0;
-        while (!done)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(mbar) : "memory");
-    }
 #endif
-    const u64 p0 = tbase + (u64)tid * IDX_ROW;                /* first byte of this thread's row */
-    const int lim = p0 >= len ? 0 : (len - p0 >= IDX_ROW ? IDX_ROW : (int)(len - p0));
-    if (lim < IDX_ROW) for (int i = lim; i < IDX_ROW; i++) row[i] = 0;     /* the end of the text: zeros match nothing */
-
-    /* ---- masks and counts */
-    u32 cnt = 0, ncr = 0, ncrlf = 0;
+        /* ---- finish the pending tile: rank base by look-back, then the positions */
+        if (pending) {
+            u32 prefix = 0;
+            if (p_tile > 0) {
+                int j = (int)p_tile - 1;                         /* newest predecessor not yet accounted for */
+                for (;;) {
+                    const int idx = j - tid;
+                    u64 sv = 2ull << 62;                          /* before tile 0: an empty prefix (TS_PREFIX | 0) */
+                    if (idx >= 0) sv = st[idx];
+                    const u32 unset = __ballot_sync(0xffffffffu, (sv & TS_MASK) == 0);
+                    const u32 pre = __ballot_sync(0xffffffffu, (sv & TS_MASK) == TS_PREFIX);
+                    if (lane == 0) { s_un[warp] = unset; s_pr[warp] = pre; }
+                    if (tid == 0) s_sum = 0;
+                    __syncthreads();
+                    int first_unset = IDX_THREADS, first_pre = IDX_THREADS;
 #pragma unroll
-    for (int k = 0; k < IDX_PIECES; k++) {
-        const int kk = (k + lane) & (IDX_PIECES - 1);
-        const uint4 v = *reinterpret_cast<const uint4*>(row + 16 * kk);
-        const u32 m = mask16(eq_lowascii(v.x, 0x0A0A0A0Au), eq_lowascii(v.y, 0x0A0A0A0Au), eq_lowascii(v.z, 0x0A0A0A0Au), eq_lowascii(v.w, 0x0A0A0A0Au));
-        const u32 nocr = ne_lowascii(v.x, 0x0D0D0D0Du) & ne_lowascii(v.y, 0x0D0D0D0Du) & ne_lowascii(v.z, 0x0D0D0D0Du) & ne_lowascii(v.w, 0x0D0D0D0Du);
-        my_masks[kk] = (unsigned short)m;
-        cnt += (u32)__popc(m);
-        if (~nocr & 0x80808080u) {
-            const u32 c = mask16(eq_lowascii(v.x, 0x0D0D0D0Du), eq_lowascii(v.y, 0x0D0D0D0Du), eq_lowascii(v.z, 0x0D0D0D0Du), eq_lowascii(v.w, 0x0D0D0D0Du));
-            ncr += (u32)__popc(c);
-            ncrlf += (u32)__popc(m & (c << 1));
-        }
-        if (m & 1u) {                                        /* a newline at the first byte of a piece: look one byte back */
-            const u64 p = p0 + 16u * (u32)kk;
-            u8 prev = 0;
-            if (kk > 0 || lane > 0) prev = row[16 * kk - 1];  /* rows of a warp are contiguous in shared memory */
-            else if (p > 0) prev = text[p - 1];
-            if (prev == '\r') ncrlf++;
-        }
-    }
-    u32 wtot;
-    const u32 ex_in_warp = warp_excl_scan(cnt, lane, wtot);
-    ncr = warp_sum(ncr); ncrlf = warp_sum(ncrlf);
-    if (lane == 0) { s_wtot[warp] = wtot; if (ncr) atomicAdd(&s_cr, ncr); if (ncrlf) atomicAdd(&s_crlf, ncrlf); }
-    __syncthreads();
-    u32 btot = 0, wpre = 0;
-#pragma unroll
-    for (int w = 0; w < IDX_THREADS / 32; w++) { const u32 t = s_wtot[w]; btot += t; if (w < warp) wpre += t; }
-
-    /* ---- rank base: chained scan over tiles, decoupled look-back with the WHOLE CTA probing (512 predecessors per round).
-     * The CTAs in flight are all in about the same phase, so a tile usually has to sum the aggregates of every tile that is in
-     * flight before it meets a finished prefix; a single warp needed ~14 probe rounds for that, which was most of a tile's time. */
-    {
-        volatile u64* st = tile_state;
-        if (tid == 0 && tile > 0) { st[tile] = TS_AGG | btot; __threadfence(); }
-        u32 prefix = 0;
-        if (tile > 0) {
-            int j = (int)tile - 1;                           /* newest predecessor not yet accounted for */
-            for (;;) {
-                const int idx = j - tid;
-                u64 sv = 2ull << 62;                          /* before tile 0: an empty prefix (TS_PREFIX | 0) */
-                if (idx >= 0) sv = st[idx];
-                const u32 unset = __ballot_sync(0xffffffffu, (sv & TS_MASK) == 0);
-                const u32 pre = __ballot_sync(0xffffffffu, (sv & TS_MASK) == TS_PREFIX);
-                if (lane == 0) { s_un[warp] = unset; s_pr[warp] = pre; }
-                if (tid == 0) s_sum = 0;
-                __syncthreads();
-                int first_unset = IDX_THREADS, first_pre = IDX_THREADS;
-#pragma unroll
-                for (int w = IDX_THREADS / 32 - 1; w >= 0; w--) {
-                    const u32 u = s_un[w], q = s_pr[w];
-                    if (u) first_unset = 32 * w + __ffs((int)u) - 1;
-                    if (q) first_pre = 32 * w + __ffs((int)q) - 1;
+                    for (int w = IDX_THREADS / 32 - 1; w >= 0; w--) {
+                        const u32 u = s_un[w], q = s_pr[w];
+                        if (u) first_unset = 32 * w + __ffs((int)u) - 1;
+                        if (q) first_pre = 32 * w + __ffs((int)q) - 1;
+                    }
+                    /* usable predecessors: those before the first unset one, up to and including the first prefix */
+                    const int upto = first_pre < first_unset ? first_pre + 1 : first_unset;
+                    const u32 v = warp_sum(tid < upto ? (u32)sv : 0u);
+                    if (lane == 0 && v) atomicAdd(&s_sum, v);
+                    __syncthreads();
+                    prefix += s_sum;
+                    if (first_pre < first_unset) break;
+                    j -= upto;
+                    if (upto == 0) RPQ_SPIN_HINT();
+                    __syncthreads();
                 }
-                /* usable predecessors: those before the first unset one, up to and including the first prefix */
-                const int upto = first_pre < first_unset ? first_pre + 1 : first_unset;
-                const u32 v = warp_sum(tid < upto ? (u32)sv : 0u);
-                if (lane == 0 && v) atomicAdd(&s_sum, v);
-                __syncthreads();
-                prefix += s_sum;
-                if (first_pre < first_unset) break;
-                j -= upto;
-                if (upto == 0) RPQ_SPIN_HINT();
-                __syncthreads();
             }
+            if (tid == 0) {
+                __threadfence();
+                st[p_tile] = TS_PREFIX | (u64)(prefix + p_btot);
+                if ((u64)(p_tile + 1) * IDX_TILE >= len) ctr->n_nl = prefix + p_btot;     /* the last tile knows the total */
+            }
+            u32 o = prefix + p_off;
+            u64 m = p_lo;
+            while (m) { const int bb = __ffsll((long long)m) - 1; m &= m - 1; if (o < nl_cap) nl[o] = p_base + (u32)bb; o++; }
+            m = p_hi;
+            while (m) { const int bb = __ffsll((long long)m) - 1; m &= m - 1; if (o < nl_cap) nl[o] = p_base + 64u + (u32)bb; o++; }
+            pending = false;
         }
-        if (tid == 0) {
-            __threadfence();
-            st[tile] = TS_PREFIX | (u64)(prefix + btot);
-            if (s_cr) atomicAdd(&ctr->n_cr, s_cr);
-            if (s_crlf) atomicAdd(&ctr->n_crlf, s_crlf);
-            if ((u64)(tile + 1) * IDX_TILE >= len) ctr->n_nl = prefix + btot;     /* the last tile knows the total */
-        }
-        s_prefix_reg = prefix;
-    }
+        if (!have) break;
 
-    /* ---- positions: the eight masks of this thread, in text order */
-    if (cnt) {
-        u32 o = s_prefix_reg + wpre + ex_in_warp;
-        const uint4 mm = *reinterpret_cast<const uint4*>(my_masks);
-        const u32 base = (u32)p0;
-        u32 w[4] = {mm.x, mm.y, mm.z, mm.w};
+        /* ---- the new tile: wait for its bytes */
+#ifndef RPQ_EMU
+        if (wbytes) {
+            u32 done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+            parity ^= 1u;
+        }
+#endif
+        const u64 p0 = tbase + (u64)tid * IDX_ROW;                /* first byte of this thread's row */
+        const int lim = p0 >= len ? 0 : (len - p0 >= IDX_ROW ? IDX_ROW : (int)(len - p0));
+        if (lim < IDX_ROW) for (int i = lim; i < IDX_ROW; i++) row[i] = 0;     /* the end of the text: zeros match nothing */
+
+        /* ---- masks and counts */
+        u32 cnt = 0, ncr = 0, ncrlf = 0;
+        u64 lo = 0, hi = 0;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            u32 m = w[q];
-            while (m) {
-                const int bb = __ffs((int)m) - 1;
-                m &= m - 1;
-                if (o < nl_cap) nl[o] = base + 32u * q + (u32)bb;
-                o++;
+        for (int k = 0; k < IDX_PIECES; k++) {
+            const int kk = (k + lane) & (IDX_PIECES - 1);
+            const uint4 v = *reinterpret_cast<const uint4*>(row + 16 * kk);
+            const u32 m = mask16(eq_lowascii(v.x, 0x0A0A0A0Au), eq_lowascii(v.y, 0x0A0A0A0Au), eq_lowascii(v.z, 0x0A0A0A0Au), eq_lowascii(v.w, 0x0A0A0A0Au));
+            const u32 nocr = ne_lowascii(v.x, 0x0D0D0D0Du) & ne_lowascii(v.y, 0x0D0D0D0Du) & ne_lowascii(v.z, 0x0D0D0D0Du) & ne_lowascii(v.w, 0x0D0D0D0Du);
+            const u64 placed = (u64)m << (16 * (kk & 3));
+            if (kk & 4) hi |= placed; else lo |= placed;
+            cnt += (u32)__popc(m);
+            if (~nocr & 0x80808080u) {
+                const u32 c = mask16(eq_lowascii(v.x, 0x0D0D0D0Du), eq_lowascii(v.y, 0x0D0D0D0Du), eq_lowascii(v.z, 0x0D0D0D0Du), eq_lowascii(v.w, 0x0D0D0D0Du));
+                ncr += (u32)__popc(c);
+                ncrlf += (u32)__popc(m & (c << 1));
+            }
+            if (m & 1u) {                                        /* a newline at the first byte of a piece: look one byte back */
+                const u64 p = p0 + 16u * (u32)kk;
+                u8 prev = 0;
+                if (kk > 0 || lane > 0) prev = row[16 * kk - 1];  /* rows of a warp are contiguous in shared memory */
+                else if (p > 0) prev = text[p - 1];
+                if (prev == '\r') ncrlf++;
             }
         }
+        u32 wtot;
+        const u32 ex_in_warp = warp_excl_scan(cnt, lane, wtot);
+        ncr = warp_sum(ncr); ncrlf = warp_sum(ncrlf);
+        if (lane == 0) { s_wtot[warp] = wtot; if (ncr) atomicAdd(&s_cr, ncr); if (ncrlf) atomicAdd(&s_crlf, ncrlf); }
+        __syncthreads();
+        u32 btot = 0, wpre = 0;
+#pragma unroll
+        for (int w = 0; w < IDX_THREADS / 32; w++) { const u32 t = s_wtot[w]; btot += t; if (w < warp) wpre += t; }
+        if (tid == 0 && tile > 0) { st[tile] = TS_AGG | btot; __threadfence(); }
+        pending = true; p_tile = tile; p_off = wpre + ex_in_warp; p_btot = btot; p_base = (u32)p0; p_lo = lo; p_hi = hi;
+    }
+    if (tid == 0) {
+        if (s_cr) atomicAdd(&ctr->n_cr, s_cr);
+        if (s_crlf) atomicAdd(&ctr->n_crlf, s_crlf);
     }
 }
 

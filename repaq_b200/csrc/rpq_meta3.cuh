@@ -21,27 +21,13 @@
 
 namespace rpq {
 
-/* 2-bit codes of four bases by bit arithmetic on the ASCII codes (A 0x41, C 0x43, G 0x47, T 0x54: bits 2..1 tell them apart),
- * checked by mapping the codes back through a 4-entry PRMT table and comparing with the input; a word holding anything else
- * takes the exact compare path (codes_fwd / codes_rc: every other byte is code 0) and clears `clean`. */
-__device__ __forceinline__ u32 codes_fwd_clean(u32 w, u32 valid_mask, bool& clean) {
-    u32 c = ((w ^ (w >> 1)) & 0x02020202u) | ((~w >> 2) & 0x01010101u);                /* G0 A1 T2 C3 */
-    const u32 t = c | (c >> 4);
-    const u32 expect = __byte_perm(0x43544147u, 0u, __byte_perm(t, 0u, 0x4420));       /* code -> "GATC" */
-    if ((expect ^ w) & valid_mask) { clean = false; c = codes_fwd(w); }
-    return c;
-}
-__device__ __forceinline__ u32 codes_rc_clean(u32 w, u32 valid_mask, bool& clean) {
-    const u32 l = w | 0x20202020u;
-    u32 c = (~(l ^ (l >> 1)) & 0x02020202u) | ((l >> 2) & 0x01010101u);                 /* code of the complement */
-    const u32 t = c | (c >> 4);
-    const u32 expect = __byte_perm(0x67617463u, 0u, __byte_perm(t, 0u, 0x4420));       /* code -> "ctag" */
-    if ((expect ^ l) & valid_mask) { clean = false; c = codes_rc(w); }
-    return c;
-}
-
-__device__ inline bool pack_forward_c(const u32* words, u32 off, int len, u32* dst, int pkw) {
+/* One code path for both strands (mates sit in neighbouring lanes: two functions would run one after the other).
+ * rev: the read is packed as its reverse complement; lower case counts as a plain base there (src/read.cpp:92-113). */
+__device__ inline bool pack_read_c(const u32* words, u32 off, int len, bool rev, u32* dst, int pkw) {
     bool clean = true;
+    const u32 sel = rev ? 0x0123u : 0x3210u;
+    const u32 lower = rev ? 0x20202020u : 0u, flip = rev ? 0x03030303u : 0u;
+    const u32 table = rev ? 0x63746167u : 0x43544147u;          /* code G0 A1 T2 C3 -> the character it came from */
     for (int j = 0; j < pkw; j++) {
         u32 acc = 0;
         const int base = j * 16;
@@ -51,32 +37,17 @@ __device__ inline bool pack_forward_c(const u32* words, u32 off, int len, u32* d
                 const int p = base + 4 * g;
                 if (p >= len) break;
                 const int left = len - p;
-                const u32 vm = left >= 4 ? 0xFFFFFFFFu : ((1u << (8 * left)) - 1u);
-                const u32 c = codes_fwd_clean(ld4(words, off + (u32)p), vm, clean) & vm;
-                acc |= squeeze4(c) << (8 * g);
-            }
-        }
-        dst[j] = acc;
-    }
-    return clean;
-}
-__device__ inline bool pack_revcomp_c(const u32* words, u32 off, int len, u32* dst, int pkw) {
-    bool clean = true;
-    for (int j = 0; j < pkw; j++) {
-        u32 acc = 0;
-        const int base = j * 16;
-        if (base < len) {
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                const int k = base + 4 * g;
-                if (k >= len) break;
-                const int left = len - k;
                 u32 w;
-                if (left >= 4) w = __byte_perm(ld4(words, off + (u32)(len - 4 - k)), 0, 0x0123);
-                else { w = 0; for (int q = 0; q < left; q++) w |= (u32)reinterpret_cast<const u8*>(words)[off + (u32)(len - 1 - k - q)] << (8 * q); }
+                if (left >= 4 || !rev) w = __byte_perm(ld4(words, off + (u32)(rev ? len - 4 - p : p)), 0, sel);
+                else { w = 0; for (int q = 0; q < left; q++) w |= (u32)reinterpret_cast<const u8*>(words)[off + (u32)(len - 1 - p - q)] << (8 * q); }
                 const u32 vm = left >= 4 ? 0xFFFFFFFFu : ((1u << (8 * left)) - 1u);
-                const u32 c = codes_rc_clean(w, vm, clean) & vm;
-                acc |= squeeze4(c) << (8 * g);
+                const u32 l = w | lower;
+                u32 c = ((l ^ (l >> 1)) & 0x02020202u) | ((~l >> 2) & 0x01010101u);
+                const u32 t = c | (c >> 4);
+                const u32 expect = __byte_perm(table, 0u, __byte_perm(t, 0u, 0x4420));
+                if ((expect ^ l) & vm) { clean = false; c = rev ? codes_rc(w) : codes_fwd(w); }      /* exact: every other byte is code 0 */
+                else c ^= flip;
+                acc |= squeeze4(c & vm) << (8 * g);
             }
         }
         dst[j] = acc;
@@ -234,9 +205,7 @@ __global__ void __launch_bounds__(256) k_meta3(EncBatchDev b, HeaderDev h, u32 n
         if (!eq0) { if (rel & 1u) atomicMax(&ck.last_odd_neq, rel + 1); else if (!*(volatile u32*)&ck.even_neq) atomicOr(&ck.even_neq, 1u); }
         /* ---- B: the read as it will be stored */
         const u32 so = s_seq[r] & 0xFFFFu;
-        bool clean;
-        if (rc_odd && (r & 1u)) clean = pack_revcomp_c(words, so, rlen, pkS + (size_t)r * cfg.pkw, (int)cfg.pkw);
-        else clean = pack_forward_c(words, so, rlen, pkS + (size_t)r * cfg.pkw, (int)cfg.pkw);
+        const bool clean = pack_read_c(words, so, rlen, rc_odd && (r & 1u), pkS + (size_t)r * cfg.pkw, (int)cfg.pkw);
         s_flag[r] = (u8)((eq0 ? 1u : 0u) | (clean ? 2u : 0u));
     }
     __syncthreads();

@@ -198,3 +198,36 @@ def test_short_reads_many_per_span(codec, paired):
         parity.check_against_oracle(codec, shorten(r[0], 1), shorten(r[1], 2), k=100)
     else:
         parity.check_against_oracle(codec, shorten(r[0], 1), k=100)
+
+
+def _mutate_bases(buf, seed):
+    """lower-case bases, N and IUPAC codes sprinkled over the sequence lines after the first chunk (the reference validates the
+    alphabet only while it builds the header, src/rfqcodec.cpp:20-145)"""
+    import numpy as np
+    rnd = np.random.RandomState(seed)
+    lines = bytes(buf).split(b"\n")
+    for k in range(1 + 4 * 700, len(lines) - 1, 4):
+        if rnd.rand() < 0.3:
+            s = bytearray(lines[k])
+            for _ in range(rnd.randint(1, 12)):
+                j = rnd.randint(len(s))
+                kind = rnd.randint(4)
+                s[j] = s[j] | 0x20 if kind == 0 else (ord("N") if kind == 1 else (ord("n") if kind == 2 else b"RYKM.-*"[rnd.randint(7)]))
+            if rnd.rand() < 0.2:
+                s[:] = bytes(s).lower()
+            lines[k] = bytes(s)
+    return b"\n".join(lines)
+
+
+def test_unclean_bases(codec, tmp_path):
+    """lower case (a plain base only for the reverse-complemented mate), N, IUPAC codes: the packed-word fast paths of k_meta3
+    must fall back exactly where the reference's per-character code differs; pinned against the reference binary when present"""
+    from oracle import oracle as O
+    from tools import fqgen
+    r1, r2 = fqgen.generate(3000, seed=21, paired=True)
+    m1, m2 = _mutate_bases(r1, 1), _mutate_bases(r2, 2)
+    if O.have_ref():
+        assert O.compress(m1, m2, chunk_bases=100000) == O.ref_compress(str(tmp_path), m1, m2, chunk_kb=100)
+        assert O.compress(m1, None, chunk_bases=100000) == O.ref_compress(str(tmp_path), m1, None, chunk_kb=100)
+    parity.check_against_oracle(codec, m1, m2, k=100, roundtrip=False)
+    parity.check_against_oracle(codec, m1, k=100, roundtrip=False)
