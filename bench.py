@@ -100,42 +100,60 @@ def cpu_reference_roundtrip(r1, r2, cores, budget_s=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region"""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi clocks / throttle reasons.  The sampler is started before the warm-up (nvidia-smi needs ~100 ms to come up,
+    the timed region of the default run is shorter than that); only samples stamped inside [begin(), end()] are used."""
+    Q = "timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu):
-        self.gpu, self.p, self.path = gpu, None, None
+        self.gpu, self.p, self.path, self.t0, self.t1 = gpu, None, None, None, None
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                       stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
     def stop(self):
         if not self.p:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.05)
         self.p.terminate()
         self.p.wait()
-        sm, mx, reasons = [], 0, set()
+        import datetime
+        rows = []
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx = max(mx, float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[2]), float(f[3]), f[6:10]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        os.unlink(self.path)
+        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
+        where = "timed region"
+        if not inside:                                  # a region shorter than the sampling period: the nearest samples around it
+            inside = [r for r in rows if self.t0 is not None and self.t0 - 0.25 <= r[0] <= self.t1 + 0.05]
+            where = "timed region +-0.25 s (region shorter than the sampling period)"
+        sm, mx, reasons = [], 0, set()
+        for _, clk, cmax, flags in inside:
+            sm.append(clk)
+            mx = max(mx, cmax)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.path)
         busy = [x for x in sm if x > 0]
-        return dict(sm_mhz=float(np.median(busy)) if busy else None, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=float(np.median(busy)) if busy else None, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm), sampled=where)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -262,13 +280,14 @@ def main():
     del o1, o2, rfq_dev
 
     # ---- timed: inputs resident in HBM (inputs are ~3.4 GB per step: far larger than the 126 MB L2, no flush needed)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(W):
         _, _, _, eo = step_device()
         gather_lengths(eo)
     barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
+    clocks.begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
     ev0.record(es)
@@ -283,6 +302,7 @@ def main():
     ev1.record(ds)
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    clocks.end()
     dev_ms = ev0.elapsed_time(ev1)                  # CUDA events: first encode op .. last decode op, host gaps included
     clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([dev_ms, wall_ms, enc_ms, dec_ms], dtype=torch.float64, device="cuda")

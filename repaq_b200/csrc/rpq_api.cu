@@ -44,6 +44,7 @@ struct rpq_ctx {
         d_in, d_desc, d_tmp[8], d_tmp2, out2;
     bool no_streams4 = false;              /* RPQ_DEBUG_NO_STREAMS4=1: k_streams3 codes every span (test coverage, A/B) */
     u64 stats_redo_spans = 0;              /* spans k_streams4 handed to k_streams3 */
+    int index_variant = 0;                 /* RPQ_DEBUG_INDEX=1: CTA-per-tile indexer (A/B) */
     u32 fmt_reads = 0;                     /* RPQ_DEBUG_FMT_READS=n: reads per formatter CTA (tuning experiments) */
     bool force_v1 = false;                 /* RPQ_DEBUG_FORCE_V1=1: take the long-read fallback kernels (test coverage) */
     bool no_pipeline = false;              /* RPQ_NO_PIPELINE=1: host batches are never cut into pipelined windows */
@@ -147,12 +148,14 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     memset(&c->stats, 0, sizeof c->stats);
     memset(&c->hdr, 0, sizeof c->hdr);
     { const char* e = getenv("RPQ_DEBUG_FORCE_V1"); c->force_v1 = e && e[0] == '1'; }
+    { const char* e = getenv("RPQ_DEBUG_INDEX"); c->index_variant = e ? atoi(e) : 0; }
     { const char* e = getenv("RPQ_DEBUG_NO_STREAMS4"); c->no_streams4 = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_DEBUG_FMT_READS"); c->fmt_reads = e ? (u32)atoi(e) : 0u; }
     { const char* e = getenv("RPQ_NO_PIPELINE"); c->no_pipeline = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_DEBUG_PIPE_WINDOW"); c->pipe_window = e ? strtoull(e, nullptr, 10) : 0; }
 #ifndef RPQ_EMU
     cudaFuncSetAttribute(k_index_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, IDX_SMEM);
+    cudaFuncSetAttribute(k_index_lines_tilecta, cudaFuncAttributeMaxDynamicSharedMemorySize, IDX_SMEM_TILECTA);
     cudaFuncSetAttribute(k_streams2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_streams3, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_streams4, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -245,7 +248,8 @@ int index_text(rpq_ctx* c, int f, const u8* d_text, u64 len, IndexCounters* hc) 
         IndexCounters* dc = c->counters.as<IndexCounters>() + f;
         rt_memset(c->tile_state.p, 0, sizeof(u64) * (tiles + 1), c->stream);
         rt_memset(dc, 0, sizeof(IndexCounters), c->stream);
-        LAUNCH(c, k_index_lines, std::min<u32>(tiles, 3u * (u32)rt_sm_count()), IDX_THREADS, IDX_SMEM, d_text, len, c->nl[f].as<u32>(), (u32)cap, c->tile_state.as<u64>(), dc, tiles);
+        if (c->index_variant == 1) LAUNCH(c, k_index_lines_tilecta, tiles, IDX_THREADS, IDX_SMEM_TILECTA, d_text, len, c->nl[f].as<u32>(), (u32)cap, c->tile_state.as<u64>(), dc);
+        else LAUNCH(c, k_index_lines, std::min<u32>(tiles, 3u * (u32)rt_sm_count()), IDX_THREADS, IDX_SMEM, d_text, len, c->nl[f].as<u32>(), (u32)cap, c->tile_state.as<u64>(), dc, tiles);
         LAUNCH(c, k_index_finish, 1, 32, 0, d_text, len, c->nl[f].as<u32>(), (u32)cap, dc);
         if (int rc = read_back(c, dc, hc)) return rc;
         if ((size_t)hc->n_nl + 1 <= cap) return RPQ_OK;

@@ -59,8 +59,9 @@ __device__ __forceinline__ u32 mask16(u32 m0, u32 m1, u32 m2, u32 m3) {
  * order, so that the 128-bit shared loads of a quarter warp fall into eight different bank groups), turns them into eight exact
  * 16-bit newline masks (kept in two 64-bit registers) with SIMD-in-register compares, and counts.  The tile's count is published
  * at once; its rank base - the chained scan over tiles with a decoupled look-back, the whole CTA probing 512 predecessors per
- * round - is only resolved one tile LATER, after the next tile's copy has been started, and then the positions are written:
- * by then the predecessors (which were all in the same phase) have published their counts, so nobody waits on the chain.
+ * round - is only resolved one tile LATER, after the next tile has been counted and published, and then the positions are
+ * written: by then the predecessors (which were all in the same phase) have published their counts.  Nothing that can wait
+ * sits between taking a ticket and publishing that tile's count, so a wait never cascades.
  * '\r' is only tested for ("any in these 16 bytes"); files that have them take the exact path.
  */
 __global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines(const u8* __restrict__ text, u64 len, u32* __restrict__ nl, u32 nl_cap,
@@ -112,6 +113,60 @@ __global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines(const u8* __rest
                          ::"r"(dst), "l"(text + wbase), "r"(wbytes), "r"(mbar) : "memory");
         }
 #endif
+        u32 cnt = 0, btot = 0, off_in_tile = 0;
+        u64 lo = 0, hi = 0;
+        u64 p0 = 0;
+        if (have) {
+
+        /* ---- the new tile: wait for its bytes */
+#ifndef RPQ_EMU
+        if (wbytes) {
+            u32 done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+            parity ^= 1u;
+        }
+#endif
+        p0 = tbase + (u64)tid * IDX_ROW;                /* first byte of this thread's row */
+        const int lim = p0 >= len ? 0 : (len - p0 >= IDX_ROW ? IDX_ROW : (int)(len - p0));
+        if (lim < IDX_ROW) for (int i = lim; i < IDX_ROW; i++) row[i] = 0;     /* the end of the text: zeros match nothing */
+
+        /* ---- masks and counts */
+        u32 ncr = 0, ncrlf = 0;
+#pragma unroll
+        for (int k = 0; k < IDX_PIECES; k++) {
+            const int kk = (k + lane) & (IDX_PIECES - 1);
+            const uint4 v = *reinterpret_cast<const uint4*>(row + 16 * kk);
+            const u32 m = mask16(eq_lowascii(v.x, 0x0A0A0A0Au), eq_lowascii(v.y, 0x0A0A0A0Au), eq_lowascii(v.z, 0x0A0A0A0Au), eq_lowascii(v.w, 0x0A0A0A0Au));
+            const u32 nocr = ne_lowascii(v.x, 0x0D0D0D0Du) & ne_lowascii(v.y, 0x0D0D0D0Du) & ne_lowascii(v.z, 0x0D0D0D0Du) & ne_lowascii(v.w, 0x0D0D0D0Du);
+            const u64 placed = (u64)m << (16 * (kk & 3));
+            if (kk & 4) hi |= placed; else lo |= placed;
+            cnt += (u32)__popc(m);
+            if (~nocr & 0x80808080u) {
+                const u32 c = mask16(eq_lowascii(v.x, 0x0D0D0D0Du), eq_lowascii(v.y, 0x0D0D0D0Du), eq_lowascii(v.z, 0x0D0D0D0Du), eq_lowascii(v.w, 0x0D0D0D0Du));
+                ncr += (u32)__popc(c);
+                ncrlf += (u32)__popc(m & (c << 1));
+            }
+            if (m & 1u) {                                        /* a newline at the first byte of a piece: look one byte back */
+                const u64 p = p0 + 16u * (u32)kk;
+                u8 prev = 0;
+                if (kk > 0 || lane > 0) prev = row[16 * kk - 1];  /* rows of a warp are contiguous in shared memory */
+                else if (p > 0) prev = text[p - 1];
+                if (prev == '\r') ncrlf++;
+            }
+        }
+        u32 wtot;
+        const u32 ex_in_warp = warp_excl_scan(cnt, lane, wtot);
+        ncr = warp_sum(ncr); ncrlf = warp_sum(ncrlf);
+        if (lane == 0) { s_wtot[warp] = wtot; if (ncr) atomicAdd(&s_cr, ncr); if (ncrlf) atomicAdd(&s_crlf, ncrlf); }
+        __syncthreads();
+        u32 wpre = 0;
+#pragma unroll
+        for (int w = 0; w < IDX_THREADS / 32; w++) { const u32 t = s_wtot[w]; btot += t; if (w < warp) wpre += t; }
+        if (tid == 0 && tile > 0) { st[tile] = TS_AGG | btot; __threadfence(); }     /* published before anything below can wait */
+        off_in_tile = wpre + ex_in_warp;
+        }
         /* ---- finish the pending tile: rank base by look-back, then the positions */
         if (pending) {
             u32 prefix = 0;
@@ -158,60 +213,148 @@ __global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines(const u8* __rest
             pending = false;
         }
         if (!have) break;
-
-        /* ---- the new tile: wait for its bytes */
-#ifndef RPQ_EMU
-        if (wbytes) {
-            u32 done = 0;
-            while (!done)
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-            parity ^= 1u;
-        }
-#endif
-        const u64 p0 = tbase + (u64)tid * IDX_ROW;                /* first byte of this thread's row */
-        const int lim = p0 >= len ? 0 : (len - p0 >= IDX_ROW ? IDX_ROW : (int)(len - p0));
-        if (lim < IDX_ROW) for (int i = lim; i < IDX_ROW; i++) row[i] = 0;     /* the end of the text: zeros match nothing */
-
-        /* ---- masks and counts */
-        u32 cnt = 0, ncr = 0, ncrlf = 0;
-        u64 lo = 0, hi = 0;
-#pragma unroll
-        for (int k = 0; k < IDX_PIECES; k++) {
-            const int kk = (k + lane) & (IDX_PIECES - 1);
-            const uint4 v = *reinterpret_cast<const uint4*>(row + 16 * kk);
-            const u32 m = mask16(eq_lowascii(v.x, 0x0A0A0A0Au), eq_lowascii(v.y, 0x0A0A0A0Au), eq_lowascii(v.z, 0x0A0A0A0Au), eq_lowascii(v.w, 0x0A0A0A0Au));
-            const u32 nocr = ne_lowascii(v.x, 0x0D0D0D0Du) & ne_lowascii(v.y, 0x0D0D0D0Du) & ne_lowascii(v.z, 0x0D0D0D0Du) & ne_lowascii(v.w, 0x0D0D0D0Du);
-            const u64 placed = (u64)m << (16 * (kk & 3));
-            if (kk & 4) hi |= placed; else lo |= placed;
-            cnt += (u32)__popc(m);
-            if (~nocr & 0x80808080u) {
-                const u32 c = mask16(eq_lowascii(v.x, 0x0D0D0D0Du), eq_lowascii(v.y, 0x0D0D0D0Du), eq_lowascii(v.z, 0x0D0D0D0Du), eq_lowascii(v.w, 0x0D0D0D0Du));
-                ncr += (u32)__popc(c);
-                ncrlf += (u32)__popc(m & (c << 1));
-            }
-            if (m & 1u) {                                        /* a newline at the first byte of a piece: look one byte back */
-                const u64 p = p0 + 16u * (u32)kk;
-                u8 prev = 0;
-                if (kk > 0 || lane > 0) prev = row[16 * kk - 1];  /* rows of a warp are contiguous in shared memory */
-                else if (p > 0) prev = text[p - 1];
-                if (prev == '\r') ncrlf++;
-            }
-        }
-        u32 wtot;
-        const u32 ex_in_warp = warp_excl_scan(cnt, lane, wtot);
-        ncr = warp_sum(ncr); ncrlf = warp_sum(ncrlf);
-        if (lane == 0) { s_wtot[warp] = wtot; if (ncr) atomicAdd(&s_cr, ncr); if (ncrlf) atomicAdd(&s_crlf, ncrlf); }
-        __syncthreads();
-        u32 btot = 0, wpre = 0;
-#pragma unroll
-        for (int w = 0; w < IDX_THREADS / 32; w++) { const u32 t = s_wtot[w]; btot += t; if (w < warp) wpre += t; }
-        if (tid == 0 && tile > 0) { st[tile] = TS_AGG | btot; __threadfence(); }
-        pending = true; p_tile = tile; p_off = wpre + ex_in_warp; p_btot = btot; p_base = (u32)p0; p_lo = lo; p_hi = hi;
+        pending = true; p_tile = tile; p_off = off_in_tile; p_btot = btot; p_base = (u32)p0; p_lo = lo; p_hi = hi;
     }
     if (tid == 0) {
         if (s_cr) atomicAdd(&ctr->n_cr, s_cr);
         if (s_crlf) atomicAdd(&ctr->n_crlf, s_crlf);
+    }
+}
+
+/* The previous arrangement, kept for A/B runs (RPQ_DEBUG_INDEX=1): a CTA per tile, the rank base resolved by warp 0 right after the
+ * tile was counted (the other 15 warps wait at a barrier for the look-back). */
+constexpr int IDX_SMEM_TILECTA = IDX_TILE + IDX_THREADS * 16;
+__global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines_tilecta(const u8* __restrict__ text, u64 len, u32* __restrict__ nl, u32 nl_cap,
+                                                               u64* tile_state, IndexCounters* ctr) {
+    RPQ_DYN_SMEM(dyn);
+    __shared__ u32 s_tile;
+    __shared__ u32 s_wtot[IDX_THREADS / 32];
+    __shared__ u32 s_prefix;
+    __shared__ u32 s_cr, s_crlf;
+#ifndef RPQ_EMU
+    __shared__ __align__(8) unsigned long long s_mbar[IDX_THREADS / 32];
+#endif
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_tile = atomicAdd(&ctr->ticket, 1u); s_cr = 0; s_crlf = 0; }
+#ifndef RPQ_EMU
+    if (tid < IDX_THREADS / 32) {
+        asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"((u32)__cvta_generic_to_shared(&s_mbar[tid])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#endif
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u64 tbase = (u64)tile * IDX_TILE;
+    u8* row = dyn + (size_t)tid * IDX_ROW;
+    unsigned short* my_masks = reinterpret_cast<unsigned short*>(dyn + IDX_TILE) + (size_t)tid * IDX_PIECES;
+
+    /* ---- stage */
+    const u64 wbase = tbase + (u64)warp * IDX_WARP_BYTES;
+    const u32 wbytes = wbase >= len ? 0u : (len - wbase >= IDX_WARP_BYTES ? (u32)IDX_WARP_BYTES : (u32)(((len - wbase) + 15) & ~15ull));
+#ifdef RPQ_EMU
+    for (u32 k = lane; k < wbytes; k += 32) { const u64 p = wbase + k; dyn[(size_t)warp * IDX_WARP_BYTES + k] = p < len ? text[p] : 0; }
+    __syncwarp();
+#else
+    if (wbytes) {
+        const u32 mbar = (u32)__cvta_generic_to_shared(&s_mbar[warp]);
+        if (lane == 0) {
+            const u32 dst = (u32)__cvta_generic_to_shared(dyn + (size_t)warp * IDX_WARP_BYTES);
+            asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(mbar), "r"(wbytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(text + wbase), "r"(wbytes), "r"(mbar) : "memory");
+        }
+        u32 done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mbar) : "memory");
+    }
+#endif
+    const u64 p0 = tbase + (u64)tid * IDX_ROW;                /* first byte of this thread's row */
+    const int lim = p0 >= len ? 0 : (len - p0 >= IDX_ROW ? IDX_ROW : (int)(len - p0));
+    if (lim < IDX_ROW) for (int i = lim; i < IDX_ROW; i++) row[i] = 0;     /* the end of the text: zeros match nothing */
+
+    /* ---- masks and counts */
+    u32 cnt = 0, ncr = 0, ncrlf = 0;
+#pragma unroll
+    for (int k = 0; k < IDX_PIECES; k++) {
+        const int kk = (k + lane) & (IDX_PIECES - 1);
+        const uint4 v = *reinterpret_cast<const uint4*>(row + 16 * kk);
+        const u32 m = mask16(eq_lowascii(v.x, 0x0A0A0A0Au), eq_lowascii(v.y, 0x0A0A0A0Au), eq_lowascii(v.z, 0x0A0A0A0Au), eq_lowascii(v.w, 0x0A0A0A0Au));
+        const u32 nocr = ne_lowascii(v.x, 0x0D0D0D0Du) & ne_lowascii(v.y, 0x0D0D0D0Du) & ne_lowascii(v.z, 0x0D0D0D0Du) & ne_lowascii(v.w, 0x0D0D0D0Du);
+        my_masks[kk] = (unsigned short)m;
+        cnt += (u32)__popc(m);
+        if (~nocr & 0x80808080u) {
+            const u32 c = mask16(eq_lowascii(v.x, 0x0D0D0D0Du), eq_lowascii(v.y, 0x0D0D0D0Du), eq_lowascii(v.z, 0x0D0D0D0Du), eq_lowascii(v.w, 0x0D0D0D0Du));
+            ncr += (u32)__popc(c);
+            ncrlf += (u32)__popc(m & (c << 1));
+        }
+        if (m & 1u) {                                        /* a newline at the first byte of a piece: look one byte back */
+            const u64 p = p0 + 16u * (u32)kk;
+            u8 prev = 0;
+            if (kk > 0 || lane > 0) prev = row[16 * kk - 1];  /* rows of a warp are contiguous in shared memory */
+            else if (p > 0) prev = text[p - 1];
+            if (prev == '\r') ncrlf++;
+        }
+    }
+    u32 wtot;
+    const u32 ex_in_warp = warp_excl_scan(cnt, lane, wtot);
+    ncr = warp_sum(ncr); ncrlf = warp_sum(ncrlf);
+    if (lane == 0) { s_wtot[warp] = wtot; if (ncr) atomicAdd(&s_cr, ncr); if (ncrlf) atomicAdd(&s_crlf, ncrlf); }
+    __syncthreads();
+    u32 btot = 0, wpre = 0;
+#pragma unroll
+    for (int w = 0; w < IDX_THREADS / 32; w++) { const u32 t = s_wtot[w]; btot += t; if (w < warp) wpre += t; }
+
+    if (warp == 0) {
+        volatile u64* st = tile_state;
+        u32 prefix = 0;
+        if (tile > 0) {
+            if (lane == 0) { st[tile] = TS_AGG | btot; __threadfence(); }
+            int j = (int)tile - 1;                       /* newest predecessor not yet accounted for */
+            for (;;) {
+                const int idx = j - lane;
+                u64 s = 2ull << 62;                       /* before tile 0: an empty prefix (TS_PREFIX | 0) */
+                if (idx >= 0) s = st[idx];
+                const u32 unset = __ballot_sync(0xffffffffu, (s & TS_MASK) == 0);
+                const u32 pre = __ballot_sync(0xffffffffu, (s & TS_MASK) == TS_PREFIX);
+                /* usable lanes: those before the first unset one, up to and including the first prefix */
+                const int first_unset = unset ? __ffs((int)unset) - 1 : 32;
+                const int first_pre = pre ? __ffs((int)pre) - 1 : 32;
+                const int upto = first_pre < first_unset ? first_pre + 1 : first_unset;   /* lanes [0, upto) are summed */
+                u32 v = lane < upto ? (u32)s : 0u;
+                prefix += warp_sum(v);
+                if (first_pre < first_unset) break;
+                j -= upto;
+                if (upto == 0) RPQ_SPIN_HINT();
+            }
+        }
+        if (lane == 0) {
+            __threadfence();
+            st[tile] = TS_PREFIX | (u64)(prefix + btot);
+            s_prefix = prefix;
+            if (s_cr) atomicAdd(&ctr->n_cr, s_cr);
+            if (s_crlf) atomicAdd(&ctr->n_crlf, s_crlf);
+            if ((u64)(tile + 1) * IDX_TILE >= len) ctr->n_nl = prefix + btot;     /* the last tile knows the total */
+        }
+    }
+    __syncthreads();
+
+    /* ---- positions: the eight masks of this thread, in text order */
+    if (cnt) {
+        u32 o = s_prefix + wpre + ex_in_warp;
+        const uint4 mm = *reinterpret_cast<const uint4*>(my_masks);
+        const u32 base = (u32)p0;
+        u32 w[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            u32 m = w[q];
+            while (m) {
+                const int bb = __ffs((int)m) - 1;
+                m &= m - 1;
+                if (o < nl_cap) nl[o] = base + 32u * q + (u32)bb;
+                o++;
+            }
+        }
     }
 }
 
