@@ -100,14 +100,46 @@ def cpu_reference_roundtrip(r1, r2, cores, budget_s=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons.  The sampler is started before the warm-up (nvidia-smi needs ~100 ms to come up,
-    the timed region of the default run is shorter than that); only samples stamped inside [begin(), end()] are used."""
+    """SM clock and throttle reasons DURING the timed region, sampled in-process through NVML (pynvml) every ~2 ms by a
+    thread: the default timed region lasts ~80 ms, too short for `nvidia-smi -lms` to land a sample in it reliably.  Only
+    samples taken between begin() and end() are reported; if NVML is unavailable, nvidia-smi is the fallback."""
     Q = "timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu):
-        self.gpu, self.p, self.path, self.t0, self.t1 = gpu, None, None, None, None
+    def __init__(self, gpu, uuid=None):
+        self.gpu, self.uuid = gpu, uuid
+        self.nv = self.h = self.th = None
+        self.on = False
+        self.rows = []
+        self.p = self.path = None
+        self.t0 = self.t1 = None
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                for cand in (self.uuid, "GPU-" + self.uuid):
+                    try:
+                        h = nv.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                idx = self.gpu
+                if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                    idx = int(vis.split(",")[self.gpu])
+                h = nv.nvmlDeviceGetHandleByIndex(idx)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.nv, self.h = nv, h
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.run = True
+            self.th = threading.Thread(target=self._loop, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -116,13 +148,41 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def _loop(self):
+        nv, h = self.nv, self.h
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while self.run:
+            if self.on:
+                try:
+                    self.rows.append((time.time(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+            else:
+                time.sleep(0.0005)
+
     def begin(self):
         self.t0 = time.time()
+        self.on = True
 
     def end(self):
+        self.on = False
         self.t1 = time.time()
 
     def stop(self):
+        if self.nv is not None:
+            self.run = False
+            self.th.join()
+            nv = self.nv
+            names = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4), ("hw_power_brake_slowdown", 0x80))
+            reasons = sorted({n for _, _, r in self.rows for n, bit in names if r & bit})
+            sm = [c for _, c, _ in self.rows if c > 0]
+            try:
+                nv.nvmlShutdown()
+            except Exception:
+                pass
+            return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_min_mhz=min(sm) if sm else None, sm_max_mhz=self.smax, reasons=reasons, samples=len(sm),
+                        sampled="NVML, every ~2 ms between the first and the last timed step")
         if not self.p:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         time.sleep(0.05)
@@ -141,10 +201,10 @@ class ClockSampler:
                 continue
         os.unlink(self.path)
         inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
-        where = "timed region"
+        where = "nvidia-smi, timed region"
         if not inside:                                  # a region shorter than the sampling period: the nearest samples around it
             inside = [r for r in rows if self.t0 is not None and self.t0 - 0.25 <= r[0] <= self.t1 + 0.05]
-            where = "timed region +-0.25 s (region shorter than the sampling period)"
+            where = "nvidia-smi, timed region +-0.25 s (region shorter than the sampling period)"
         sm, mx, reasons = [], 0, set()
         for _, clk, cmax, flags in inside:
             sm.append(clk)
@@ -280,7 +340,11 @@ def main():
     del o1, o2, rfq_dev
 
     # ---- timed: inputs resident in HBM (inputs are ~3.4 GB per step: far larger than the 126 MB L2, no flush needed)
-    clocks = ClockSampler(local)
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    clocks = ClockSampler(local, uuid)
     if rank == 0:
         clocks.start()
     for _ in range(W):
@@ -364,42 +428,102 @@ def main():
                                       note="whole encode+decode: (F+R)+(R+F) algorithmic bytes over the sum of all kernel times"),
                         kernels_ms={k: round(v[1], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])})
 
-    # ---- e2e: pinned host buffers through the C ABI, H2D and D2H inside the timed region
+    # ---- e2e: pinned host buffers through the C ABI, H2D and D2H inside the timed region.
+    # Two measurements of the same K steps (encode host->host, then decode host->host):
+    #   serial    : step i+1 starts when step i is done; one PCIe direction is busy at a time
+    #   pipelined : the encode of step i+1 (host->device heavy) runs while step i is decoded (device->host heavy): two host
+    #               threads, one context each (the ABI's rule is one caller thread per context); encode results alternate
+    #               between two contexts so that the decoder reads a buffer nobody is overwriting.  Every step's H2D and
+    #               D2H is inside the timed region; all K steps have completed when the clock stops.
     e2e = None
     if not args.no_e2e:
+        import queue
         h1 = torch.from_numpy(r1).pin_memory()
         h2 = torch.from_numpy(r2).pin_memory()
+        enc_b = K.Codec(device=local)
+        enc_b.set_header(header)
+        encs = [enc, enc_b]
 
-        def step_host():
-            eo = enc.encode_raw(h1.data_ptr(), h1.numel(), h2.data_ptr(), h2.numel(), 0, False, chunk_bases, True, (K.NEVER, K.NEVER), 0, 0)
-            se = enc.stats()
-            do = dec.decode_raw(eo.data, eo.bytes, 0, True, 0)
-            sd = dec.stats()
-            return eo, do, se, sd
-        for _ in range(W):
-            eo, do, se, sd = step_host()
-        barrier()
-        t_e = time.perf_counter()
-        h2d = d2h = 0
-        parts = dict(enc_h2d_ms=0.0, enc_kernels_ms=0.0, enc_d2h_ms=0.0, dec_h2d_ms=0.0, dec_kernels_ms=0.0, dec_d2h_ms=0.0)
-        for _ in range(args.steps):
-            eo, do, se, sd = step_host()
-            h2d += se.h2d_bytes + sd.h2d_bytes
-            d2h += se.d2h_bytes + sd.d2h_bytes
-            for k, v in (("enc_h2d_ms", se.ms_h2d), ("enc_kernels_ms", se.ms_kernels), ("enc_d2h_ms", se.ms_d2h),
-                         ("dec_h2d_ms", sd.ms_h2d), ("dec_kernels_ms", sd.ms_kernels), ("dec_d2h_ms", sd.ms_d2h)):
-                parts[k] += v / args.steps
-        barrier()
-        e_ms = 1e3 * (time.perf_counter() - t_e)
-        # result check on the host copies
-        a1 = np.ctypeslib.as_array(C.cast(do.out1, C.POINTER(C.c_uint8)), shape=(do.out1_bytes,))
-        assert do.out1_bytes == r1.size and np.array_equal(a1[:1 << 20], r1[:1 << 20]) and np.array_equal(a1[-(1 << 20):], r1[-(1 << 20):])
-        te = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e_ms = float(te[0])
-        e2e = dict(value=job_bytes * args.steps / 1e9 / (e_ms / 1e3), unit=UNIT, h2d_bytes_per_step=int(h2d // args.steps), d2h_bytes_per_step=int(d2h // args.steps),
-                   ms_per_step=e_ms / args.steps, breakdown_ms_per_step={k: round(v, 3) for k, v in parts.items()}, timing="host wall clock around the C-ABI calls (they return after the D2H completed), max over ranks")
+        def encode_host(cd):
+            return cd.encode_raw(h1.data_ptr(), h1.numel(), h2.data_ptr(), h2.numel(), 0, False, chunk_bases, True, (K.NEVER, K.NEVER), 0, 0)
+
+        def check_host(do):
+            a1 = np.ctypeslib.as_array(C.cast(do.out1, C.POINTER(C.c_uint8)), shape=(do.out1_bytes,))
+            a2 = np.ctypeslib.as_array(C.cast(do.out2, C.POINTER(C.c_uint8)), shape=(do.out2_bytes,))
+            assert do.out1_bytes == r1.size and np.array_equal(a1[:1 << 20], r1[:1 << 20]) and np.array_equal(a1[-(1 << 20):], r1[-(1 << 20):])
+            assert do.out2_bytes == r2.size and np.array_equal(a2[:1 << 20], r2[:1 << 20]) and np.array_equal(a2[-(1 << 20):], r2[-(1 << 20):])
+
+        def run_serial(n):
+            acc = dict(h2d=0, d2h=0, dec_h2d_ms=0.0, dec_kernels_ms=0.0, dec_d2h_ms=0.0)
+            do = None
+            for _ in range(n):
+                eo = encode_host(enc)
+                se = enc.stats()
+                do = dec.decode_raw(eo.data, eo.bytes, 0, True, 0)
+                sd = dec.stats()
+                acc["h2d"] += se.h2d_bytes + sd.h2d_bytes
+                acc["d2h"] += se.d2h_bytes + sd.d2h_bytes
+                acc["dec_h2d_ms"] += sd.ms_h2d / n
+                acc["dec_kernels_ms"] += sd.ms_kernels / n
+                acc["dec_d2h_ms"] += sd.ms_d2h / n
+            return acc, do
+
+        def run_pipelined(n):
+            acc = dict(h2d=0, d2h=0)
+            ready = queue.Queue()
+            free = [threading.Semaphore(1), threading.Semaphore(1)]
+            err = []
+
+            def producer():
+                try:
+                    torch.cuda.set_device(local)
+                    for i in range(n):
+                        free[i & 1].acquire()                    # the decoder is done with this context's previous result
+                        eo = encode_host(encs[i & 1])
+                        se = encs[i & 1].stats()
+                        ready.put((i, eo, se.h2d_bytes, se.d2h_bytes))
+                except Exception as ex:                          # noqa: BLE001
+                    err.append(ex)
+                    ready.put(None)
+            th = threading.Thread(target=producer)
+            th.start()
+            do = None
+            for _ in range(n):
+                item = ready.get()
+                if item is None:
+                    break
+                i, eo, hb, db = item
+                do = dec.decode_raw(eo.data, eo.bytes, 0, True, 0)
+                sd = dec.stats()
+                free[i & 1].release()
+                acc["h2d"] += hb + sd.h2d_bytes
+                acc["d2h"] += db + sd.d2h_bytes
+            th.join()
+            if err:
+                raise err[0]
+            return acc, do
+
+        def timed(fn):
+            fn(W)
+            barrier()
+            t_e = time.perf_counter()
+            acc, do = fn(args.steps)
+            barrier()
+            ms = 1e3 * (time.perf_counter() - t_e)
+            check_host(do)
+            te = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            return float(te[0]), acc
+        s_ms, s_acc = timed(run_serial)
+        p_ms, p_acc = timed(run_pipelined)
+        gbs = lambda ms: job_bytes * args.steps / 1e9 / (ms / 1e3)      # noqa: E731
+        e2e = dict(value=gbs(p_ms), unit=UNIT, h2d_bytes_per_step=int(p_acc["h2d"] // args.steps), d2h_bytes_per_step=int(p_acc["d2h"] // args.steps),
+                   ms_per_step=p_ms / args.steps, mode="pipelined: encode of step i+1 overlaps decode of step i (two host threads, one context each; H2D and D2H share the link full duplex)",
+                   serial=dict(value=gbs(s_ms), ms_per_step=s_ms / args.steps, h2d_bytes_per_step=int(s_acc["h2d"] // args.steps), d2h_bytes_per_step=int(s_acc["d2h"] // args.steps),
+                               decode_breakdown_ms_per_step={k: round(v, 3) for k, v in s_acc.items() if k.endswith("_ms")}),
+                   timing="host wall clock around the C-ABI calls (they return after their D2H completed), K steps, max over ranks")
+        enc_b.close()
         del h1, h2
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload

@@ -204,44 +204,37 @@ __global__ void __launch_bounds__(256) k_emit2(EncBatchDev b, HeaderDev h, u8* o
         return packed_window(b.pk + (size_t)ii * pkw, j0, pkw);
     };
     u8* col = o + ck.off_seq;
-    const u32 w0 = (so + 15u) >> 4, w1 = (so + kept - 1u) >> 4;
-    const bool col_aligned = (reinterpret_cast<uintptr_t>(col) & 3u) == 0;
-    auto store_word = [&](u32 W, u32 word) {
-        const u32 bo = 4u * W;
-        if (col_aligned && bo + 4u <= ck.seq_size) { *reinterpret_cast<u32*>(col + bo) = word; return; }
-        const u32 nbytes = ck.seq_size - bo < 4u ? ck.seq_size - bo : 4u;
-        for (u32 k = 0; k < nbytes; k++) col[bo + k] = (u8)(word >> (8 * k));
+    /* The column starts wherever the chunk layout puts it; output words are therefore counted from the 4-byte boundary at or
+     * below it: word V holds the column bytes [4V - al, 4V - al + 4), i.e. the stream's bases [16V - 4 al, 16V - 4 al + 16), and
+     * leaves with one aligned 32-bit store.  Only word 0 of a misaligned column and the column's last word are partial. */
+    const u32 al = (u32)(reinterpret_cast<uintptr_t>(col) & 3u);
+    const u32 sh_so = so + 4u * al;                                                /* the read's first base, counted from word 0 */
+    u8* colw = col - al;
+    const u32 col_end = ck.seq_size + al;                                          /* end of the column, counted from colw */
+    const u32 w0 = (sh_so + 15u) >> 4, w1 = (sh_so + kept - 1u) >> 4;
+    auto store_word = [&](u32 V, u32 word) {
+        const u32 bo = 4u * V;
+        if ((V > 0u || al == 0u) && bo + 4u <= col_end) { *reinterpret_cast<u32*>(colw + bo) = word; return; }
+        const u32 from = V == 0u ? al : 0u;
+        const u32 nbytes = col_end - bo < 4u ? col_end - bo : 4u;
+        for (u32 k = from; k < nbytes; k++) colw[bo + k] = (u8)(word >> (8 * k));
     };
-    u32 W = w0;
-    /* words that lie entirely inside this read: a funnel shift of two neighbouring packed words, the loads a few words ahead */
-    if (w1 > w0 && !(rc_file && (rel & 1u) && !il)) {
-        const int ov = (il && (rel & 1u) && (h.flags & RPQ_ENCODE_PE_BY_OVERLAP)) ? (int)b.ov[i >> 1] : 0;
-        const u32 a = 16u * w0 - so + (ov > 0 ? (u32)ov : 0u);
-        const u32* src = b.pk + (size_t)i * pkw;
-        const u32 sh = (a & 15u) * 2u;
-        u32 k = a >> 4;
-        u32 lo = k < pkw ? src[k] : 0u;
-#pragma unroll 4
-        for (; W < w1; W++) {
-            k++;
-            const u32 hi = k < pkw ? src[k] : 0u;
-            store_word(W, __funnelshift_r(lo, hi, sh));
-            lo = hi;
-        }
-    }
-    for (; W <= w1; W++) {
-        const u32 p0 = 16u * W;
-        u32 have = so + kept - p0; if (have > 16u) have = 16u;                  /* own bases in this word */
+    /* word V built from this read's kept bases and, where they end early, the reads that follow */
+    auto boundary_word = [&](u32 V) {
+        const u32 lead = V == 0u ? 4u * al : 0u;                                    /* base slots of word 0 below the column */
+        const u32 p0 = 16u * V + lead - 4u * al;                                    /* stream position of the first real base */
+        const u32 room = 16u - lead;
+        u32 have = so + kept - p0; if (have > room) have = room;                    /* own bases in this word */
         u32 word = window(i, rel, p0 - so);
         if (have < 16u) {
             word &= (1u << (2 * have)) - 1u;
             /* pull from the following reads that still have kept bases */
             u32 r2 = rel + 1, filled = have;
-            while (filled < 16u && r2 < ck.count && p0 + filled < ck.seq_kept) {
+            while (filled < room && r2 < ck.count && p0 + filled < ck.seq_kept) {
                 const u32 i2 = ck.first + r2;
                 const u32 k2 = kept_bases(b, h, il, i2, r2);
                 if (k2) {
-                    u32 take = 16u - filled; if (take > k2) take = k2;
+                    u32 take = room - filled; if (take > k2) take = k2;
                     u32 w2 = window(i2, r2, 0u);
                     if (take < 16u) w2 &= (1u << (2 * take)) - 1u;
                     word |= w2 << (2 * filled);
@@ -250,8 +243,27 @@ __global__ void __launch_bounds__(256) k_emit2(EncBatchDev b, HeaderDev h, u8* o
                 r2++;
             }
         }
-        store_word(W, word);
+        store_word(V, lead ? word << (2 * lead) : word);
+    };
+    if (so == 0u && al != 0u) boundary_word(0u);                                   /* word 0 of a misaligned column: nobody's first base is at its start */
+    u32 W = w0;
+    /* words that lie entirely inside this read: a funnel shift of two neighbouring packed words, the loads a few words ahead */
+    if (w1 > w0 && !(rc_file && (rel & 1u) && !il)) {
+        const int ov = (il && (rel & 1u) && (h.flags & RPQ_ENCODE_PE_BY_OVERLAP)) ? (int)b.ov[i >> 1] : 0;
+        const u32 a = 16u * w0 - sh_so + (ov > 0 ? (u32)ov : 0u);
+        const u32* src = b.pk + (size_t)i * pkw;
+        const u32 sh = (a & 15u) * 2u;
+        u32 k = a >> 4;
+        u32 lo = k < pkw ? src[k] : 0u;
+#pragma unroll 4
+        for (; W < w1; W++) {
+            k++;
+            const u32 hi = k < pkw ? src[k] : 0u;
+            *reinterpret_cast<u32*>(colw + 4u * W) = __funnelshift_r(lo, hi, sh);  /* W >= 1 and 4W + 4 <= col_end here */
+            lo = hi;
+        }
     }
+    for (; W <= w1; W++) boundary_word(W);
 }
 
 /* name1 / name2 / strand arenas for chunks whose parts are not all the same: warp per read (text bytes, coalesced) */
