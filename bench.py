@@ -252,6 +252,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=env_int("RPQ_BENCH_PAIRS", 4760000), help="read pairs per GPU (4.76 M = the 3.4 GB nova pair)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel profiling pass (experiments)")
     args = ap.parse_args()
 
     rank = env_int("RANK", 0)
@@ -379,14 +380,15 @@ def main():
     value = job_bytes * args.steps / 1e9 / (dev_ms / 1e3)
 
     # ---- per-kernel device time (separate pass, event pair around every launch) -> roofline of the dominant kernel
-    enc.set_profiling(True)
-    dec.set_profiling(True)
-    step_device()
     prof = {}
-    for k, (n, ms) in list(enc.profile().items()) + list(dec.profile().items()):
-        prof[k] = (n, ms)
-    enc.set_profiling(False)
-    dec.set_profiling(False)
+    if not args.no_roofline:
+        enc.set_profiling(True)
+        dec.set_profiling(True)
+        step_device()
+        for k, (n, ms) in list(enc.profile().items()) + list(dec.profile().items()):
+            prof[k] = (n, ms)
+        enc.set_profiling(False)
+        dec.set_profiling(False)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -479,7 +481,9 @@ def main():
                     torch.cuda.set_device(local)
                     for i in range(n):
                         free[i & 1].acquire()                    # the decoder is done with this context's previous result
+                        t_c = time.perf_counter()
                         eo = encode_host(encs[i & 1])
+                        acc["enc_call_ms"] = acc.get("enc_call_ms", 0.0) + 1e3 * (time.perf_counter() - t_c) / n
                         se = encs[i & 1].stats()
                         ready.put((i, eo, se.h2d_bytes, se.d2h_bytes))
                 except Exception as ex:                          # noqa: BLE001
@@ -493,7 +497,9 @@ def main():
                 if item is None:
                     break
                 i, eo, hb, db = item
+                t_c = time.perf_counter()
                 do = dec.decode_raw(eo.data, eo.bytes, 0, True, 0)
+                acc["dec_call_ms"] = acc.get("dec_call_ms", 0.0) + 1e3 * (time.perf_counter() - t_c) / n
                 sd = dec.stats()
                 free[i & 1].release()
                 acc["h2d"] += hb + sd.h2d_bytes
@@ -519,7 +525,7 @@ def main():
         p_ms, p_acc = timed(run_pipelined)
         gbs = lambda ms: job_bytes * args.steps / 1e9 / (ms / 1e3)      # noqa: E731
         e2e = dict(value=gbs(p_ms), unit=UNIT, h2d_bytes_per_step=int(p_acc["h2d"] // args.steps), d2h_bytes_per_step=int(p_acc["d2h"] // args.steps),
-                   ms_per_step=p_ms / args.steps, mode="pipelined: encode of step i+1 overlaps decode of step i (two host threads, one context each; H2D and D2H share the link full duplex)",
+                   ms_per_step=p_ms / args.steps, encode_call_ms=round(p_acc.get("enc_call_ms", 0.0), 2), decode_call_ms=round(p_acc.get("dec_call_ms", 0.0), 2), mode="pipelined: encode of step i+1 overlaps decode of step i (two host threads, one context each; H2D and D2H share the link full duplex)",
                    serial=dict(value=gbs(s_ms), ms_per_step=s_ms / args.steps, h2d_bytes_per_step=int(s_acc["h2d"] // args.steps), d2h_bytes_per_step=int(s_acc["d2h"] // args.steps),
                                decode_breakdown_ms_per_step={k: round(v, 3) for k, v in s_acc.items() if k.endswith("_ms")}),
                    timing="host wall clock around the C-ABI calls (they return after their D2H completed), K steps, max over ranks")

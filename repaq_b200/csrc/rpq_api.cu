@@ -4,6 +4,7 @@
  * buffers from a handful of scalars read back between stages.
  */
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -21,6 +22,37 @@
 #include "rpq_host.h"
 
 using namespace rpq;
+
+namespace rpq {
+/* Small device tables and scalars go to (mapped) pinned host memory with plain stores from an SM instead of a copy-engine
+ * transfer: a copy-engine transfer queues behind whatever bulk copies other contexts have in flight in the same direction
+ * (a decoder returning gigabytes of FASTQ beside this encoder), and the host waits for every one of these read-backs. */
+__global__ void __launch_bounds__(256) k_fetch(const u32* __restrict__ src, u32* __restrict__ dst, u32 nwords) {
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < nwords; k += gridDim.x * blockDim.x) dst[k] = src[k];
+}
+/* Bulk results go to pinned host memory the same way when the context is told to (RPQ_D2H=sm, the default for decoded FASTQ):
+ * a few CTAs stream 16-byte stores over PCIe (posted writes, 512 contiguous bytes per warp instruction).  The copy engines then
+ * only carry host-to-device traffic, so an encoder's input copies and a decoder's output run full duplex; with both directions
+ * on the copy engines the device-to-host queue of one context was seen to hold back the other context's host-to-device copies
+ * for as long as it was never empty (profiles/README.md, r01_v9).  src and dst must be congruent modulo 16. */
+__global__ void __launch_bounds__(256) k_push(const u8* __restrict__ src, u8* __restrict__ dst, unsigned long long n) {
+    const unsigned long long head = (16u - (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u)) & 15u;
+    const unsigned long long h = head < n ? head : n;
+    const unsigned long long n16 = (n - h) / 16;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (unsigned long long)gridDim.x * blockDim.x;
+    if (tid < h) dst[tid] = src[tid];
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + h);
+    uint4* d4 = reinterpret_cast<uint4*>(dst + h);
+    unsigned long long k = tid;
+    for (; k + 3 * nthreads < n16; k += 4 * nthreads) {                 /* four loads in flight per thread */
+        const uint4 a = s4[k], b = s4[k + nthreads], c = s4[k + 2 * nthreads], d = s4[k + 3 * nthreads];
+        d4[k] = a; d4[k + nthreads] = b; d4[k + 2 * nthreads] = c; d4[k + 3 * nthreads] = d;
+    }
+    for (; k < n16; k += nthreads) d4[k] = s4[k];
+    const unsigned long long done = h + 16 * n16;
+    if (tid < n - done) dst[done + tid] = src[done + tid];
+}
+}  // namespace rpq
 
 namespace {
 
@@ -44,17 +76,21 @@ struct rpq_ctx {
         d_in, d_desc, d_tmp[8], d_tmp2, out2;
     bool no_streams4 = false;              /* RPQ_DEBUG_NO_STREAMS4=1: k_streams3 codes every span (test coverage, A/B) */
     u64 stats_redo_spans = 0;              /* spans k_streams4 handed to k_streams3 */
-    int index_variant = 0;                 /* RPQ_DEBUG_INDEX=1: CTA-per-tile indexer (A/B) */
+    int index_variant = 1;                 /* 1: CTA-per-tile indexer (default, 1.13 ms per 3.4 GB); RPQ_DEBUG_INDEX=0: persistent CTAs (1.31 ms) */
     u32 fmt_reads = 0;                     /* RPQ_DEBUG_FMT_READS=n: reads per formatter CTA (tuning experiments) */
     bool force_v1 = false;                 /* RPQ_DEBUG_FORCE_V1=1: take the long-read fallback kernels (test coverage) */
+    bool d2h_sm = true;                    /* RPQ_D2H=ce: bulk results leave through the copy engines (cudaMemcpyAsync) instead of k_push */
+    u32 push_ctas = 32;                    /* RPQ_PUSH_CTAS=n */
+    u32 d2h_depth = 2;                     /* RPQ_D2H_DEPTH=n: windows of decoded FASTQ whose copies may be queued at a time (0: wait for each) */
     bool no_pipeline = false;              /* RPQ_NO_PIPELINE=1: host batches are never cut into pipelined windows */
     uint64_t pipe_window = 0;              /* RPQ_DEBUG_PIPE_WINDOW=<bytes>: window size of the pipelined host path (tests) */
     std::vector<rpq_ctx*> lanes;           /* sub-contexts (own stream + buffers) of the pipelined host path */
     cudaStream_t copy_stream = 0;          /* decode: device-to-host copies of finished windows */
     bool copy_stream_ok = false;
-    RtEvent win_ev[16];
+    RtEvent win_ev[16], cp_ev[16];
     void* pinned_small = nullptr;          /* 64 KiB scratch for scalar read-backs */
     DevBuf host_out, host_out2;            /* pinned host buffers for results */
+    DevBuf pinned_tab;                     /* pinned host copy of the chunk table (k_fetch) */
     std::vector<rpq_chunk_info> infos;
     std::vector<ChunkDev> h_chunks;
     rpq_stats stats;
@@ -148,10 +184,13 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     memset(&c->stats, 0, sizeof c->stats);
     memset(&c->hdr, 0, sizeof c->hdr);
     { const char* e = getenv("RPQ_DEBUG_FORCE_V1"); c->force_v1 = e && e[0] == '1'; }
-    { const char* e = getenv("RPQ_DEBUG_INDEX"); c->index_variant = e ? atoi(e) : 0; }
+    { const char* e = getenv("RPQ_DEBUG_INDEX"); c->index_variant = e ? atoi(e) : 1; }
     { const char* e = getenv("RPQ_DEBUG_NO_STREAMS4"); c->no_streams4 = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_DEBUG_FMT_READS"); c->fmt_reads = e ? (u32)atoi(e) : 0u; }
     { const char* e = getenv("RPQ_NO_PIPELINE"); c->no_pipeline = e && e[0] == '1'; }
+    { const char* e = getenv("RPQ_D2H"); c->d2h_sm = !(e && e[0] == 'c'); }
+    { const char* e = getenv("RPQ_D2H_DEPTH"); if (e) c->d2h_depth = (u32)atoi(e) > 8u ? 8u : (u32)atoi(e); }
+    { const char* e = getenv("RPQ_PUSH_CTAS"); if (e && atoi(e) > 0) c->push_ctas = (u32)atoi(e); }
     { const char* e = getenv("RPQ_DEBUG_PIPE_WINDOW"); c->pipe_window = e ? strtoull(e, nullptr, 10) : 0; }
 #ifndef RPQ_EMU
     cudaFuncSetAttribute(k_index_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, IDX_SMEM);
@@ -172,7 +211,7 @@ extern "C" void rpq_destroy(rpq_ctx* c) {
     rt_stream_sync(c->stream);
     for (rpq_ctx* l : c->lanes) rpq_destroy(l);
     c->lanes.clear();
-    if (c->copy_stream_ok) { rt_stream_sync(c->copy_stream); rt_stream_destroy(c->copy_stream); for (auto& e : c->win_ev) rt_event_destroy(&e); }
+    if (c->copy_stream_ok) { rt_stream_sync(c->copy_stream); rt_stream_destroy(c->copy_stream); for (auto& e : c->win_ev) rt_event_destroy(&e); for (auto& e : c->cp_ev) rt_event_destroy(&e); }
     DevBuf* all[] = {&c->loc, &c->pk, &c->pk_rc, &c->text[0], &c->text[1], &c->nl[0], &c->nl[1], &c->tile_state, &c->counters, &c->rlen, &c->unit_bases, &c->prefix, &c->scan_tmp,
                      &c->ustats, &c->chunk_first, &c->chunks, &c->meta, &c->meta0, &c->ov, &c->seqoff, &c->qualoff, &c->n1off, &c->n2off, &c->soff,
                      &c->errbits, &c->tmpx, &c->tmpy, &c->span_first[0], &c->span_first[1], &c->span_chunk[0], &c->span_chunk[1], &c->dir[0], &c->dir[1],
@@ -180,7 +219,7 @@ extern "C" void rpq_destroy(rpq_ctx* c) {
                      &c->d_tmp2, &c->d_tmp[0], &c->d_tmp[1], &c->d_tmp[2], &c->d_tmp[3], &c->d_tmp[4], &c->d_tmp[5], &c->d_tmp[6], &c->d_tmp[7]};
     for (DevBuf* b : all) rt_free_device(b->p);
     rt_free_pinned(c->pinned_small);
-    rt_free_pinned(c->host_out.p); rt_free_pinned(c->host_out2.p);
+    rt_free_pinned(c->host_out.p); rt_free_pinned(c->host_out2.p); rt_free_pinned(c->pinned_tab.p);
     for (auto& e : c->ev) rt_event_destroy(&e);
     rt_stream_destroy(c->stream);
     delete c;
@@ -232,9 +271,28 @@ namespace {
 
 /* scalar read-back through the pinned scratch; synchronises the stream */
 template <class T> int read_back(rpq_ctx* c, const void* dev, T* host, size_t count = 1) {
-    if (rt_memcpy_d2h(c->pinned_small, dev, sizeof(T) * count, c->stream)) return RPQ_ERR_CUDA;
+    static_assert(sizeof(T) % 4 == 0, "read_back moves 32-bit words");
+    RPQ_LAUNCH(k_fetch, 1, 64, 0, c->stream, (const u32*)dev, (u32*)c->pinned_small, (u32)(sizeof(T) * count / 4));
     if (rt_stream_sync(c->stream)) return RPQ_ERR_CUDA;
     memcpy(host, c->pinned_small, sizeof(T) * count);
+    return RPQ_OK;
+}
+
+/* bulk device -> pinned host on `stream`: k_push or the copy engine */
+int push_to_host(rpq_ctx* c, void* host, const void* dev, size_t bytes, cudaStream_t stream) {
+    if (!bytes) return 0;
+    if (c->d2h_sm && ((reinterpret_cast<uintptr_t>(host) ^ reinterpret_cast<uintptr_t>(dev)) & 15u) == 0) {
+        RPQ_LAUNCH(k_push, c->push_ctas, 256, 0, stream, (const u8*)dev, (u8*)host, (unsigned long long)bytes);
+        return 0;
+    }
+    return rt_memcpy_d2h(host, dev, bytes, stream);
+}
+
+/* queues the copy of a device table (a multiple of 4 bytes) into c->pinned_tab; valid after the stream is synchronised */
+int fetch_table(rpq_ctx* c, const void* dev, size_t bytes) {
+    if (!ensure_pinned(c, c->pinned_tab, bytes + 64)) return RPQ_ERR_NOMEM;
+    const u32 nwords = (u32)(bytes / 4);
+    if (nwords) RPQ_LAUNCH(k_fetch, (nwords + 1023) / 1024 < 64 ? (nwords + 1023) / 1024 : 64, 256, 0, c->stream, (const u32*)dev, c->pinned_tab.as<u32>(), nwords);
     return RPQ_OK;
 }
 

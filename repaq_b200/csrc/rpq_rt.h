@@ -42,6 +42,7 @@ inline int rt_memcpy_d2h(void* d, const void* s, size_t n, cudaStream_t) { if (n
 inline int rt_memcpy_d2d(void* d, const void* s, size_t n, cudaStream_t) { if (n) memmove(d, s, n); return 0; }
 inline int rt_memset(void* d, int v, size_t n, cudaStream_t) { if (n) memset(d, v, n); return 0; }
 inline int rt_stream_create(cudaStream_t* s) { *s = 0; return 0; }
+inline int rt_stream_create_high_priority(cudaStream_t* s) { *s = 0; return 0; }
 inline void rt_stream_destroy(cudaStream_t) {}
 inline int rt_stream_sync(cudaStream_t) { return 0; }
 inline int rt_last_error(char* buf, size_t n) { (void)buf; (void)n; return 0; }
@@ -63,6 +64,12 @@ inline int rt_memcpy_d2h(void* d, const void* s, size_t n, cudaStream_t st) { re
 inline int rt_memcpy_d2d(void* d, const void* s, size_t n, cudaStream_t st) { return n ? rt_check(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st), "D2D") : 0; }
 inline int rt_memset(void* d, int v, size_t n, cudaStream_t st) { return n ? rt_check(cudaMemsetAsync(d, v, n, st), "memset") : 0; }
 inline int rt_stream_create(cudaStream_t* s) { return rt_check(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking), "stream create"); }
+/* a stream whose blocks are dispatched before the pending blocks of normal streams */
+inline int rt_stream_create_high_priority(cudaStream_t* s) {
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    return rt_check(cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, greatest), "stream create");
+}
 inline void rt_stream_destroy(cudaStream_t s) { cudaStreamDestroy(s); }
 inline int rt_stream_sync(cudaStream_t s) { return rt_check(cudaStreamSynchronize(s), "stream sync"); }
 inline int rt_last_error(char* buf, size_t n) {
@@ -93,6 +100,7 @@ inline void rt_event_destroy(RtEvent*) {}
 inline void rt_event_record(RtEvent* e, cudaStream_t) { e->t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 inline float rt_event_ms(const RtEvent& a, const RtEvent& b) { return (float)(b.t - a.t); }
 inline void rt_stream_wait_event(cudaStream_t, RtEvent*) {}
+inline void rt_event_sync(RtEvent*) {}
 inline size_t rt_scan_tmp_bytes(size_t) { return 16; }
 inline int rt_inclusive_sum_u32_u64(const uint32_t* in, unsigned long long* out, size_t n, void*, size_t, cudaStream_t) {
     unsigned long long acc = 0;
@@ -106,6 +114,7 @@ inline void rt_event_destroy(RtEvent* e) { cudaEventDestroy(e->e); }
 inline void rt_event_record(RtEvent* e, cudaStream_t s) { cudaEventRecord(e->e, s); }
 inline float rt_event_ms(const RtEvent& a, const RtEvent& b) { float ms = 0; cudaEventElapsedTime(&ms, a.e, b.e); return ms; }
 inline void rt_stream_wait_event(cudaStream_t s, RtEvent* e) { cudaStreamWaitEvent(s, e->e, 0); }
+inline void rt_event_sync(RtEvent* e) { cudaEventSynchronize(e->e); }
 struct RtCastU64 { __host__ __device__ unsigned long long operator()(uint32_t v) const { return v; } };
 inline size_t rt_scan_tmp_bytes(size_t n) {
     size_t bytes = 0;

@@ -162,6 +162,17 @@ def test_stream_coder_generations(monkeypatch):
         cd.close()
 
 
+def test_persistent_indexer_variant(monkeypatch):
+    """RPQ_DEBUG_INDEX=0 selects the persistent-CTA line indexer (the CTA-per-tile one is the default)"""
+    monkeypatch.setenv("RPQ_DEBUG_INDEX", "0")
+    cd = K.Codec(lib_path=EMU)
+    try:
+        for name in ("nova_pe_k1000", "nova_pe_crlf_k100", "bgi_se_varlen_k100", "nova_pe_nonl_k100", "one_read"):
+            parity.check_encode_golden(cd, name)
+    finally:
+        cd.close()
+
+
 def test_pipelined_host_windows(monkeypatch):
     """the pipelined host path (windows over three lanes) must give the same bytes as one batch; tiny windows via
     RPQ_DEBUG_PIPE_WINDOW so that several windows fit a test input"""

@@ -119,6 +119,20 @@ def test_large_roundtrip_property(codec):
     assert rfq[: len(ref)] == ref
 
 
+def test_persistent_indexer_variant(monkeypatch):
+    """RPQ_DEBUG_INDEX=0: the persistent-CTA line indexer must index exactly like the default CTA-per-tile one"""
+    from tools import fqgen
+    monkeypatch.setenv("RPQ_DEBUG_INDEX", "0")
+    cd = K.Codec(device=0)
+    try:
+        for name in ("nova_pe_k1000", "nova_pe_crlf_k100", "bgi_se_varlen_k100", "nova_pe_nonl_k100"):
+            parity.check_encode_golden(cd, name)
+        r1, r2 = fqgen.generate(200000, seed=58, paired=True)
+        parity.check_against_oracle(cd, r1, r2)
+    finally:
+        cd.close()
+
+
 def test_library_really_ran_on_gpu(codec):
     s = codec.stats()
     assert s.launches > 0
