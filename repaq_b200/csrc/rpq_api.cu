@@ -30,11 +30,10 @@ namespace rpq {
 __global__ void __launch_bounds__(256) k_fetch(const u32* __restrict__ src, u32* __restrict__ dst, u32 nwords) {
     for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < nwords; k += gridDim.x * blockDim.x) dst[k] = src[k];
 }
-/* Bulk results go to pinned host memory the same way when the context is told to (RPQ_D2H=sm, the default for decoded FASTQ):
- * a few CTAs stream 16-byte stores over PCIe (posted writes, 512 contiguous bytes per warp instruction).  The copy engines then
- * only carry host-to-device traffic, so an encoder's input copies and a decoder's output run full duplex; with both directions
- * on the copy engines the device-to-host queue of one context was seen to hold back the other context's host-to-device copies
- * for as long as it was never empty (profiles/README.md, r01_v9).  src and dst must be congruent modulo 16. */
+/* Optional (RPQ_D2H=sm): bulk results leave the same way, a few CTAs streaming 16-byte stores over PCIe (posted writes,
+ * 512 contiguous bytes per warp instruction), so that the copy engines only carry host-to-device traffic.  Measured beside an
+ * encoder it is slower than the copy engine with one window queued at a time (28.3 against 30.7 GB/s end to end,
+ * profiles/README.md r01_v9), so the copy engine is the default.  src and dst must be congruent modulo 16. */
 __global__ void __launch_bounds__(256) k_push(const u8* __restrict__ src, u8* __restrict__ dst, unsigned long long n) {
     const unsigned long long head = (16u - (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u)) & 15u;
     const unsigned long long h = head < n ? head : n;
@@ -79,9 +78,9 @@ struct rpq_ctx {
     int index_variant = 1;                 /* 1: CTA-per-tile indexer (default, 1.13 ms per 3.4 GB); RPQ_DEBUG_INDEX=0: persistent CTAs (1.31 ms) */
     u32 fmt_reads = 0;                     /* RPQ_DEBUG_FMT_READS=n: reads per formatter CTA (tuning experiments) */
     bool force_v1 = false;                 /* RPQ_DEBUG_FORCE_V1=1: take the long-read fallback kernels (test coverage) */
-    bool d2h_sm = true;                    /* RPQ_D2H=ce: bulk results leave through the copy engines (cudaMemcpyAsync) instead of k_push */
+    bool d2h_sm = false;                   /* RPQ_D2H=sm: bulk results leave through k_push (SM stores) instead of the copy engines; measured slower (profiles/README.md r01_v9) */
     u32 push_ctas = 32;                    /* RPQ_PUSH_CTAS=n */
-    u32 d2h_depth = 2;                     /* RPQ_D2H_DEPTH=n: windows of decoded FASTQ whose copies may be queued at a time (0: wait for each) */
+    u32 d2h_depth = 1;                     /* RPQ_D2H_DEPTH=n: windows of decoded FASTQ whose copies may be queued at a time (0: wait for each) */
     bool no_pipeline = false;              /* RPQ_NO_PIPELINE=1: host batches are never cut into pipelined windows */
     uint64_t pipe_window = 0;              /* RPQ_DEBUG_PIPE_WINDOW=<bytes>: window size of the pipelined host path (tests) */
     std::vector<rpq_ctx*> lanes;           /* sub-contexts (own stream + buffers) of the pipelined host path */
@@ -188,7 +187,7 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     { const char* e = getenv("RPQ_DEBUG_NO_STREAMS4"); c->no_streams4 = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_DEBUG_FMT_READS"); c->fmt_reads = e ? (u32)atoi(e) : 0u; }
     { const char* e = getenv("RPQ_NO_PIPELINE"); c->no_pipeline = e && e[0] == '1'; }
-    { const char* e = getenv("RPQ_D2H"); c->d2h_sm = !(e && e[0] == 'c'); }
+    { const char* e = getenv("RPQ_D2H"); c->d2h_sm = e && e[0] == 's'; }
     { const char* e = getenv("RPQ_D2H_DEPTH"); if (e) c->d2h_depth = (u32)atoi(e) > 8u ? 8u : (u32)atoi(e); }
     { const char* e = getenv("RPQ_PUSH_CTAS"); if (e && atoi(e) > 0) c->push_ctas = (u32)atoi(e); }
     { const char* e = getenv("RPQ_DEBUG_PIPE_WINDOW"); c->pipe_window = e ? strtoull(e, nullptr, 10) : 0; }

@@ -423,14 +423,17 @@ __global__ void k_unit_lengths(EncBatchDev b, u32 n_units, u32* __restrict__ rle
     const u32 w_min = __reduce_min_sync(FULL, live ? bases : 0xFFFFFFFFu), w_max = __reduce_max_sync(FULL, bases);
     const u32 w_long = __reduce_max_sync(FULL, longest), w_head = __reduce_max_sync(FULL, head);
     if (lane == 0) {
-        if (w_empty != 0xFFFFFFFFu) atomicMin(&st->first_empty, w_empty);
-        if (w_badq != 0xFFFFFFFFu) atomicMin(&st->first_qual_len, w_badq);
-        if (w_badn != 0xFFFFFFFFu) atomicMin(&st->first_name_len, w_badn);
-        if (w_badl != 0xFFFFFFFFu) atomicMin(&st->first_read_len, w_badl);
-        if (w_min != 0xFFFFFFFFu) atomicMin(&st->min_bases, w_min);
-        atomicMax(&st->max_bases, w_max);
-        atomicMax(&st->max_read, w_long);
-        atomicMax(&st->max_head, w_head);
+        /* an atomic only when it would change the value: all warps update the same eight words, and on uniform reads
+         * (the common case) every warp but the first few would queue up at L2 for nothing */
+        volatile UnitStats* vs = st;
+        if (w_empty < vs->first_empty) atomicMin(&st->first_empty, w_empty);
+        if (w_badq < vs->first_qual_len) atomicMin(&st->first_qual_len, w_badq);
+        if (w_badn < vs->first_name_len) atomicMin(&st->first_name_len, w_badn);
+        if (w_badl < vs->first_read_len) atomicMin(&st->first_read_len, w_badl);
+        if (w_min < vs->min_bases) atomicMin(&st->min_bases, w_min);
+        if (w_max > vs->max_bases) atomicMax(&st->max_bases, w_max);
+        if (w_long > vs->max_read) atomicMax(&st->max_read, w_long);
+        if (w_head > vs->max_head) atomicMax(&st->max_head, w_head);
     }
 }
 

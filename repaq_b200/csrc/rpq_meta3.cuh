@@ -21,14 +21,134 @@
 
 namespace rpq {
 
-/* One code path for both strands (mates sit in neighbouring lanes: two functions would run one after the other).
- * rev: the read is packed as its reverse complement; lower case counts as a plain base there (src/read.cpp:92-113). */
+/* ---- SIMD-in-a-register helpers for the name path ---- */
+/* 0x80 in every byte of x that is zero (exact, no borrow between bytes) */
+__device__ __forceinline__ u32 zero_bytes(u32 x) { return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu); }
+/* the four 0x80 flags of a word as 4 adjacent bits (the partial products of the multiply never overlap) */
+__device__ __forceinline__ u32 flags4(u32 t) { return (((t >> 7) * 0x00204081u) >> 21) & 0xFu; }
+/* four 2-bit codes held in the low 2 bits of each byte -> one byte, by one multiply (products land 6 bits apart: no carries) */
+__device__ __forceinline__ u32 squeeze4m(u32 c) { return (c * 0x01041040u) >> 24; }
+/* value of four decimal digits held as 0..9 in bytes 0 (most significant) .. 3 */
+__device__ __forceinline__ u32 swar_dec4(u32 t) { const u32 p = (t * 10u + (t >> 8)) & 0x00FF00FFu; return (p * 100u + (p >> 16)) & 0xFFFFu; }
+
+/* atoi of name[a+1, b2): fields of 1..8 plain digits (every real coordinate) in two SIMD steps, anything else (empty, sign,
+ * blanks, letters, 9+ digits with glibc's saturation) through atoi_like */
+__device__ __forceinline__ int field_value(const u32* words, u32 off, int a, int b2) {
+    const int n = b2 - a - 1;
+    if (n >= 1 && n <= 8) {
+        const u32 o = off + (u32)a + 1u;
+        const int nh = n > 4 ? n - 4 : 0, nl = n - nh;                 /* leading 0..4 and trailing 1..4 characters */
+        const u32 wl = ld4(words, o + (u32)nh) ^ 0x30303030u, ml = 0xFFFFFFFFu >> (8 * (4 - nl));
+        u32 bad = ((((wl & 0x7f7f7f7fu) + 0x76767676u) | wl) & 0x80808080u) & ml;      /* a byte that is not 0..9 */
+        u32 v = swar_dec4((wl & ml) << (8 * (4 - nl)));
+        if (nh) {
+            const u32 wh = ld4(words, o) ^ 0x30303030u, mh = 0xFFFFFFFFu >> (8 * (4 - nh));
+            bad |= ((((wh & 0x7f7f7f7fu) + 0x76767676u) | wh) & 0x80808080u) & mh;
+            v += swar_dec4((wh & mh) << (8 * (4 - nh))) * 10000u;
+        }
+        if (!bad) return (int)v;
+    }
+    return atoi_like(reinterpret_cast<const u8*>(words) + off + a + 1, n);
+}
+
+/* FastqMeta::parse (reference src/fastqmeta.cpp:22-80) on a name staged in shared memory at byte offset `off` of `words`:
+ * same closed form as thread_tokenise (rpq_meta2.cuh), but ':' and ' ' are located 16 bytes at a time as bit masks.  Names
+ * whose scan does not end within 64 bytes take thread_tokenise. */
+__device__ inline ReadMeta thread_tokenise3(const u32* words, u32 off, int len) {
+    unsigned long long cm = 0, sm = 0;
+    bool known = false;
+    for (int base = 0; base < len && base < 64 && !known; base += 16) {
+        u32 c16 = 0, s16 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const u32 w = ld4(words, off + (u32)(base + 4 * k));
+            c16 |= flags4(zero_bytes(w ^ 0x3A3A3A3Au)) << (4 * k);
+            s16 |= flags4(zero_bytes(w ^ 0x20202020u)) << (4 * k);
+        }
+        const int left = len - base;
+        if (left < 16) { const u32 m = (1u << left) - 1u; c16 &= m; s16 &= m; }
+        cm |= (unsigned long long)c16 << base; sm |= (unsigned long long)s16 << base;
+        known = s16 != 0 || __popcll(cm) >= 7;
+    }
+    if (!known && len > 64) return thread_tokenise(reinterpret_cast<const u8*>(words) + off, len);
+    int S = -1;
+    if (sm) { S = __ffsll((long long)sm) - 1; cm &= (1ull << S) - 1ull; }       /* only colons before the first space count */
+    const int ncol = __popcll(cm);
+    unsigned long long t = cm;
+    t &= t - 1; t &= t - 1;                                                       /* colons 1 and 2 */
+    const int c3 = __ffsll((long long)t) - 1; t &= t - 1;
+    const int c4 = __ffsll((long long)t) - 1; t &= t - 1;
+    const int c5 = __ffsll((long long)t) - 1; t &= t - 1;
+    const int c6 = __ffsll((long long)t) - 1; t &= t - 1;
+    const int c7 = __ffsll((long long)t) - 1;
+    ReadMeta m;
+    m.x = 0; m.y = 0; m.tile = 0; m.lane = 0; m.has = 0; m.name_len = (u8)len; m.strand_len = 0; m.name1_len = (u8)len; m.name2_off = (u8)len;
+    auto fld = [&](int a, int b2) { return field_value(words, off, a, b2); };
+    int stop = -1;
+    if (ncol >= 7) { stop = c7; m.name1_len = (u8)c3; m.lane = (u8)fld(c3, c4); m.tile = (u16)fld(c4, c5); m.x = (u32)fld(c5, c6); m.y = (u32)fld(c6, c7); }
+    else if (S >= 0 && ncol == 6) { stop = S; m.name1_len = (u8)c3; m.lane = (u8)fld(c3, c4); m.tile = (u16)fld(c4, c5); m.x = (u32)fld(c5, c6); m.y = (u32)fld(c6, S); }
+    else if (S >= 0 && ncol == 5) { stop = S; m.name1_len = (u8)c3; m.lane = (u8)fld(c3, c4); m.tile = (u16)fld(c5, S); }
+    else if (S >= 0 && ncol == 4) { stop = S; m.name1_len = (u8)c4; m.lane = (u8)fld(c4, S); }
+    if (stop > 0) { m.has = 1; m.name2_off = (u8)stop; }
+    else { m.name1_len = (u8)len; m.name2_off = (u8)len; m.lane = 0; m.tile = 0; m.x = 0; m.y = 0; }
+    return m;
+}
+
+/* n bytes at byte offset `off` of the shared word array against n bytes of global text at g, four at a time (aligned global
+ * words, funnel-shifted); reads up to 7 bytes past g + n (the text buffers are padded) */
+__device__ __forceinline__ bool equal_shared_global(const u32* words, u32 off, const u8* g, int n) {
+    const u32* gw = reinterpret_cast<const u32*>(reinterpret_cast<uintptr_t>(g) & ~(uintptr_t)3);
+    const u32 gsh = (u32)(reinterpret_cast<uintptr_t>(g) & 3u) * 8u;
+    u32 diff = 0;
+    int k = 0;
+    u32 lo = n > 0 ? gw[0] : 0u;
+    for (; k + 4 <= n; k += 4) { const u32 hi = gw[(k >> 2) + 1]; diff |= ld4(words, off + (u32)k) ^ __funnelshift_r(lo, hi, gsh); lo = hi; }
+    if (k < n) diff |= (ld4(words, off + (u32)k) ^ __funnelshift_r(lo, gw[(k >> 2) + 1], gsh)) & ((1u << (8 * (n - k))) - 1u);
+    return diff == 0;
+}
+
+/* The read as it will be stored, 16 bases per word.  One code path for both strands (mates sit in neighbouring lanes: two
+ * functions would run one after the other).  rev: the read is packed as its reverse complement; lower case counts as a
+ * plain base there (src/read.cpp:92-113).  Whole words of 16 bases take four consecutive shared words each (one new load per
+ * four bases, carried over), the codes are checked against the characters they stand for once per word, and only a word
+ * that holds something else (N, lower case in a forward read, ...) is recoded exactly. */
 __device__ inline bool pack_read_c(const u32* words, u32 off, int len, bool rev, u32* dst, int pkw) {
     bool clean = true;
     const u32 sel = rev ? 0x0123u : 0x3210u;
     const u32 lower = rev ? 0x20202020u : 0u, flip = rev ? 0x03030303u : 0u;
     const u32 table = rev ? 0x63746167u : 0x43544147u;          /* code G0 A1 T2 C3 -> the character it came from */
-    for (int j = 0; j < pkw; j++) {
+    const int full = len >> 4;
+    /* group k (bases 4k..4k+3 of the result) = source bytes [off + 4k, +4) forward, [off + len - 4 - 4k, +4) reversed */
+    const u32 edge = rev ? off + (u32)len : off;
+    const u32 sh = (edge & 3u) * 8u;
+    const int step = rev ? -1 : 1;
+    int ni = (int)(edge >> 2) + step;                          /* next shared word to fetch: upwards forward, downwards reversed */
+    u32 carry = words[edge >> 2];
+    for (int j = 0; j < full; j++) {
+        u32 wq[4], bad = 0, acc = 0;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const u32 x = words[ni];
+            ni += step;
+            const u32 raw = __funnelshift_r(rev ? x : carry, rev ? carry : x, sh);      /* selects, not branches */
+            carry = x;
+            const u32 w = __byte_perm(raw, 0, sel);
+            const u32 l = w | lower;
+            const u32 c = ((l ^ (l >> 1)) & 0x02020202u) | ((~l >> 2) & 0x01010101u);
+            const u32 t = c | (c >> 4);
+            bad |= __byte_perm(table, 0u, __byte_perm(t, 0u, 0x4420)) ^ l;
+            acc |= squeeze4m(c ^ flip) << (8 * g);
+            wq[g] = w;
+        }
+        if (bad) {                                              /* exact: every byte that is not a plain base is code 0 */
+            clean = false;
+            acc = 0;
+#pragma unroll
+            for (int g = 0; g < 4; g++) acc |= squeeze4m(rev ? codes_rc(wq[g]) : codes_fwd(wq[g])) << (8 * g);
+        }
+        dst[j] = acc;
+    }
+    for (int j = full; j < pkw; j++) {                          /* the last, partial word and the zero padding */
         u32 acc = 0;
         const int base = j * 16;
         if (base < len) {
@@ -45,9 +165,9 @@ __device__ inline bool pack_read_c(const u32* words, u32 off, int len, bool rev,
                 u32 c = ((l ^ (l >> 1)) & 0x02020202u) | ((~l >> 2) & 0x01010101u);
                 const u32 t = c | (c >> 4);
                 const u32 expect = __byte_perm(table, 0u, __byte_perm(t, 0u, 0x4420));
-                if ((expect ^ l) & vm) { clean = false; c = rev ? codes_rc(w) : codes_fwd(w); }      /* exact: every other byte is code 0 */
+                if ((expect ^ l) & vm) { clean = false; c = rev ? codes_rc(w) : codes_fwd(w); }
                 else c ^= flip;
-                acc |= squeeze4(c & vm) << (8 * g);
+                acc |= squeeze4m(c & vm) << (8 * g);
             }
         }
         dst[j] = acc;
@@ -85,8 +205,15 @@ __device__ inline int overlap_search(const u32* a, int la, const u32* p, int lp,
     if (minlen < 16) return 0;
     /* o >= 16: window start s from la-16 down to la-minlen, a full 16-base compare per shift */
     const int s_hi = la - 16, s_lo = la - minlen;
+    const u32 pat8 = (pat & 0xFFFFu) * 0x00010001u;              /* the first 8 bases of the pattern in both halves */
     for (int wi = s_hi >> 4; wi >= (s_lo >> 4); wi--) {
         const u32 lo = a[wi], hi = wi + 1 < pkw ? a[wi + 1] : 0u;
+        /* filter: the two halves of the window at shift sh are the first 8 bases of the candidates sh and sh + 8; a zero
+         * half of (window ^ pat8) exists iff (x - 0x00010001) & ~x & 0x80008000 is not 0 (exact as an any-test) */
+        u32 any = 0;
+#pragma unroll
+        for (int sh = 0; sh < 8; sh++) { const u32 x = __funnelshift_r(lo, hi, 2 * sh) ^ pat8; any |= (x - 0x00010001u) & ~x; }
+        if (!(any & 0x80008000u)) continue;
         u32 hits = 0;
 #pragma unroll
         for (int sh = 0; sh < 16; sh++) hits |= (u32)(__funnelshift_r(lo, hi, 2 * sh) == pat) << sh;
@@ -179,11 +306,11 @@ __global__ void __launch_bounds__(256) k_meta3(EncBatchDev b, HeaderDev h, u32 n
         u32 f, rec; read_locus(b, i, f, rec);
         const u32 crlf = b.t[f].crlf;
         const u32* words = slots + (size_t)r * cfg.slot_words;
-        const u8* bytes = reinterpret_cast<const u8*>(words) + (lc.x & 15u);
         const int nlen = (int)(lc.y - lc.x - 1u - crlf);
         const int rlen = (int)(lc.z - lc.y - 1u - crlf);
         const int slen = (int)(lc.w - lc.z - 1u - crlf);
-        ReadMeta m = thread_tokenise(bytes, nlen < 256 ? nlen : 255);
+        const u32 noff = lc.x & 15u;                                  /* the name's byte offset inside the slot */
+        ReadMeta m = thread_tokenise3(words, noff, nlen < 256 ? nlen : 255);
         m.strand_len = (u8)slen;
         b.meta[i] = m;
         s_meta[r] = m;
@@ -196,9 +323,9 @@ __global__ void __launch_bounds__(256) k_meta3(EncBatchDev b, HeaderDev h, u32 n
         if (m.strand_len != m0.strand_len) clear |= AB_SLEN;
         if (m.lane != m0.lane) clear |= AB_LANE;
         if (m.tile != m0.tile) clear |= AB_TILE;
-        if (m.name1_len != m0.name1_len || !bytes_equal(bytes, name0, m.name1_len)) clear |= AB_N1;
-        if (m.strand_len != m0.strand_len || !bytes_equal(bytes + (lc.z - lc.x), strand0, slen)) clear |= AB_STRAND;
-        const bool eq0 = (n2len == n2len0) && bytes_equal(bytes + m.name2_off, name0 + m0.name2_off, n2len);
+        if (m.name1_len != m0.name1_len || !equal_shared_global(words, noff, name0, m.name1_len)) clear |= AB_N1;
+        if (m.strand_len != m0.strand_len || !equal_shared_global(words, noff + (lc.z - lc.x), strand0, slen)) clear |= AB_STRAND;
+        const bool eq0 = (n2len == n2len0) && equal_shared_global(words, noff + m.name2_off, name0 + m0.name2_off, n2len);
         ChunkDev& ck = b.chunks[c];
         if (clear && (*(volatile u32*)&ck.and_bits & clear)) atomicAnd(&ck.and_bits, ~clear);
         const u32 rel = i - first;
@@ -217,11 +344,23 @@ __global__ void __launch_bounds__(256) k_meta3(EncBatchDev b, HeaderDev h, u32 n
             ChunkDev& ck = b.chunks[c];
             const u32 rel = i0 - b.chunk_first[c];
             const ReadMeta ma = s_meta[2 * tid], mb = s_meta[2 * tid + 1];
-            const u8* n1 = reinterpret_cast<const u8*>(slots + (size_t)(2 * tid) * cfg.slot_words) + (b.loc[i0].x & 15u) + ma.name2_off;
-            const u8* n2 = reinterpret_cast<const u8*>(slots + (size_t)(2 * tid + 1) * cfg.slot_words) + (b.loc[i0 + 1].x & 15u) + mb.name2_off;
+            const u32* w1 = slots + (size_t)(2 * tid) * cfg.slot_words;
+            const u32* w2 = slots + (size_t)(2 * tid + 1) * cfg.slot_words;
+            const u32 o1 = (b.loc[i0].x & 15u) + ma.name2_off, o2 = (b.loc[i0 + 1].x & 15u) + mb.name2_off;
             const int l1 = (int)ma.name_len - (int)ma.name2_off, l2 = (int)mb.name_len - (int)mb.name2_off;
             bool okA = l1 == l2;
-            for (int q = 0; okA && q < l1; q++) { u8 ch = n1[q]; if (h.name2_diff_char != 0 && q == (int)h.name2_diff_pos) ch = h.name2_diff_char; if (ch != n2[q]) okA = false; }
+            if (okA) {                                             /* four bytes at a time; R1's byte at name2_diff_pos reads as name2_diff_char */
+                const int dp = h.name2_diff_char != 0 ? (int)h.name2_diff_pos : -1;
+                u32 diff = 0;
+                for (int q = 0; q < l1; q += 4) {
+                    u32 a = ld4(w1, o1 + (u32)q);
+                    if ((u32)(dp - q) < 4u) { const u32 sh = 8u * (u32)(dp - q); a = (a & ~(0xFFu << sh)) | ((u32)h.name2_diff_char << sh); }
+                    u32 x = a ^ ld4(w2, o2 + (u32)q);
+                    if (l1 - q < 4) x &= (1u << (8 * (l1 - q))) - 1u;
+                    diff |= x;
+                }
+                okA = diff == 0;
+            }
             const bool okB = ma.lane == mb.lane && ma.tile == mb.tile && ma.x == mb.x && ma.y == mb.y;
             if (!okA) atomicMin(&ck.fA, rel + 1);
             if (!okB) atomicMin(&ck.fB, rel + 1);

@@ -46,6 +46,29 @@ def _names_file():
     return [(b"name%02d" % i, n + b"\nACGTTGCAACGTTGCAACGT\n+\nFFFFFFFFFFFFFFFFFFFF\n") for i, (n, _) in enumerate(KAT_NAMES)]
 
 
+def _numeric_edge_names(name2):
+    """records whose names all tokenise with lane/tile/x/y (so the header keeps those columns); x and y stay below 2^21"""
+    import random
+    rng = random.Random(20261017)
+    names = [
+        b"@a:b:c:1:2:3:4", b"@a:b:c:0000000001:00000000002:000000003:0000000000004", b"@a:b:c:12345678:87654321:1048575:2097151",
+        b"@a:b:c:123456789:999999999:5:6", b"@a:b:c:99999999999999999999:18446744073709551616:7:8", b"@a:b:c:+5:-3:9:10",
+        b"@a:b:c:\t7:\x0b2:3:4", b"@a:b:c:1x:2:3y:4", b"@a:b:c::::", b"@a:b:c:4294967296:65536:00:000", b"@a:b:c:2147483648:9223372036854775807:1:1",
+        b"@a:b:c:-9223372036854775809:-1:2:2", b"@a:b:c:12a4:1 2:3:4"[:13] + b":5:6:7", b"@" + b"X" * 70 + b":b:c:1:2:3:4", b"@a:" + b"Y" * 80 + b":c:11:22:33:44",
+    ]
+    for pad in range(40, 72):                      # the space that ends the scan walks across bytes 56..80
+        names.append(b"@" + b"Z" * pad + b":bb:cc:3:1101:%d:%d" % (1000 + pad, 2000 + pad))
+    for _ in range(300):
+        parts = [bytes(rng.choice(b"ABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789-_") for _ in range(rng.randint(1, 24))) for _ in range(3)]
+        def num(maxv):
+            v = rng.randint(0, maxv)
+            return (b"%d" % v).rjust(rng.choice([0, 0, 0, 1, 4, 5, 8, 9, 12]), b"0")
+        fields = [num(300), num(70000), num((1 << 21) - 1), num((1 << 21) - 1)]
+        names.append(b"@" + b":".join(parts + fields))
+    rec = b"\nACGTTGCAACGTTGCAACGT\n+\nFFFFFFFFFFFFFFFFFFFF\n"
+    return b"".join(n + name2 + rec for n in names)
+
+
 def build_cases():
     """-> list of dict(name, r1, r2|None, k (chunk kilobases), interleaved)"""
     cases = []
@@ -123,6 +146,11 @@ def build_cases():
     # read length > 255 mixed with short: 2-byte length column, variable
     r1, r2 = fqgen.generate(600, seed=16, paired=True, flags=fqgen.LONG | fqgen.VARLEN)
     add("nova_pe_300bp_varlen_k100", r1, r2, k=100)
+
+    # name fields at the edges of the SIMD tokeniser / digit parser of k_meta3: 1..13 digits, leading zeros, signs, blanks,
+    # letters, empty fields, saturation, separators on 16-byte boundaries, scans ending before / at / after byte 64
+    add("names_numeric_edge", _numeric_edge_names(b" 1:N:0:ACGT"))
+    add("names_numeric_edge_pe", _numeric_edge_names(b" 1:N:0:ACGT"), _numeric_edge_names(b" 2:N:0:ACGT"))
 
     # single read, single pair, empty-ish
     add("one_read", join(records(KAT_A1)[:1]))
