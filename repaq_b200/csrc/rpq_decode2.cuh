@@ -18,62 +18,86 @@ struct Fmt2Cfg {
 namespace rpq {
 
 /*
- * k_dec_coords2: decodeCoords (reference src/rfqcodec.cpp:1332-1389) with a WARP per (chunk, column), 32 stream bytes per
- * step (v1 ran one thread per stream and was latency bound: 1 ms for 3.4 KB streams).  Token length depends on the first
- * byte only (0xxxxxxx: 2 bytes absolute, 10xxxxxx: 1 byte delta, 110xxxxx: 1 byte repeat, 111xxxxx: 3 bytes absolute);
- * values are a segmented inclusive scan (absolute tokens reset, deltas add), output slots an exclusive scan of counts.
- * grid (n_chunks, 2), 32 threads.
+ * k_dec_coords3: decodeCoords (reference src/rfqcodec.cpp:1332-1389) with a CTA per (chunk, column), one stream byte per thread
+ * and DC3_THREADS bytes per step.  v1 ran a thread per stream (latency bound: 1 ms for 3.4 KB streams), v2 a warp per stream
+ * whose step still resolved the token heads one after the other (0.39 ms, the time of its longest warp whatever the batch).
+ * Token length depends on the first byte only (0xxxxxxx: 2 bytes absolute, 10xxxxxx: 1 byte delta, 110xxxxx: 1 byte repeat,
+ * 111xxxxx: 3 bytes absolute), so "how many payload bytes are still to be skipped" is a 3-state machine; every byte is a map of
+ * that state (three 2-bit fields), and an inclusive scan of the maps under composition tells every thread whether its byte is a
+ * head.  Values are a segmented inclusive scan (absolute tokens reset, deltas add), output slots an exclusive scan of counts;
+ * both scans and the state cross warps through shared memory.  grid (n_chunks, 2).
  */
-__global__ void __launch_bounds__(32) k_dec_coords2(DecBatchDev b, HeaderDev h) {
+constexpr int DC3_THREADS = 256;
+constexpr u32 DC3_IDENT = 0x24u;                      /* state s -> s */
+/* first f, then g */
+__device__ __forceinline__ u32 dc3_compose(u32 f, u32 g) {
+    return ((g >> (2u * (f & 3u))) & 3u) | (((g >> (2u * ((f >> 2) & 3u))) & 3u) << 2) | (((g >> (2u * ((f >> 4) & 3u))) & 3u) << 4);
+}
+
+__global__ void __launch_bounds__(DC3_THREADS) k_dec_coords3(DecBatchDev b, HeaderDev h) {
+    constexpr int NW = DC3_THREADS / 32;
+    __shared__ u32 s_map[NW], s_r[NW], s_v[NW], s_c[NW];
     const u32 c = blockIdx.x, col = blockIdx.y;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!(h.flags & (col ? RPQ_HAS_Y : RPQ_HAS_X))) return;
     const DecChunk& ck = b.chunks[c];
     const u8* buf = b.body + ck.in_off + (col ? ck.off_y : ck.off_x);
     const u32 len = col ? ck.y_size : ck.x_size;
     const u32 num = (ck.flags & RPQ_PE_INTERLEAVED) ? ck.reads / 2 : ck.reads;
     u32* data = (col ? b.ys : b.xs) + ck.read_base;
-    u32 last = 1000, d = 0, skip = 0;
-    for (u32 base = 0; base < len; base += 32) {
-        const u32 p = base + lane;
+    u32 last = 1000, d = 0, state = 0;                 /* state: payload bytes of the previous step's last token still to come */
+    u32 nb = (u32)tid < len ? buf[tid] : 0u;
+    for (u32 base = 0; base < len; base += DC3_THREADS) {
+        const u32 p = base + (u32)tid;
         const bool valid = p < len;
-        const u32 b0 = valid ? buf[p] : 0xC0u;
-        const u32 tlen = !(b0 & 0x80) ? 2u : ((b0 & 0xE0) == 0xE0) ? 3u : 1u;
-        u32 multi = __ballot_sync(0xffffffffu, valid && tlen > 1);
-        const u32 is3 = __ballot_sync(0xffffffffu, valid && tlen == 3);
-        u32 skipped = skip >= 32 ? 0xffffffffu : ((1u << skip) - 1u);
-        u32 next_skip = skip > 32 ? skip - 32 : 0;
-        while (multi) {
-            const int i = __ffs((int)multi) - 1;
-            multi &= multi - 1;
-            if ((skipped >> i) & 1u) continue;
-            const u32 hi = (u32)i + (((is3 >> i) & 1u) ? 2u : 1u);
-            for (u32 k = (u32)i + 1; k <= hi && k < 32; k++) skipped |= 1u << k;
-            if (hi >= 32) next_skip = hi - 31;
-        }
-        const bool head = valid && !((skipped >> lane) & 1u);
+        const u32 b0 = nb;
+        nb = p + DC3_THREADS < len ? buf[p + DC3_THREADS] : 0u;          /* the next step's byte is in flight during this one */
+        const u32 cont = !(b0 & 0x80u) ? 1u : ((b0 & 0xE0u) == 0xE0u ? 2u : 0u);
+        /* this byte as a map: state 0 (a head) -> cont, 1 -> 0, 2 -> 1 */
+        u32 inc = valid ? (cont | 0x10u) : DC3_IDENT;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) { const u32 prev = __shfl_up_sync(0xffffffffu, inc, s); if (lane >= s) inc = dc3_compose(prev, inc); }
+        if (lane == 31) s_map[warp] = inc;
+        u32 exm = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) exm = DC3_IDENT;
+        __syncthreads();
+        u32 st = state, st_all = state;
+#pragma unroll
+        for (int q = 0; q < NW; q++) { const u32 m = s_map[q]; st_all = (m >> (2u * st_all)) & 3u; if (q < warp) st = st_all; }
+        state = st_all;
+        const bool head = valid && ((exm >> (2u * st)) & 3u) == 0u;
         u32 reset = 0, val = 0, cnt = 0;
         if (head) {
-            if (!(b0 & 0x80)) { reset = 1; val = (b0 << 8) | (p + 1 < len ? buf[p + 1] : 0u); cnt = 1; }
-            else if (!(b0 & 0x40)) { val = (b0 & 0x3F) + 1; cnt = 1; }
-            else if (!(b0 & 0x20)) { cnt = (b0 & 0x1F) + 1; }
-            else { reset = 1; val = ((b0 & 0x1F) << 16) | ((u32)(p + 1 < len ? buf[p + 1] : 0u) << 8) | (u32)(p + 2 < len ? buf[p + 2] : 0u); cnt = 1; }
+            if (!(b0 & 0x80u)) { reset = 1; val = (b0 << 8) | (p + 1 < len ? buf[p + 1] : 0u); cnt = 1; }
+            else if (!(b0 & 0x40u)) { val = (b0 & 0x3Fu) + 1; cnt = 1; }
+            else if (!(b0 & 0x20u)) { cnt = (b0 & 0x1Fu) + 1; }
+            else { reset = 1; val = ((b0 & 0x1Fu) << 16) | ((u32)(p + 1 < len ? buf[p + 1] : 0u) << 8) | (u32)(p + 2 < len ? buf[p + 2] : 0u); cnt = 1; }
         }
-        /* segmented inclusive scan of (reset, val) */
-        u32 r = reset, v = val;
+        /* segmented inclusive scan of (reset, val), inclusive scan of cnt: inside the warp ... */
+        u32 r = reset, v = val, ci = cnt;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
-            const u32 pr = __shfl_up_sync(0xffffffffu, r, s), pv = __shfl_up_sync(0xffffffffu, v, s);
-            if (lane >= s && !r) { v += pv; r = pr; }
+            const u32 pr = __shfl_up_sync(0xffffffffu, r, s), pv = __shfl_up_sync(0xffffffffu, v, s), pc = __shfl_up_sync(0xffffffffu, ci, s);
+            if (lane >= s) { if (!r) { v += pv; r = pr; } ci += pc; }
         }
+        if (lane == 31) { s_r[warp] = r; s_v[warp] = v; s_c[warp] = ci; }
+        __syncthreads();
+        /* ... and across the warps before this one (and all of them, for the next step) */
+        u32 wr = 0, wv = 0, wc = 0, ar = 0, av = 0, ac = 0;
+#pragma unroll
+        for (int q = 0; q < NW; q++) {
+            const u32 qr = s_r[q], qv = s_v[q], qc = s_c[q];
+            if (qr) { ar = 1; av = qv; } else av += qv;
+            ac += qc;
+            if (q + 1 == warp) { wr = ar; wv = av; wc = ac; }
+        }
+        if (!r) { v += wv; r = wr; }
         const u32 value = r ? v : last + v;
-        u32 tot; const u32 ex = warp_excl_scan(cnt, lane, tot);
-        if (head) { for (u32 k = 0; k < cnt; k++) if (d + ex + k < num) data[d + ex + k] = value; }
-        last = __shfl_sync(0xffffffffu, value, 31);
-        d += tot;
-        skip = next_skip;
+        if (head) { const u32 o = d + wc + ci - cnt; for (u32 k = 0; k < cnt; k++) if (o + k < num) data[o + k] = value; }
+        last = ar ? av : last + av;
+        d += ac;
     }
-    for (u32 k = d + lane; k < num; k += 32) data[k] = 0;      /* memset(xBuf, 0): values the stream does not cover stay 0 */
+    for (u32 k = d + (u32)tid; k < num; k += DC3_THREADS) data[k] = 0;      /* memset(xBuf, 0): values the stream does not cover stay 0 */
 }
 
 }  // namespace rpq
@@ -107,8 +131,11 @@ __global__ void k_dec_walk_fast(const u8* body, u64 len, HeaderDev h, DecChunk* 
         if (bytes < (long long)head || at + (u64)bytes > len) break;
 #ifndef RPQ_EMU
         {
-            const long long pf = (long long)at + 2ll * bytes + ((long long)lane - 16) * 128;
-            if (pf >= 0 && (u64)pf + 128 <= len) asm volatile("prefetch.global.L2 [%0];" ::"l"(body + pf));
+            /* 16 KiB around the expected place of the header after the next one, four lines per lane: the size of the chunks of one
+             * file varies by a few KiB, and a header that is not in L2 when the chain arrives costs a DRAM round trip */
+            const long long pf = (long long)at + 3ll * bytes + ((long long)lane - 16) * 512;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const long long q = pf + 128 * k; if (q >= 0 && (u64)q + 128 <= len) asm volatile("prefetch.global.L2 [%0];" ::"l"(body + q)); }
         }
 #endif
         if (lane == 0) {
