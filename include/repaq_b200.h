@@ -153,6 +153,43 @@ typedef struct rpq_decode_out {
 
 int rpq_decode(rpq_ctx* ctx, const rpq_decode_in* in, rpq_decode_out* out);
 
+/* ---- compare: Repaq::compare / comparePE (src/repaq.cpp:36-233), also the check behind `-c ... -v` (completeCheckAndOutput,
+ * src/repaq.cpp:430-528): every chunk of an .rfq body is decoded and its reads are checked one by one - name, sequence, strand,
+ * quality - against the reads of the FASTQ file(s); the first difference ends the run.  Decoded text and FASTQ index stay in
+ * device memory.  Large files are compared in batches: whole chunks on one side, a window of FASTQ text that holds at least as
+ * many reads on the other (r?_consumed tells where the next window starts); the caller adds the counters up. */
+#define RPQ_CMP_EQUAL 0          /* every decoded read equals its FASTQ read */
+#define RPQ_CMP_NAME 1           /* "... have different name in the N read" (src/repaq.cpp:86) */
+#define RPQ_CMP_SEQUENCE 2
+#define RPQ_CMP_STRAND 3
+#define RPQ_CMP_QUALITY 4
+#define RPQ_CMP_RFQ_MORE 5       /* "The RFQ file has more reads than the FASTQ file." (:75); needs fq_final */
+#define RPQ_CMP_FASTQ_MORE 6     /* "The FASTQ file has more reads than the RFQ file." (:120); needs rfq_final */
+#define RPQ_CMP_NEED_FASTQ 7     /* the FASTQ window ended before the chunks did and fq_final is 0: call again with more text */
+
+typedef struct rpq_compare_in {
+    const uint8_t* rfq; uint64_t rfq_bytes;   /* whole chunks of the .rfq body (may be empty) */
+    int rfq_mem;                              /* RPQ_MEM_HOST or RPQ_MEM_DEVICE */
+    int rfq_final;                            /* 1: no chunks follow these */
+    const char* r1; uint64_t r1_len;          /* FASTQ text the decoded reads are checked against, < 4 GiB per file and call */
+    const char* r2; uint64_t r2_len;          /* mate file (comparePE), or NULL */
+    int fq_mem;
+    int fq_final;                             /* 1: the FASTQ text ends here */
+} rpq_compare_in;
+
+typedef struct rpq_compare_out {
+    int verdict;                              /* RPQ_CMP_* */
+    /* the counters of reportCompareResult (src/repaq.cpp:235-259) for this call: reads and bases up to and including the read
+     * that ended the run (both mates counted) */
+    uint64_t fastq_reads, rfq_reads, fastq_bases, rfq_bases;
+    uint64_t read_index;                      /* 0-based index (mates interleaved) of the read that ended the run */
+    const char* rfq_field; uint32_t rfq_field_len;       /* verdicts 1..4: the two strings of the message, host memory owned */
+    const char* fastq_field; uint32_t fastq_field_len;   /* by ctx, NUL terminated, valid until the next call */
+    uint64_t r1_consumed, r2_consumed, rfq_consumed;     /* RPQ_CMP_EQUAL: text / body bytes covered by the reads compared */
+} rpq_compare_out;
+
+int rpq_compare(rpq_ctx* ctx, const rpq_compare_in* in, rpq_compare_out* out);
+
 /* ---- instrumentation for bench.py: kernels launched and device milliseconds (CUDA events on the context's
  * stream) of the last rpq_encode / rpq_decode call, split by stage. */
 typedef struct rpq_stats {

@@ -46,6 +46,8 @@ def lib():
         L.orc_decompress.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.orc_free.argtypes = [C.c_void_p]
+        L.orc_compare.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.orc_compare.restype = C.c_int
         _lib = L
     return _lib
 
@@ -97,6 +99,21 @@ def decompress(rfq: bytes, pe_out=False):
     return (a, b) if pe_out else a
 
 
+def compare(rfq: bytes, r1, r2=None) -> str:
+    """Repaq::compare / comparePE: the JSON report the reference prints for `repaq --compare -i r1 [-I r2] -r x.rfq`."""
+    L = lib()
+    pq, lq = _as_buf(rfq)
+    p1, l1 = _as_buf(r1)
+    p2, l2 = (None, 0) if r2 is None else _as_buf(r2)
+    out = C.c_void_p()
+    rc = L.orc_compare(pq, lq, p1, l1, p2, l2, C.byref(out))
+    if rc:
+        raise RuntimeError(L.orc_last_error().decode())
+    txt = C.string_at(out).decode("latin1")
+    L.orc_free(out)
+    return txt
+
+
 def have_ref():
     return os.path.exists(REF_BIN)
 
@@ -126,3 +143,17 @@ def ref_decompress(tmpdir, rfq: bytes, pe_out=False):
     subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     a = open(o1, "rb").read()
     return (a, open(o2, "rb").read()) if pe_out else a
+
+
+def ref_compare(tmpdir, rfq: bytes, r1: bytes, r2: bytes = None) -> str:
+    """Run the unmodified reference binary in compare mode; returns what it prints on stdout."""
+    p = os.path.join(tmpdir, "cmp.rfq")
+    open(p, "wb").write(rfq)
+    p1 = os.path.join(tmpdir, "cmp1.fq")
+    open(p1, "wb").write(r1)
+    cmd = [REF_BIN, "--compare", "-i", p1, "-r", p]
+    if r2 is not None:
+        p2 = os.path.join(tmpdir, "cmp2.fq")
+        open(p2, "wb").write(r2)
+        cmd += ["-I", p2]
+    return subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout.decode("latin1")

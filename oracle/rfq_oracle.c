@@ -867,3 +867,108 @@ int orc_decompress(const uint8_t* rfq, size_t len, int pe_out, char** out1, size
     if (out2) { *out2 = (char*)b.p; *l2 = b.n; } else free(b.p);
     return 0;
 }
+
+/* ------------------------------------------------------------------ compare mode ---- */
+static void sb_put(strbuf* b, const char* s, size_t n) {
+    if (b->n + n + 1 > b->cap) { b->cap = (b->n + n + 1) * 2; b->p = (char*)realloc(b->p, b->cap); }
+    memcpy(b->p + b->n, s, n); b->n += n; b->p[b->n] = 0;
+}
+static void sb_str(strbuf* b, const char* s) { sb_put(b, s, strlen(s)); }
+static void sb_num(strbuf* b, long v) { char t[32]; snprintf(t, sizeof t, "%ld", v); sb_str(b, t); }
+
+/* Repaq::reportCompareResult (src/repaq.cpp:235-259) */
+static char* cmp_report(int passed, const strbuf* msg, long fq_reads, long fq_bases, long rfq_reads, long rfq_bases) {
+    strbuf j = {0, 0, 0};
+    sb_str(&j, "{\n");
+    sb_str(&j, passed ? "\t\"result\":\"passed\",\n" : "\t\"result\":\"failed\",\n");
+    sb_str(&j, "\t\"msg\":\""); if (msg->n) sb_put(&j, msg->p, msg->n); sb_str(&j, "\",\n");
+    sb_str(&j, "\t\"fastq_reads\":"); sb_num(&j, fq_reads); sb_str(&j, ",\n");
+    sb_str(&j, "\t\"rfq_reads\":"); sb_num(&j, rfq_reads); sb_str(&j, ",\n");
+    sb_str(&j, "\t\"fastq_bases\":"); sb_num(&j, fq_bases); sb_str(&j, ",\n");
+    sb_str(&j, "\t\"rfq_bases\":"); sb_num(&j, rfq_bases); sb_str(&j, "\n");
+    sb_str(&j, "}\n");
+    return j.p;
+}
+
+/* Repaq::compare (src/repaq.cpp:36-130) and comparePE (:132-233): every chunk of the .rfq is decoded and its reads are
+ * checked name, sequence, strand, quality against the reads of the FASTQ file(s); the first difference ends the run.
+ * r2 == NULL: single end.  *json = the text the reference prints (malloc'd). */
+int orc_compare(const uint8_t* rfq, size_t len, const char* r1, size_t l1, const char* r2, size_t l2, char** json) {
+    orc_header h; size_t at = orc_header_read(rfq, len, &h);
+    if (!at) return -1;
+    const int pe = r2 != NULL;
+    orc_reader* a = orc_reader_open(r1, l1);
+    orc_reader* b = pe ? orc_reader_open(r2, l2) : NULL;
+    long fq_reads = 0, fq_bases = 0, rfq_reads = 0, rfq_bases = 0;
+    strbuf msg = {0, 0, 0};
+    int done = 0, passed = 0;
+    orc_read left, right; int have_pair = 0;
+    char* keep[4] = {0, 0, 0, 0};                      /* the left mate's fields: the reader reuses its line buffers */
+    const char* unit = pe ? " pair. " : " read. ";
+    while (!done && at < len) {
+        orc_decoded d; size_t used = orc_decode_chunk(&h, rfq + at, len - at, &d);
+        if (!used) break;
+        at += used;
+        size_t prev = 0;
+        for (size_t r = 0; r < d.n_reads && !done; r++) {
+            /* the decoded read: four lines of d.text[prev, read_end[r]) */
+            const char* f[4]; size_t fl[4]; size_t p = prev;
+            for (int k = 0; k < 4; k++) { f[k] = d.text + p; size_t q = p; while (d.text[q] != '\n') q++; fl[k] = q - p; p = q + 1; }
+            prev = d.read_end[r];
+            rfq_bases += (long)fl[1];
+            rfq_reads++;
+            orc_read fq; int got = 1;
+            if (!pe) got = orc_reader_next(a, &fq);
+            else {
+                if (!have_pair) {
+                    /* FastqReaderPair::read pulls both mates, and fails when either is missing */
+                    int g1 = orc_reader_next(a, &left);
+                    if (g1) {
+                        const char* src[4] = {left.name, left.seq, left.strand, left.qual}; const uint32_t sl[4] = {left.name_len, left.seq_len, left.strand_len, left.qual_len};
+                        for (int k = 0; k < 4; k++) { free(keep[k]); keep[k] = (char*)malloc(sl[k] + 1); memcpy(keep[k], src[k], sl[k]); }
+                        left.name = keep[0]; left.seq = keep[1]; left.strand = keep[2]; left.qual = keep[3];
+                    }
+                    int g2 = orc_reader_next(b, &right);
+                    got = g1 && g2;
+                    have_pair = got;
+                }
+                if (got) fq = (rfq_reads % 2 == 1) ? left : right;
+            }
+            const long shown = pe ? rfq_reads / 2 : rfq_reads;
+            if (!got) {
+                sb_str(&msg, "The RFQ file has more reads than the FASTQ file. The RFQ file has >= "); sb_num(&msg, shown);
+                sb_str(&msg, pe ? " pairs, while the FASTQ file only has " : " reads, while the FASTQ file only has ");
+                sb_num(&msg, pe ? fq_reads / 2 : fq_reads); sb_str(&msg, pe ? " pairs" : " reads");
+                done = 1; break;
+            }
+            fq_reads++; fq_bases += (long)fq.seq_len;
+            const char* g[4] = {fq.name, fq.seq, fq.strand, fq.qual}; const uint32_t gl[4] = {fq.name_len, fq.seq_len, fq.strand_len, fq.qual_len};
+            static const char* what[4] = {"name", "sequence", "strand", "quality"};
+            for (int k = 0; k < 4; k++) {
+                if (fl[k] != gl[k] || memcmp(f[k], g[k], fl[k]) != 0) {
+                    sb_str(&msg, "The RFQ file and FASTQ file have different "); sb_str(&msg, what[k]); sb_str(&msg, " in the "); sb_num(&msg, shown); sb_str(&msg, unit);
+                    sb_put(&msg, f[k], fl[k]); sb_str(&msg, " | "); sb_put(&msg, g[k], gl[k]);
+                    done = 1; break;
+                }
+            }
+            if (pe && rfq_reads % 2 == 0) have_pair = 0;
+        }
+        orc_decoded_free(&d);
+    }
+    if (!done) {
+        orc_read x, y; int more;
+        if (!pe) more = orc_reader_next(a, &x);
+        else { int g1 = orc_reader_next(a, &x); int g2 = orc_reader_next(b, &y); more = g1 && g2; }
+        if (more) {
+            fq_reads++;
+            sb_str(&msg, "The FASTQ file has more reads than the RFQ file. The FASTQ file has >= "); sb_num(&msg, pe ? fq_reads / 2 : fq_reads);
+            sb_str(&msg, pe ? " pairs, while the RFQ file only has " : " reads, while the RFQ file only has ");
+            sb_num(&msg, pe ? rfq_reads / 2 : rfq_reads); sb_str(&msg, pe ? " pairs" : " reads");
+        } else passed = 1;
+    }
+    *json = cmp_report(passed, &msg, fq_reads, fq_bases, rfq_reads, rfq_bases);
+    free(msg.p);
+    for (int k = 0; k < 4; k++) free(keep[k]);
+    orc_reader_close(a); if (b) orc_reader_close(b);
+    return 0;
+}

@@ -124,6 +124,10 @@ int orc_compress(const char* r1, size_t l1, const char* r2, size_t l2, int inter
 /* Repaq::decompress (pe_out == 0) / decompressPE (pe_out != 0) (src/repaq.cpp:262-413) */
 int orc_decompress(const uint8_t* rfq, size_t len, int pe_out, char** out1, size_t* l1, char** out2, size_t* l2);
 
+/* Repaq::compare / comparePE (src/repaq.cpp:36-233) with the report of reportCompareResult (:235-259): *json is the
+ * text the reference prints on stdout (malloc'd).  r2 == NULL: single end. */
+int orc_compare(const uint8_t* rfq, size_t len, const char* r1, size_t l1, const char* r2, size_t l2, char** json);
+
 void orc_free(void* p);
 
 #ifdef __cplusplus

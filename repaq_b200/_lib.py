@@ -44,13 +44,26 @@ class DecodeOut(C.Structure):
                 ("n_chunks", C.c_uint32), ("chunks", C.POINTER(ChunkInfo)), ("n_reads", C.c_uint64), ("consumed", C.c_uint64)]
 
 
+class CompareIn(C.Structure):
+    _fields_ = [("rfq", C.c_void_p), ("rfq_bytes", C.c_uint64), ("rfq_mem", C.c_int), ("rfq_final", C.c_int),
+                ("r1", C.c_void_p), ("r1_len", C.c_uint64), ("r2", C.c_void_p), ("r2_len", C.c_uint64),
+                ("fq_mem", C.c_int), ("fq_final", C.c_int)]
+
+
+class CompareOut(C.Structure):
+    _fields_ = [("verdict", C.c_int), ("fastq_reads", C.c_uint64), ("rfq_reads", C.c_uint64), ("fastq_bases", C.c_uint64),
+                ("rfq_bases", C.c_uint64), ("read_index", C.c_uint64), ("rfq_field", C.c_void_p), ("rfq_field_len", C.c_uint32),
+                ("fastq_field", C.c_void_p), ("fastq_field_len", C.c_uint32), ("r1_consumed", C.c_uint64),
+                ("r2_consumed", C.c_uint64), ("rfq_consumed", C.c_uint64)]
+
+
 class Stats(C.Structure):
     _fields_ = [("launches", C.c_uint32), ("ms_total", C.c_float), ("ms_kernels", C.c_float), ("ms_h2d", C.c_float),
                 ("ms_d2h", C.c_float), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 EXPORTS = ["rpq_make_header", "rpq_header_write", "rpq_header_read", "rpq_create", "rpq_destroy", "rpq_last_error",
-           "rpq_set_header", "rpq_stream", "rpq_encode", "rpq_decode", "rpq_get_stats", "rpq_set_profiling", "rpq_get_profile"]
+           "rpq_set_header", "rpq_stream", "rpq_encode", "rpq_decode", "rpq_compare", "rpq_get_stats", "rpq_set_profiling", "rpq_get_profile"]
 
 _libs = {}
 
@@ -77,6 +90,7 @@ def load(path=None):
     L.rpq_stream.restype = C.c_void_p
     L.rpq_encode.argtypes = [C.c_void_p, C.POINTER(EncodeIn), C.POINTER(EncodeOut)]
     L.rpq_decode.argtypes = [C.c_void_p, C.POINTER(DecodeIn), C.POINTER(DecodeOut)]
+    L.rpq_compare.argtypes = [C.c_void_p, C.POINTER(CompareIn), C.POINTER(CompareOut)]
     L.rpq_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.rpq_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.rpq_get_profile.argtypes = [C.c_void_p]

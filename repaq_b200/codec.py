@@ -3,6 +3,7 @@
 * `Codec`      ~ class RfqCodec          (reference src/rfqcodec.h:17-43): set_header / make_header / encode / decode
 * `compress`   ~ Repaq::compress, compressPE   (src/repaq.cpp:530-759) on in-memory FASTQ images
 * `decompress` ~ Repaq::decompress, decompressPE (src/repaq.cpp:262-413), including the trailing-newline rule
+* `compare`    ~ Repaq::compare, comparePE (src/repaq.cpp:36-233) with the report of reportCompareResult (:235-259)
 
 No algorithmic work happens here: Python sizes buffers, passes pointers, and applies the reference's host-side
 file-level rules (Q13 flag thresholds, last-newline trimming).
@@ -160,6 +161,68 @@ class Codec:
         o2 = C.string_at(out.out2, out.out2_bytes) if out.out2_bytes else b""
         infos = [{f: getattr(out.chunks[i], f) for f, _ in _lib.ChunkInfo._fields_} for i in range(out.n_chunks)]
         return o1, o2, infos, dict(n_reads=out.n_reads, consumed=out.consumed)
+
+
+    def compare_raw(self, prfq, nrfq, rfq_mem, rfq_final, p1, l1, p2, l2, fq_mem, fq_final):
+        cin = _lib.CompareIn()
+        cin.rfq, cin.rfq_bytes, cin.rfq_mem, cin.rfq_final = prfq, nrfq, rfq_mem, int(rfq_final)
+        cin.r1, cin.r1_len, cin.r2, cin.r2_len, cin.fq_mem, cin.fq_final = p1, l1, p2, l2, fq_mem, int(fq_final)
+        out = _lib.CompareOut()
+        rc = self.L.rpq_compare(self.ctx, C.byref(cin), C.byref(out))
+        if rc:
+            raise self._err(rc)
+        return out
+
+
+CMP_FIELDS = {1: "name", 2: "sequence", 3: "strand", 4: "quality"}
+
+
+def compare_report(passed, msg, fastq_reads, fastq_bases, rfq_reads, rfq_bases):
+    """Repaq::reportCompareResult (reference src/repaq.cpp:235-259): the text printed on stdout / written with -j"""
+    return ("{\n\t\"result\":\"%s\",\n\t\"msg\":\"%s\",\n\t\"fastq_reads\":%d,\n\t\"rfq_reads\":%d,\n\t\"fastq_bases\":%d,\n\t\"rfq_bases\":%d\n}\n"
+            % ("passed" if passed else "failed", msg, fastq_reads, rfq_reads, fastq_bases, rfq_bases))
+
+
+def compare_message(out, pe):
+    """the `msg` of a finished comparison, worded as Repaq::compare / comparePE do (src/repaq.cpp:71-122, :174-225)"""
+    v = out.verdict
+    shown = (lambda n: n // 2) if pe else (lambda n: n)
+    unit, units = ("pair", "pairs") if pe else ("read", "reads")
+    if v == 0:
+        return ""
+    if v in CMP_FIELDS:
+        a = C.string_at(out.rfq_field, out.rfq_field_len).decode("latin1")
+        g = C.string_at(out.fastq_field, out.fastq_field_len).decode("latin1")
+        return "The RFQ file and FASTQ file have different %s in the %d %s. %s | %s" % (CMP_FIELDS[v], shown(out.rfq_reads), unit, a, g)
+    if v == 5:
+        return ("The RFQ file has more reads than the FASTQ file. The RFQ file has >= %d %s, while the FASTQ file only has %d %s"
+                % (shown(out.rfq_reads), units, shown(out.fastq_reads), units))
+    if v == 6:
+        return ("The FASTQ file has more reads than the RFQ file. The FASTQ file has >= %d %s, while the RFQ file only has %d %s"
+                % (shown(out.fastq_reads), units, shown(out.rfq_reads), units))
+    raise RepaqError(-2, "comparison not finished (verdict %d)" % v)
+
+
+def compare(rfq, r1, r2=None, codec=None, device=0, lib_path=None):
+    """.rfq file image against FASTQ image(s), like `repaq --compare -i r1 [-I r2] -r x.rfq`: returns the JSON text the
+    reference prints.  Decode, index and the field-wise check all run on the GPU (rpq_compare)."""
+    own = codec is None
+    codec = codec or Codec(device, lib_path)
+    try:
+        h, used = parse_header(rfq, codec.lib_path)
+        codec.set_header(h)
+        body = np.frombuffer(rfq, dtype=np.uint8)[used:]
+        pb, nb, kb = _buf(body)
+        p1, l1, k1 = _buf(r1)
+        p2, l2, k2 = _buf(r2)
+        if r2 is not None and p2 is None:                      # an empty mate file is still "paired end"
+            k2 = np.zeros(1, dtype=np.uint8)
+            p2, l2 = k2.ctypes.data, 0
+        out = codec.compare_raw(pb, nb, 0, True, p1, l1, p2, l2, 0, True)
+        return compare_report(out.verdict == 0, compare_message(out, r2 is not None), out.fastq_reads, out.fastq_bases, out.rfq_reads, out.rfq_bases)
+    finally:
+        if own:
+            codec.close()
 
 
 def nobreak_rule(size, last_byte):

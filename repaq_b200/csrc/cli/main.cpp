@@ -1,9 +1,10 @@
 /*
- * repaq_b200_cli - host C++ driver with the reference's command line for the two modes on the hot path
- * (`repaq -c` / `repaq -d`, reference src/main.cpp:31-49, src/repaq.cpp:262-413,530-759) on top of the C ABI.
+ * repaq_b200_cli - host C++ driver with the reference's command line for the modes on the hot path
+ * (`repaq -c`, `repaq -d`, `repaq --compare`; reference src/main.cpp:31-49, src/repaq.cpp:36-413,530-759) on top of the C ABI.
  * File-level rules kept from the reference: header written first (src/repaq.cpp:554-557), Q13 NO_LINE_BREAK thresholds
  * (src/fastqreader.cpp:31-46), trailing-newline trimming on decode (src/repaq.cpp:300-328, 375-413).
- * Not implemented here: .gz input/output, the xz pipe, --compare / -v / -f (outside the tier's scope).
+ * Compare mode prints the reference's JSON report (src/repaq.cpp:235-259).
+ * Not implemented here: .gz input/output, the xz pipe, -v / -f (outside the tier's scope).
  */
 #include <stdint.h>
 #include <stdio.h>
@@ -50,7 +51,7 @@ static void nobreak_rule(const std::vector<char>& f, uint64_t& from, bool& tail)
     else { from = nl ? UINT64_MAX : (n / MiB) * MiB; tail = false; }
 }
 
-struct Opt { std::string in1, in2, out1, out2; bool compress = false, decompress = false, interleaved = false, to_stdout = false, from_stdin = false; int k = 1000; int device = 0; };
+struct Opt { std::string in1, in2, out1, out2, rfq_compare, json_compare; bool compress = false, decompress = false, compare = false, interleaved = false, to_stdout = false, from_stdin = false; int k = 1000; int device = 0; };
 
 static int do_compress(const Opt& o) {
     std::vector<char> r1 = slurp(o.in1), r2;
@@ -132,6 +133,72 @@ static int do_decompress(const Opt& o) {
     return 0;
 }
 
+/* Repaq::compare / comparePE (src/repaq.cpp:36-233): the .rfq is decoded and checked read by read against the FASTQ file(s) on
+ * the GPU, in batches of whole chunks against windows of FASTQ text; the report is reportCompareResult's (:235-259). */
+static int do_compare(const Opt& o) {
+    std::vector<char> rfq = slurp(o.rfq_compare), r1 = slurp(o.in1), r2;
+    const bool pe = !o.in2.empty();
+    if (pe) r2 = slurp(o.in2);
+    char err[768]; rpq_header h; size_t used = 0;
+    if (rpq_header_read((const uint8_t*)rfq.data(), rfq.size(), &h, &used, err, sizeof err)) error_exit(err);
+    rpq_ctx* ctx = NULL;
+    if (rpq_create(o.device, &ctx)) error_exit("no CUDA device: repaq_b200 has no CPU fallback");
+    if (rpq_set_header(ctx, &h)) error_exit(rpq_last_error(ctx));
+    const uint64_t FQ_WIN = 3ull << 30;                    /* < 4 GiB of text per file and call */
+    uint64_t rfq_win = 256ull << 20;                       /* chunks decoded per call: ~2 GB of FASTQ at the usual ratios */
+    uint64_t at = used, a = 0, b = 0;
+    unsigned long long fq_reads = 0, fq_bases = 0, rfq_reads = 0, rfq_bases = 0;
+    bool passed = false; std::string msg;
+    for (;;) {
+        rpq_compare_in in; memset(&in, 0, sizeof in);
+        const uint64_t nq = rfq.size() - at < rfq_win ? rfq.size() - at : rfq_win;
+        const uint64_t n1 = r1.size() - a < FQ_WIN ? r1.size() - a : FQ_WIN, n2 = pe ? (r2.size() - b < FQ_WIN ? r2.size() - b : FQ_WIN) : 0;
+        in.rfq = (const uint8_t*)rfq.data() + at; in.rfq_bytes = nq; in.rfq_mem = RPQ_MEM_HOST; in.rfq_final = at + nq == rfq.size();
+        in.r1 = r1.data() + a; in.r1_len = n1; in.r2 = pe ? (r2.empty() ? "" : r2.data() + b) : NULL; in.r2_len = n2; in.fq_mem = RPQ_MEM_HOST;
+        in.fq_final = (a + n1 == r1.size()) && (!pe || b + n2 == r2.size());
+        rpq_compare_out res;
+        if (rpq_compare(ctx, &in, &res)) error_exit(rpq_last_error(ctx));
+        if (res.verdict == RPQ_CMP_NEED_FASTQ) {           /* these chunks decode to more reads than 3 GiB of text hold: fewer chunks per call */
+            if (rfq_win <= (4ull << 20)) error_exit("compare: a batch of chunks does not fit the FASTQ window");
+            rfq_win /= 2; continue;
+        }
+        fq_reads += res.fastq_reads; fq_bases += res.fastq_bases; rfq_reads += res.rfq_reads; rfq_bases += res.rfq_bases;
+        const unsigned long long sr = pe ? rfq_reads / 2 : rfq_reads, sf = pe ? fq_reads / 2 : fq_reads;
+        const char* unit = pe ? "pair" : "read";
+        if (res.verdict >= RPQ_CMP_NAME && res.verdict <= RPQ_CMP_QUALITY) {
+            static const char* what[4] = {"name", "sequence", "strand", "quality"};
+            msg = std::string("The RFQ file and FASTQ file have different ") + what[res.verdict - RPQ_CMP_NAME] + " in the " + std::to_string(sr) + " " + unit + ". " +
+                  std::string(res.rfq_field, res.rfq_field_len) + " | " + std::string(res.fastq_field, res.fastq_field_len);
+            break;
+        }
+        if (res.verdict == RPQ_CMP_RFQ_MORE) {
+            msg = "The RFQ file has more reads than the FASTQ file. The RFQ file has >= " + std::to_string(sr) + " " + unit + "s, while the FASTQ file only has " + std::to_string(sf) + " " + unit + "s";
+            break;
+        }
+        if (res.verdict == RPQ_CMP_FASTQ_MORE) {
+            msg = "The FASTQ file has more reads than the RFQ file. The FASTQ file has >= " + std::to_string(sf) + " " + unit + "s, while the RFQ file only has " + std::to_string(sr) + " " + unit + "s";
+            break;
+        }
+        /* equal so far */
+        a += res.r1_consumed; b += res.r2_consumed; at += res.rfq_consumed;
+        if (in.rfq_final) at = rfq.size();                 /* whatever follows the last whole chunk is not a chunk: the reference stops there too */
+        else if (res.rfq_consumed == 0) { if (rfq_win >= (2ull << 30)) error_exit("compare: a chunk does not fit the batch window"); rfq_win *= 2; continue; }
+        if (at == rfq.size() && in.fq_final) { passed = true; break; }
+    }
+    std::string json = "{\n";
+    json += passed ? "\t\"result\":\"passed\",\n" : "\t\"result\":\"failed\",\n";
+    json += "\t\"msg\":\"" + msg + "\",\n";
+    json += "\t\"fastq_reads\":" + std::to_string(fq_reads) + ",\n";
+    json += "\t\"rfq_reads\":" + std::to_string(rfq_reads) + ",\n";
+    json += "\t\"fastq_bases\":" + std::to_string(fq_bases) + ",\n";
+    json += "\t\"rfq_bases\":" + std::to_string(rfq_bases) + "\n";
+    json += "}\n";
+    if (!o.json_compare.empty()) spill(o.json_compare, json.data(), json.size(), false);
+    fwrite(json.data(), 1, json.size(), stdout);
+    rpq_destroy(ctx);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc == 1) { fprintf(stderr, "repaq_b200: repack FASTQ to a smaller binary file (.rfq) on a B200\nversion 0.5.1 (algorithm 2)\n"); return 0; }
     if (argc == 2 && strcmp(argv[1], "--version") == 0) { printf("repaq 0.5.1\n"); return 0; }
@@ -149,6 +216,9 @@ int main(int argc, char** argv) {
         else if (a == "-o" || a.compare(0, 7, "--out1=") == 0 || a == "--out1") o.out1 = val("out1");
         else if (a == "-O" || a.compare(0, 7, "--out2=") == 0 || a == "--out2") o.out2 = val("out2");
         else if (a == "-k" || a.compare(0, 8, "--chunk=") == 0 || a == "--chunk") o.k = atoi(val("chunk").c_str());
+        else if (a == "-r" || a.compare(0, 17, "--rfq_to_compare=") == 0 || a == "--rfq_to_compare") o.rfq_compare = val("rfq_to_compare");
+        else if (a == "-j" || a.compare(0, 22, "--json_compare_result=") == 0 || a == "--json_compare_result") o.json_compare = val("json_compare_result");
+        else if (a == "-p" || a == "--compare") o.compare = true;
         else if (a == "-c" || a == "--compress") o.compress = true;
         else if (a == "-d" || a == "--decompress") o.decompress = true;
         else if (a == "--interleaved_in") o.interleaved = true;
@@ -157,7 +227,12 @@ int main(int argc, char** argv) {
         else if (a.compare(0, 9, "--device=") == 0) o.device = atoi(a.c_str() + 9);
         else error_exit("unsupported option for the B200 driver: " + a);
     }
-    if (o.compress && o.decompress) error_exit("repaq can run in compress/decompress/compare mode, you can only choose any one mode.");
+    if ((int)o.compress + (int)o.decompress + (int)o.compare > 1) error_exit("repaq can run in compress/decompress/compare mode, you can only choose any one mode.");
+    if (o.compare) {
+        if (o.in1.empty()) error_exit("Please specify input file by <in1>, or enable --stdin if you want to read STDIN");
+        if (o.rfq_compare.empty()) error_exit("In compare mode, you should specify the RFQ file to compare by <rfq_to_compare>");
+        return do_compare(o);
+    }
     if (!o.decompress) o.compress = true;                                   /* compress is the default mode */
     if (o.in1.empty()) { if (o.from_stdin) o.in1 = "/dev/stdin"; else error_exit("Please specify input file by <in1>, or enable --stdin if you want to read STDIN"); }
     if (o.out1.empty()) { if (o.to_stdout) o.out1 = "/dev/stdout"; else error_exit("Please specify output file by <out1>, or enable --stdout if you want to read STDIN"); }

@@ -19,6 +19,7 @@
 #include "rpq_decode.cuh"
 #include "rpq_decode2.cuh"
 #include "rpq_decode3.cuh"
+#include "rpq_compare.cuh"
 #include "rpq_host.h"
 
 using namespace rpq;
@@ -92,6 +93,7 @@ struct rpq_ctx {
     DevBuf pinned_tab;                     /* pinned host copy of the chunk table (k_fetch) */
     std::vector<rpq_chunk_info> infos;
     std::vector<ChunkDev> h_chunks;
+    DecBatchDev last_dec;                  /* tables and outputs of the last rpq_decode (rpq_compare reads them) */
     rpq_stats stats;
     RtEvent ev[8];
     uint32_t launches = 0;
@@ -182,6 +184,7 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     for (auto& e : c->ev) rt_event_create(&e);
     memset(&c->stats, 0, sizeof c->stats);
     memset(&c->hdr, 0, sizeof c->hdr);
+    memset(&c->last_dec, 0, sizeof c->last_dec);
     { const char* e = getenv("RPQ_DEBUG_FORCE_V1"); c->force_v1 = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_DEBUG_INDEX"); c->index_variant = e ? atoi(e) : 1; }
     { const char* e = getenv("RPQ_DEBUG_NO_STREAMS4"); c->no_streams4 = e && e[0] == '1'; }
@@ -295,7 +298,7 @@ int fetch_table(rpq_ctx* c, const void* dev, size_t bytes) {
     return RPQ_OK;
 }
 
-int index_text(rpq_ctx* c, int f, const u8* d_text, u64 len, IndexCounters* hc) {
+int index_text(rpq_ctx* c, int f, const u8* d_text, u64 len, IndexCounters* hc, bool eof) {
     const u32 tiles = (u32)((len + IDX_TILE - 1) / IDX_TILE);
     if (!ensure(c, c->tile_state, sizeof(u64) * (tiles + 1)) || !ensure(c, c->counters, sizeof(IndexCounters) * 2)) return RPQ_ERR_NOMEM;
     size_t cap = (size_t)(len / 16) + 4096;
@@ -307,7 +310,7 @@ int index_text(rpq_ctx* c, int f, const u8* d_text, u64 len, IndexCounters* hc) 
         rt_memset(dc, 0, sizeof(IndexCounters), c->stream);
         if (c->index_variant == 1) LAUNCH(c, k_index_lines_tilecta, tiles, IDX_THREADS, IDX_SMEM_TILECTA, d_text, len, c->nl[f].as<u32>(), (u32)cap, c->tile_state.as<u64>(), dc);
         else LAUNCH(c, k_index_lines, std::min<u32>(tiles, 3u * (u32)rt_sm_count()), IDX_THREADS, IDX_SMEM, d_text, len, c->nl[f].as<u32>(), (u32)cap, c->tile_state.as<u64>(), dc, tiles);
-        LAUNCH(c, k_index_finish, 1, 32, 0, d_text, len, c->nl[f].as<u32>(), (u32)cap, dc);
+        LAUNCH(c, k_index_finish, 1, 32, 0, d_text, len, c->nl[f].as<u32>(), (u32)cap, dc, eof ? 1 : 0);
         if (int rc = read_back(c, dc, hc)) return rc;
         if ((size_t)hc->n_nl + 1 <= cap) return RPQ_OK;
         cap = (size_t)hc->n_nl + 16;           /* pathological line density: index again with room for every line */
@@ -319,3 +322,4 @@ int index_text(rpq_ctx* c, int f, const u8* d_text, u64 len, IndexCounters* hc) 
 
 #include "rpq_api_encode.inc"
 #include "rpq_api_decode.inc"
+#include "rpq_api_compare.inc"

@@ -358,14 +358,16 @@ __global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines_tilecta(const u8
     }
 }
 
-/* line-end mode, the virtual final newline, line count */
-__global__ void k_index_finish(const u8* text, u64 len, u32* nl, u32 nl_cap, IndexCounters* ctr) {
+/* line-end mode, the virtual final newline, line count.  eof: the text ends where the input ends, so an unterminated last line
+ * is a line (FastqReader::getLine returns it, src/fastqreader.cpp:107-120); otherwise the text is a window of a longer input
+ * and the unterminated tail belongs to a record of the next window. */
+__global__ void k_index_finish(const u8* text, u64 len, u32* nl, u32 nl_cap, IndexCounters* ctr, int eof) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const u32 n = ctr->n_nl;
     u32 crlf = 0, bad = 0;
     if (ctr->n_cr) { crlf = 1; if (ctr->n_cr != ctr->n_crlf || ctr->n_crlf != n) bad = 1; }
     u32 lines = n;
-    if (len > 0 && text[len - 1] != '\n') {
+    if (eof && len > 0 && text[len - 1] != '\n') {
         if (n < nl_cap) nl[n] = (u32)len + crlf;       /* so that line_end() == len */
         lines = n + 1;
     }

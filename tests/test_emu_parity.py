@@ -4,6 +4,7 @@ same code is checked by tests/test_gpu_parity.py (-m gpu)."""
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 from repaq_b200 import codec as K
@@ -242,3 +243,39 @@ def test_unclean_bases(codec, tmp_path):
         assert O.compress(m1, None, chunk_bases=100000) == O.ref_compress(str(tmp_path), m1, None, chunk_kb=100)
     parity.check_against_oracle(codec, m1, m2, k=100, roundtrip=False)
     parity.check_against_oracle(codec, m1, k=100, roundtrip=False)
+
+
+def test_window_cut_inside_the_chunk_closing_record(codec):
+    """a batch that is not final and ends in the middle of the quality line of the very record that would close a chunk: the
+    unterminated tail is not a record (it belongs to the next batch), so the batch yields no chunk - it used to be indexed as a
+    record with a short quality line and rejected"""
+    from tools import fqgen
+    r1, _ = fqgen.generate(1200, seed=31)
+    h = K.make_header(r1, lib_path=codec.lib_path)
+    codec.set_header(h)
+    nl = np.flatnonzero(r1 == 10)
+    closing = 666                                              # -k 100, 150 bp: read 667 closes the chunk
+    cut = int(nl[4 * closing + 3]) - 40
+    data, infos, st = codec.encode(r1[:cut], chunk_bases=100000, final=False)
+    assert infos == [] and st["r1_consumed"] == 0
+    data, infos, st = codec.encode(r1[:cut + 41], chunk_bases=100000, final=False)     # the whole record: one chunk
+    assert len(infos) == 1 and st["r1_consumed"] == cut + 41
+    whole = K.compress(r1, k=100, codec=codec)
+    assert whole[len(K.header_bytes(h, codec.lib_path)):].startswith(data)
+
+
+def test_blank_lines(codec):
+    """the reference's getLine() swallows a '\\n' that directly follows a line break (src/fastqreader.cpp:113-116): a blank line
+    between records is invisible to it, one at the very end of the file is an empty line that ends the input.  The first is outside
+    the supported domain (refused, not silently truncated), the second behaves like the reference."""
+    from oracle import oracle as O
+    from tools import fqgen
+    r1, _ = fqgen.generate(300, seed=32)
+    b = bytes(r1)
+    nl = np.flatnonzero(r1 == 10)
+    at = int(nl[4 * 100 - 1]) + 1
+    with pytest.raises(K.RepaqError) as e:
+        K.compress(b[:at] + b"\n" + b[at:], k=100, codec=codec)
+    assert e.value.code == -4 and "blank line" in str(e.value)
+    for tail in (b"\n", b"\n\n"):
+        assert K.compress(b + tail, k=100, codec=codec) == O.compress(b + tail, chunk_bases=100000)

@@ -133,6 +133,12 @@ def test_persistent_indexer_variant(monkeypatch):
         cd.close()
 
 
+def test_window_cut_and_blank_lines(codec):
+    from tests import test_emu_parity as E
+    E.test_window_cut_inside_the_chunk_closing_record(codec)
+    E.test_blank_lines(codec)
+
+
 def test_library_really_ran_on_gpu(codec):
     s = codec.stats()
     assert s.launches > 0
