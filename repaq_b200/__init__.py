@@ -1,7 +1,7 @@
 """repaq_b200 - B200-native FASTQ <-> .rfq chunk codec (byte-identical to OpenGene/repaq v0.5.1).
 
 Python is only the binding: `Codec` mirrors the reference's RfqCodec surface (reference src/rfqcodec.h:17-43) and the
-two drivers `compress` / `decompress` mirror Repaq::compress* / decompress* (src/repaq.cpp) on in-memory files; the
+drivers `compress` / `decompress` / `compare` mirror Repaq::compress* / decompress* / compare* (src/repaq.cpp) on in-memory files; the
 work is done by the CUDA library behind the C ABI of include/repaq_b200.h.
 """
-from .codec import Codec, RepaqError, compress, decompress, make_header  # noqa: F401
+from .codec import Codec, RepaqError, compare, compress, decompress, make_header  # noqa: F401

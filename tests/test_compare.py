@@ -137,7 +137,9 @@ def test_gpu_compare_at_size(gpu_codec):
     r1, r2 = fqgen.generate(400000, seed=77, paired=True)
     rfq = K.compress(r1, r2, codec=gpu_codec)
     rep = json.loads(K.compare(rfq, r1, r2, codec=gpu_codec), strict=False)
-    assert rep == dict(result="passed", msg="", fastq_reads=800000, rfq_reads=800000, fastq_bases=120000000, rfq_bases=120000000)
+    n = 2 * (int(np.count_nonzero(r1 == 10)) // 4)            # the generator rounds the request up to whole rows of reads
+    assert n >= 800000
+    assert rep == dict(result="passed", msg="", fastq_reads=n, rfq_reads=n, fastq_bases=150 * n, rfq_bases=150 * n)
     p1, p2 = fqgen.truncate_reads(r1, 20000), fqgen.truncate_reads(r2, 20000)
     small = K.compress(p1, p2, codec=gpu_codec)
     assert K.compare(small, p1, p2, codec=gpu_codec) == O.compare(small, bytes(p1), bytes(p2))
