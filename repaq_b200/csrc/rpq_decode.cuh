@@ -140,10 +140,13 @@ __device__ __forceinline__ u32 dec_rlen(const DecBatchDev& b, const HeaderDev& h
     return ld32(p + 4 * k);
 }
 
-/* one CTA per chunk: lengths, exclusive scans (quality, compacted bases, name parts, output text per stream) */
+/* one CTA per chunk: lengths, exclusive scans (quality, compacted bases, name parts, output text per stream).  Seven running sums
+ * per read - but which of them can differ from read to read is a property of the chunk (its flags), so only those are scanned:
+ * a NovaSeq chunk (same read length, same name parts and strand) scans three.  One barrier per 256 reads: the warp totals go
+ * through a double-buffered table and every thread keeps the carries itself. */
 __global__ void __launch_bounds__(DR_THREADS) k_dec_reads(DecBatchDev b, HeaderDev h) {
-    __shared__ Scan7 s_warp[DR_THREADS / 32];
-    __shared__ Scan7 s_carry;
+    constexpr int NW = DR_THREADS / 32;
+    __shared__ u32 s_warp[2][NW][8];
     const u32 c = blockIdx.x;
     DecChunk& ck = b.chunks[c];
     const u8* in = b.body + ck.in_off;
@@ -152,13 +155,26 @@ __global__ void __launch_bounds__(DR_THREADS) k_dec_reads(DecBatchDev b, HeaderD
     const bool ov_on = il && (h.flags & RPQ_ENCODE_PE_BY_OVERLAP);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     u32 maxrec = 0, maxrl = 0;
-    if (tid == 0) { Scan7 z; for (int k = 0; k < 7; k++) z.v[k] = 0; s_carry = z; }
-    __syncthreads();
-    for (u32 base = 0; base < n; base += DR_THREADS) {
+    /* components: 0 read length, 1 kept bases, 2 name1, 3 name2, 4 strand, 5 / 6 record text of output stream 0 / 1 */
+    u32 need = 1u << 5;
+    if (!(fl & RPQ_READ_LEN_SAME)) need |= 1u << 0;
+    if (ov_on) need |= 1u << 1;
+    if (!(fl & RPQ_NAME1_SAME)) need |= 1u << 2;
+    if ((h.flags & RPQ_HAS_NAME2) && !(fl & RPQ_NAME2_SAME)) need |= 1u << 3;
+    if (!(fl & RPQ_STRAND_SAME)) need |= 1u << 4;
+    if (b.split_pairs) need |= 1u << 6;
+    const u32 rl_same = (fl & RPQ_READ_LEN_SAME) ? dec_rlen(b, h, ck, 0) : 0u;
+    u32 carry[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) carry[k] = 0;
+    u32 it = 0;
+    for (u32 base = 0; base < n; base += DR_THREADS, it ^= 1u) {
         const u32 r = base + tid;
-        Scan7 v; for (int k = 0; k < 7; k++) v.v[k] = 0;
+        u32 v[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) v[k] = 0;
         if (r < n) {
-            const u32 rl = dec_rlen(b, h, ck, r);
+            const u32 rl = (fl & RPQ_READ_LEN_SAME) ? rl_same : dec_rlen(b, h, ck, r);
             u32 kept = rl;
             if (ov_on && (r & 1u)) { int o = (int)(signed char)in[ck.off_ov + (r >> 1)] - (int)h.overlap_shift; u32 a = (u32)(o < 0 ? -o : o); kept = a <= rl ? rl - a : 0; }
             const u32 l1 = (fl & (RPQ_NAME1_SAME | RPQ_NAME1_LEN_SAME)) ? in[ck.off_n1len] : in[ck.off_n1len + r];
@@ -172,43 +188,60 @@ __global__ void __launch_bounds__(DR_THREADS) k_dec_reads(DecBatchDev b, HeaderD
             if (h.flags & RPQ_HAS_X) name += 1 + dec_digits(b.xs[ck.read_base + xy]);
             if (h.flags & RPQ_HAS_Y) name += 1 + dec_digits(b.ys[ck.read_base + xy]);
             const u32 text = name + 1 + rl + 1 + ls + 1 + rl + 1;          /* Read::toString */
-            v.v[0] = rl; v.v[1] = kept;
-            v.v[2] = (fl & RPQ_NAME1_SAME) ? 0u : l1; v.v[3] = (fl & RPQ_NAME2_SAME) ? 0u : l2; v.v[4] = (fl & RPQ_STRAND_SAME) ? 0u : ls;
+            v[0] = rl; v[1] = kept;
+            v[2] = (fl & RPQ_NAME1_SAME) ? 0u : l1; v[3] = (fl & RPQ_NAME2_SAME) ? 0u : l2; v[4] = (fl & RPQ_STRAND_SAME) ? 0u : ls;
             const u32 stream = b.split_pairs ? (r & 1u) : 0u;
-            v.v[5 + stream] = text;
+            v[5 + stream] = text;
             b.rlen[ck.read_base + r] = rl;
             b.olen[ck.read_base + r] = text;
             b.read_chunk[ck.read_base + r] = c;
             if (text > maxrec) maxrec = text;
             if (rl > maxrl) maxrl = rl;
         }
-        Scan7 inc = v;
+        u32 inc[7];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
+        for (int k = 0; k < 7; k++) {
+            inc[k] = v[k];
+            if ((need >> k) & 1u) {                              /* uniform over the CTA */
 #pragma unroll
-            for (int k = 0; k < 7; k++) { const u32 t = __shfl_up_sync(0xffffffffu, inc.v[k], d); if (lane >= d) inc.v[k] += t; }
+                for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, inc[k], d); if (lane >= d) inc[k] += t; }
+                if (lane == 31) s_warp[it][warp][k] = inc[k];
+            }
         }
-        if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
-        Scan7 pre = s_carry;
-        for (int q = 0; q < warp; q++) for (int k = 0; k < 7; k++) pre.v[k] += s_warp[q].v[k];
+        u32 pre[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            pre[k] = carry[k];
+            if ((need >> k) & 1u) {
+                u32 tot = 0;
+#pragma unroll
+                for (int q = 0; q < NW; q++) { const u32 t = s_warp[it][q][k]; if (q < warp) pre[k] += t; tot += t; }
+                carry[k] += tot;
+            }
+        }
         if (r < n) {
             const u32 i = ck.read_base + r;
-            b.qualoff[i] = pre.v[0] + inc.v[0] - v.v[0];
-            b.seqoff[i] = pre.v[1] + inc.v[1] - v.v[1];
-            b.n1off[i] = pre.v[2] + inc.v[2] - v.v[2];
-            b.n2off[i] = pre.v[3] + inc.v[3] - v.v[3];
-            b.soff[i] = pre.v[4] + inc.v[4] - v.v[4];
+            const u32 qo = (need & 1u) ? pre[0] + inc[0] - v[0] : r * rl_same;
+            b.qualoff[i] = qo;
+            b.seqoff[i] = (need & 2u) ? pre[1] + inc[1] - v[1] : qo;
+            b.n1off[i] = pre[2] + inc[2] - v[2];
+            b.n2off[i] = pre[3] + inc[3] - v[3];
+            b.soff[i] = pre[4] + inc[4] - v[4];
             const u32 stream = b.split_pairs ? (r & 1u) : 0u;
-            b.outoff[i] = pre.v[5 + stream] + inc.v[5 + stream] - v.v[5 + stream];
+            b.outoff[i] = pre[5 + stream] + inc[5 + stream] - v[5 + stream];
         }
-        __syncthreads();
-        if (tid == 0) { Scan7 t = s_carry; for (int q = 0; q < DR_THREADS / 32; q++) for (int k = 0; k < 7; k++) t.v[k] += s_warp[q].v[k]; s_carry = t; }
-        __syncthreads();
     }
-    if (tid == 0) { ck.total_len = s_carry.v[0]; ck.seq_kept = s_carry.v[1]; ck.out_bytes[0] = s_carry.v[5]; ck.out_bytes[1] = s_carry.v[6]; }
+    if (tid == 0) {
+        const u32 total = (need & 1u) ? carry[0] : n * rl_same;
+        ck.total_len = total; ck.seq_kept = (need & 2u) ? carry[1] : total; ck.out_bytes[0] = carry[5]; ck.out_bytes[1] = carry[6];
+    }
     maxrec = warp_max(maxrec); maxrl = warp_max(maxrl);
-    if (lane == 0) { atomicMax(reinterpret_cast<u32*>(b.totals + 4), maxrec); atomicMax(reinterpret_cast<u32*>(b.totals + 4) + 1, maxrl); }
+    if (lane == 0) {
+        u32* mx = reinterpret_cast<u32*>(b.totals + 4);
+        if (maxrec > ((volatile u32*)mx)[0]) atomicMax(mx, maxrec);
+        if (maxrl > ((volatile u32*)mx)[1]) atomicMax(mx + 1, maxrl);
+    }
 }
 
 /* prefix over chunks: plane, N bitmap and output offsets; totals for the host */

@@ -261,6 +261,11 @@ __global__ void __launch_bounds__(256) k_dec_format3(DecBatchDev b, HeaderDev h,
             for (u32 jo = need + 4u * nw; jo < rl; jo++) o_seq[jo] = slow_base(jo);
         }
     }
+    /* ---- the records leave shared memory: the 16-byte aligned body of each output stream as ONE TMA bulk store (shared ->
+     * global, issued by one thread; `UBLKCP` in SASS), the few bytes before and after it with plain stores */
+#ifndef RPQ_EMU
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        /* this thread's shared stores, visible to the bulk copy engine */
+#endif
     __syncthreads();
     for (u32 s = 0; s < nstreams; s++) {
         const u64 a = s_start[s], e = s_end[s];
@@ -271,12 +276,23 @@ __global__ void __launch_bounds__(256) k_dec_format3(DecBatchDev b, HeaderDev h,
         const u64 v0 = (a + 15) & ~15ull, v1 = e & ~15ull;
         if (v0 >= v1) { for (u64 p = a + tid; p < e; p += blockDim.x) g[p] = sm[p - base]; continue; }
         for (u64 p = a + tid; p < v0; p += blockDim.x) g[p] = sm[p - base];
+#ifdef RPQ_EMU
         const u32 nvec = (u32)((v1 - v0) >> 4);
         uint4* gd = reinterpret_cast<uint4*>(g + v0);
         const uint4* sd = reinterpret_cast<const uint4*>(sm + (v0 - base));
         for (u32 k = tid; k < nvec; k += blockDim.x) gd[k] = sd[k];
+#else
+        if (tid == (int)(32u * s)) {                                    /* one thread per stream, in different warps */
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(g + v0), "r"((u32)__cvta_generic_to_shared(sm + (v0 - base))), "r"((u32)(v1 - v0)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+#endif
         for (u64 p = v1 + tid; p < e; p += blockDim.x) g[p] = sm[p - base];
     }
+#ifndef RPQ_EMU
+    if (tid == 0 || tid == 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    /* shared memory must outlive the reads of the copy */
+#endif
 }
 
 }  // namespace rpq

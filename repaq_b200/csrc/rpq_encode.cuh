@@ -1048,7 +1048,9 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) k_raw_qual(EncBatchDev b, u8*
     else for (u32 k = lane; k < rl; k += 32) d[k] = q[k];
 }
 
-/* pieces of the span slots -> final position; one CTA per span; also the stream length table */
+/* pieces of the span slots -> final position; one small CTA (64 threads) per span: a span's pieces are a few hundred bytes
+ * behind a chain of four dependent loads, so the kernel lives on how many spans are in flight (32 CTAs per SM), not on threads
+ * per span; also the stream length table */
 __global__ void __launch_bounds__(256) k_gather(EncBatchDev b, StreamJob job, const u32* __restrict__ span_chunk, u8* out, int is_npos) {
     const u32 span = blockIdx.x;
     if (span >= *job.n_spans) return;

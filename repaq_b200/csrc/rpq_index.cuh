@@ -417,25 +417,35 @@ __global__ void k_unit_lengths(EncBatchDev b, u32 n_units, u32* __restrict__ rle
         }
         unit_bases[u] = bases;
     }
-    /* one atomic per warp and statistic */
+    /* one request per CTA and statistic: all CTAs update the same eight words, so even a filtering load per warp queues up at one
+     * L2 slice (1.2 M requests per 3.4 GB batch).  Warp reduce, shared-memory atomics, then eight threads compare with the word in
+     * memory and only issue a global atomic that would change it (on uniform reads only the first CTAs do). */
+    __shared__ u32 s_stat[8];
     const u32 FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 8) s_stat[threadIdx.x] = threadIdx.x < 5 ? 0xFFFFFFFFu : 0u;
+    __syncthreads();
     const u32 w_empty = __reduce_min_sync(FULL, empty ? u : 0xFFFFFFFFu), w_badq = __reduce_min_sync(FULL, badq ? u : 0xFFFFFFFFu);
     const u32 w_badn = __reduce_min_sync(FULL, badn ? u : 0xFFFFFFFFu), w_badl = __reduce_min_sync(FULL, badl ? u : 0xFFFFFFFFu);
     const u32 w_min = __reduce_min_sync(FULL, live ? bases : 0xFFFFFFFFu), w_max = __reduce_max_sync(FULL, bases);
     const u32 w_long = __reduce_max_sync(FULL, longest), w_head = __reduce_max_sync(FULL, head);
     if (lane == 0) {
-        /* an atomic only when it would change the value: all warps update the same eight words, and on uniform reads
-         * (the common case) every warp but the first few would queue up at L2 for nothing */
-        volatile UnitStats* vs = st;
-        if (w_empty < vs->first_empty) atomicMin(&st->first_empty, w_empty);
-        if (w_badq < vs->first_qual_len) atomicMin(&st->first_qual_len, w_badq);
-        if (w_badn < vs->first_name_len) atomicMin(&st->first_name_len, w_badn);
-        if (w_badl < vs->first_read_len) atomicMin(&st->first_read_len, w_badl);
-        if (w_min < vs->min_bases) atomicMin(&st->min_bases, w_min);
-        if (w_max > vs->max_bases) atomicMax(&st->max_bases, w_max);
-        if (w_long > vs->max_read) atomicMax(&st->max_read, w_long);
-        if (w_head > vs->max_head) atomicMax(&st->max_head, w_head);
+        if (w_empty != 0xFFFFFFFFu) atomicMin(&s_stat[0], w_empty);
+        if (w_badq != 0xFFFFFFFFu) atomicMin(&s_stat[1], w_badq);
+        if (w_badn != 0xFFFFFFFFu) atomicMin(&s_stat[2], w_badn);
+        if (w_badl != 0xFFFFFFFFu) atomicMin(&s_stat[3], w_badl);
+        atomicMin(&s_stat[4], w_min);
+        atomicMax(&s_stat[5], w_max);
+        atomicMax(&s_stat[6], w_long);
+        atomicMax(&s_stat[7], w_head);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        /* UnitStats starts with first_empty, first_qual_len, first_name_len, first_read_len, min_bases, max_bases, max_read, max_head */
+        u32* word = reinterpret_cast<u32*>(st) + threadIdx.x;
+        const u32 v = s_stat[threadIdx.x], cur = *reinterpret_cast<volatile u32*>(word);
+        if (threadIdx.x < 5) { if (v < cur) atomicMin(word, v); }
+        else if (v > cur) atomicMax(word, v);
     }
 }
 

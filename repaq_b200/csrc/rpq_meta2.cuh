@@ -162,6 +162,13 @@ __device__ __forceinline__ u32 packed_window(const u32* src, u32 j0, u32 pkw) {
 __global__ void __launch_bounds__(256) k_emit2(EncBatchDev b, HeaderDev h, u8* out) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= b.n_reads) return;
+#ifndef RPQ_EMU
+    {   /* the read's packed words (two or three sectors) are on their way while the chunk and per-read tables are fetched */
+        const char* row = reinterpret_cast<const char*>(b.pk + (size_t)i * b.pkw);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 4 * b.pkw - 4));
+    }
+#endif
     const u32 c = chunk_of_read(b, i);
     const ChunkDev& ck = b.chunks[c];
     const u32 rel = i - ck.first;
