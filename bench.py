@@ -417,6 +417,14 @@ def main():
         "k_dec_coords3": (1 + 8) * n_reads, "k_dec_reads": 48 * n_reads, "k_chunk_finish": 44 * n_reads,
         "k_coords": 9 * n_reads,
     }
+    # DRAM bytes per launch from the committed ncu launch list of this workload (profiles/r01_traffic.json, tools/ncu_traffic.py)
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if int(tj.get("pairs_per_gpu", 0)) == rows * fqgen.ROW_READS:
+            traffic = {k: v["traffic_bytes_per_launch"] for k, v in tj["kernels"].items()}
+    except Exception:
+        pass
     kern_total = sum(ms for _, ms in prof.values())
     top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
     roofline = None
@@ -424,7 +432,8 @@ def main():
         name, (n, ms) = top
         ab = float(alg.get(name, fastq_bytes))
         ach = ab / 1e9 / (ms / n / 1e3)
-        roofline = dict(bound="hbm", kernel=name, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None, peak_source=peak_src,
+        roofline = dict(bound="hbm", kernel=name, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic.get(name), peak_source=peak_src,
+                        traffic_source="profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu capture of this workload" if name in traffic else None,
                         share_of_kernel_time=ms / kern_total, algorithmic_bytes_per_launch=ab,
                         pipeline=dict(achieved=(fastq_bytes + rfq_b) * 2 / 1e9 / (kern_total / 1e3), frac=(fastq_bytes + rfq_b) * 2 / 1e9 / (kern_total / 1e3) / peak,
                                       note="whole encode+decode: (F+R)+(R+F) algorithmic bytes over the sum of all kernel times"),

@@ -31,6 +31,16 @@ namespace rpq {
 __global__ void __launch_bounds__(256) k_fetch(const u32* __restrict__ src, u32* __restrict__ dst, u32 nwords) {
     for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < nwords; k += gridDim.x * blockDim.x) dst[k] = src[k];
 }
+/* Fill with a byte by a FEW CTAs (16-byte stores): the decoder's quality plane is filled under the chunk walk, a single warp
+ * chasing one header per chunk; a copy-engine memset at full HBM speed next to it made every hop of that chain wait in the memory
+ * queues (0.68 -> 1.14 ms, profiles/README.md r01_v10), a fill that takes a fraction of the bandwidth does not. */
+__global__ void __launch_bounds__(256) k_fill(uint4* __restrict__ dst, unsigned long long n16, u32 v4) {
+    const uint4 v = make_uint4(v4, v4, v4, v4);
+    const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; k + 3 * nthreads < n16; k += 4 * nthreads) { dst[k] = v; dst[k + nthreads] = v; dst[k + 2 * nthreads] = v; dst[k + 3 * nthreads] = v; }
+    for (; k < n16; k += nthreads) dst[k] = v;
+}
 /* Optional (RPQ_D2H=sm): bulk results leave the same way, a few CTAs streaming 16-byte stores over PCIe (posted writes,
  * 512 contiguous bytes per warp instruction), so that the copy engines only carry host-to-device traffic.  Measured beside an
  * encoder it is slower than the copy engine with one window queued at a time (28.3 against 30.7 GB/s end to end,
@@ -81,6 +91,7 @@ struct rpq_ctx {
     bool force_v1 = false;                 /* RPQ_DEBUG_FORCE_V1=1: take the long-read fallback kernels (test coverage) */
     bool d2h_sm = false;                   /* RPQ_D2H=sm: bulk results leave through k_push (SM stores) instead of the copy engines; measured slower (profiles/README.md r01_v9) */
     u32 push_ctas = 32;                    /* RPQ_PUSH_CTAS=n */
+    u32 fill_ctas = 64;                    /* RPQ_FILL_CTAS=n: CTAs of the plane fill that runs under the chunk walk (0: copy-engine memset after the tables) */
     u32 d2h_depth = 1;                     /* RPQ_D2H_DEPTH=n: windows of decoded FASTQ whose copies may be queued at a time (0: wait for each) */
     bool no_pipeline = false;              /* RPQ_NO_PIPELINE=1: host batches are never cut into pipelined windows */
     uint64_t pipe_window = 0;              /* RPQ_DEBUG_PIPE_WINDOW=<bytes>: window size of the pipelined host path (tests) */
@@ -195,6 +206,7 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     { const char* e = getenv("RPQ_NO_PIPELINE"); c->no_pipeline = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_D2H"); c->d2h_sm = e && e[0] == 's'; }
     { const char* e = getenv("RPQ_D2H_DEPTH"); if (e) c->d2h_depth = (u32)atoi(e) > 8u ? 8u : (u32)atoi(e); }
+    { const char* e = getenv("RPQ_FILL_CTAS"); if (e) c->fill_ctas = (u32)atoi(e); }
     { const char* e = getenv("RPQ_PUSH_CTAS"); if (e && atoi(e) > 0) c->push_ctas = (u32)atoi(e); }
     { const char* e = getenv("RPQ_DEBUG_PIPE_WINDOW"); c->pipe_window = e ? strtoull(e, nullptr, 10) : 0; }
 #ifndef RPQ_EMU

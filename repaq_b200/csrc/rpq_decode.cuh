@@ -98,7 +98,7 @@ __global__ void k_dec_walk(const u8* body, u64 len, HeaderDev h, DecChunk* chunk
         if (lane == 0) chunks[n] = c;
         n++; read_base += nr; at += o;
     }
-    if (lane == 0) { *n_out = n; *consumed = at; (void)err; }
+    if (lane == 0) { n_out[0] = n; n_out[1] = read_base; *consumed = at; (void)err; }      /* chunks, reads, body bytes */
 }
 
 /* ------------------------------------------------------------------ coordinates ---- */

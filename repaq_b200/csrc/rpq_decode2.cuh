@@ -145,7 +145,7 @@ __global__ void k_dec_walk_fast(const u8* body, u64 len, HeaderDev h, DecChunk* 
         }
         n++; read_base += reads; at += (u64)bytes;
     }
-    if (lane == 0) { *n_out = n; *consumed = at; }
+    if (lane == 0) { n_out[0] = n; n_out[1] = read_base; *consumed = at; }                 /* chunks, reads, body bytes */
 }
 
 __global__ void __launch_bounds__(128) k_dec_describe(const u8* body, HeaderDev h, DecChunk* chunks, u32 n_chunks, u32* mismatch) {

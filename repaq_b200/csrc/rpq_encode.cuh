@@ -856,7 +856,7 @@ __global__ void __launch_bounds__(256) k_chunk_offsets(EncBatchDev b, u64* total
         if (tid == 0) { u64 t = s_carry; for (int q = 0; q < 8; q++) t += s_w[q]; s_carry = t; }
         __syncthreads();
     }
-    if (tid == 0) *total = s_carry;
+    if (tid == 0) { total[0] = s_carry; total[1] = *b.err; }     /* the error bits ride along: one read-back for the host */
 }
 
 /* spans of every chunk for one stream kind; one CTA.  span_chunk has room for the host's upper bound. */

@@ -385,6 +385,7 @@ struct UnitStats {
     u32 max_head;         /* most bytes from the start of a name line to the start of the quality line */
     u32 n_chunks;         /* written by k_cut */
     u32 units_in_chunks;  /* units covered by the emitted chunks */
+    u32 end[2];           /* written by k_cut_ends: offset of the line break that ends the last covered record, per file */
 };
 
 __global__ void k_unit_lengths(EncBatchDev b, u32 n_units, u32* __restrict__ rlen, u32* __restrict__ unit_bases, UnitStats* st) {
@@ -499,6 +500,17 @@ __global__ void k_cut(const u64* __restrict__ prefix, u32 n_units, u32 chunk_bas
     u32 covered = cur;
     if (final && cur < n_units) { n++; covered = n_units; if (lane == 0 && n < cap) chunk_first[n] = n_units * per; }
     if (lane == 0) { st->n_chunks = n; st->units_in_chunks = covered; }
+}
+
+/* where the text covered by the chunks ends (one launch behind k_cut, so that the host reads everything back at once) */
+__global__ void k_cut_ends(UnitStats* st, const u32* __restrict__ nl0, const u32* __restrict__ nl1, int two, int pe) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    st->end[0] = st->end[1] = 0;
+    if (st->units_in_chunks == 0) return;
+    const u32 last_unit = st->units_in_chunks - 1;
+    const u32 rec0 = two ? last_unit : (pe ? 2 * last_unit + 1 : last_unit);
+    st->end[0] = nl0[4ull * rec0 + 3];
+    if (two) st->end[1] = nl1[4ull * last_unit + 3];
 }
 
 }  // namespace rpq

@@ -8,8 +8,9 @@ mkdir -p gpurun_out
 WANT=$(cat $(ls repaq_b200/csrc/*.cu repaq_b200/csrc/*.cuh repaq_b200/csrc/*.h repaq_b200/csrc/*.inc repaq_b200/csrc/*.cpp include/repaq_b200.h | sort) | sha1sum | cut -c1-40)
 if [ "$WANT" != "$(cat repaq_b200/.build_stamp 2>/dev/null)" ]; then echo "STALE BUILD"; exit 9; fi
 echo "== bench (device only)"; timeout 600 python bench.py --no-e2e --no-cpu > gpurun_out/bench_dev.log 2>&1; echo "rc=$?"; tail -c 1500 gpurun_out/bench_dev.log
-# launches of our kernels before the timed step: gate step + 3 warm-up steps; STEP_LAUNCHES per step
-SKIP=${SKIP:-108}; CNT=${CNT:-30}
+# ~45 launches of our kernels per step (k_fetch read-backs included); the window below holds at least one whole step after the
+# gate step and two warm-up steps (tools/ncu_traffic.py cuts one step out of it)
+SKIP=${SKIP:-130}; CNT=${CNT:-110}
 echo "== ncu dram counters, full size"
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:^k_ -s $SKIP -c $CNT --csv --log-file gpurun_out/traffic_full.csv \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-roofline > gpurun_out/ncu_traffic.log 2>&1; echo "rc=$?"
