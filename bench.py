@@ -299,7 +299,7 @@ def main():
         se = enc.stats()
         do = dec.decode_raw(eo.data, eo.bytes, 1, True, 1)
         sd = dec.stats()
-        state.update(rfq_bytes=int(eo.bytes), n_chunks=int(eo.n_chunks), eo=eo, do=do, out=(int(do.out1_bytes), int(do.out2_bytes)))
+        state.update(rfq_bytes=int(eo.bytes), n_chunks=int(eo.n_chunks), eo=eo, do=do, out=(int(do.out1_bytes), int(do.out2_bytes)), dec_walk=int(sd.dec_walk))
         return se.ms_total, sd.ms_total, se.launches + sd.launches, eo
 
     def gather_lengths(eo):
@@ -557,7 +557,8 @@ def main():
                                 l2="inputs (GBs) far larger than the 126 MB L2; no flush needed", generator="tools/fqgen.c seed 2", gen_seconds=round(gen_s, 1),
                                 parallelism="chunk-sharded, one process per GPU; NCCL all_gather of per-chunk lengths only"),
                     encode_gbs=job_bytes * args.steps / 1e9 / (enc_ms / 1e3), decode_gbs=job_bytes * args.steps / 1e9 / (dec_ms / 1e3),
-                    wall_ms_per_step=wall_ms / args.steps, gpu_launches=int(launches), clocks=clk, e2e=e2e, roofline=roofline, cpu_baseline=cpu)
+                    wall_ms_per_step=wall_ms / args.steps, gpu_launches=int(launches),
+                    decode_chunk_walk={1: "one warp on the mSize chain", 2: "16 warps on the mSize chain (k_dec_walk_par)", 3: "exact sequential walk"}.get(state.get("dec_walk"), "host"), clocks=clk, e2e=e2e, roofline=roofline, cpu_baseline=cpu)
         print(json.dumps(line))
     enc.close()
     dec.close()

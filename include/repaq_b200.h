@@ -198,6 +198,8 @@ typedef struct rpq_stats {
     float ms_kernels;        /* same window with host<->device copies excluded */
     float ms_h2d, ms_d2h;
     uint64_t h2d_bytes, d2h_bytes;
+    uint32_t dec_walk;       /* rpq_decode of a device-resident body: 1 chain on mSize by one warp, 2 by several warps (k_dec_walk_par),
+                                3 exact sequential walk (forced, or the fast chain did not check out); 0 host walk / no decode */
 } rpq_stats;
 int rpq_get_stats(const rpq_ctx* ctx, rpq_stats* out);
 /* per-kernel device time: after rpq_set_profiling(ctx, 1) every launch is bracketed by a CUDA event pair;

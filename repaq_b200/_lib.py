@@ -59,7 +59,7 @@ class CompareOut(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("launches", C.c_uint32), ("ms_total", C.c_float), ("ms_kernels", C.c_float), ("ms_h2d", C.c_float),
-                ("ms_d2h", C.c_float), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("ms_d2h", C.c_float), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("dec_walk", C.c_uint32)]
 
 
 EXPORTS = ["rpq_make_header", "rpq_header_write", "rpq_header_read", "rpq_create", "rpq_destroy", "rpq_last_error",

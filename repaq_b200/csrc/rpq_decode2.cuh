@@ -148,6 +148,139 @@ __global__ void k_dec_walk_fast(const u8* body, u64 len, HeaderDev h, DecChunk* 
     if (lane == 0) { n_out[0] = n; n_out[1] = read_base; *consumed = at; }                 /* chunks, reads, body bytes */
 }
 
+/*
+ * The same chain followed by several warps at once.  The chain itself cannot be entered in the middle - but a place where a chunk
+ * header starts can be recognised: k_dec_find_heads scans forward from W-1 evenly spaced anchors for the first offset whose header
+ * fields are consistent with the container AND whose mSize leads to another such header (or to the end of the body).  Warp w of
+ * k_dec_walk_par then follows the chain from its start to the start of the next warp.  A start that is not on the real chain is
+ * harmless: the warp before it does not land on it, the stitch test fails and the host takes the sequential walk, exactly as it
+ * does when k_dec_describe finds a chunk whose columns do not add up.  1430 hops of ~0.5 us become 16 x 90.
+ */
+constexpr int WP_WARPS = 16;
+constexpr u32 WP_SLAB = 1u << 16;                 /* chunks a warp can record */
+constexpr u32 WP_NONE = 0xFFFFFFFFu;
+struct WalkSeg { u64 in_off; u32 reads, flags, bytes, read_base; };
+
+/* the walk's one-load header test at body offset p: 0 if the bytes there cannot be a chunk header, else the chunk's size */
+__device__ __forceinline__ u64 wp_header_bytes(const u8* body, u64 len, const HeaderDev& h, u64 p, u32 head, u32& reads, u32& fl) {
+    if (p + head > len) return 0;
+    const u8* in = body + p;
+    const u32 ms = ld32(in);
+    reads = ld32(in + 4); fl = (u32)in[8] | ((u32)in[9] << 8);
+    if (reads == 0) return 0;
+    const u32 xy = (fl & RPQ_PE_INTERLEAVED) ? reads / 2 : reads;
+    long long bytes = (long long)ms;
+    if (h.flags & RPQ_HAS_LANE) bytes += (fl & RPQ_LANE_SAME) ? 1 : xy;
+    if (!(h.flags & RPQ_HAS_NAME2)) bytes -= (fl & RPQ_NAME2_LEN_SAME) ? 1 : reads;
+    if (!(h.flags & RPQ_HAS_TILE)) bytes -= 2ll * ((fl & RPQ_TILE_SAME) ? 1 : xy);
+    if (bytes < (long long)head || p + (u64)bytes > len) return 0;
+    return (u64)bytes;
+}
+
+/* grid = WP_WARPS - 1 CTAs: CTA j looks for the start of warp j + 1 */
+__global__ void __launch_bounds__(256) k_dec_find_heads(const u8* body, u64 len, HeaderDev h, u64* starts) {
+    __shared__ u32 s_best;
+    const u32 w = blockIdx.x + 1;
+    const u32 head = 18u + ((h.flags & RPQ_ENCODE_N_POS) ? 4u : 0u);
+    const u64 anchor = len / WP_WARPS * w;
+    u64 window = len - anchor; if (window > (8ull << 20)) window = 8ull << 20;       /* chunks are 0.1 .. 2 MB at the usual -k */
+    if (threadIdx.x == 0) { s_best = WP_NONE; starts[w] = ~0ull; }
+    __syncthreads();
+    for (u64 base = 0; base < window; base += 8 * blockDim.x) {
+#ifndef RPQ_EMU
+        {   /* the lines of the rounds to come are on their way to L2 (every round would otherwise wait for DRAM) */
+            const u64 q = anchor + base + 16ull * 8 * blockDim.x + 128ull * threadIdx.x;
+            if (threadIdx.x < 8u * blockDim.x / 128u + 1u && q + 128 <= len) asm volatile("prefetch.global.L2 [%0];" ::"l"(body + q));
+            if (base == 0) for (u64 k = 128ull * threadIdx.x; k < 16ull * 8 * blockDim.x; k += 128ull * blockDim.x) if (anchor + k + 128 <= len) asm volatile("prefetch.global.L2 [%0];" ::"l"(body + anchor + k));
+        }
+#endif
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const u64 rel = base + (u64)k * blockDim.x + threadIdx.x;
+            if (rel >= window) continue;
+            const u64 p = anchor + rel;
+            const u8* in = body + p;
+            /* cheap rejections first: 12 flag bits, a read count and column sizes that fit the size the header claims */
+            if (p + head > len || (in[9] & 0xF0u)) continue;
+            u32 reads, fl;
+            const u64 bytes = wp_header_bytes(body, len, h, p, head, reads, fl);
+            if (!bytes || reads > (1u << 26)) continue;
+            const u64 seq = ld32(in + 10), qual = ld32(in + 14);
+            if (seq + qual + head > bytes || seq > 4ull * reads * 65536ull) continue;
+            u32 r2, f2;
+            if (p + bytes != len && !wp_header_bytes(body, len, h, p + bytes, head, r2, f2)) continue;
+            atomicMin(&s_best, (u32)rel);
+        }
+        __syncthreads();
+        const u32 best = s_best;
+        __syncthreads();                             /* nobody updates s_best for the next round before everybody has read it */
+        if (best != WP_NONE) break;                  /* the earliest hit of the earliest round with a hit */
+    }
+    if (threadIdx.x == 0 && s_best != WP_NONE) starts[w] = anchor + s_best;
+}
+
+/* one CTA of WP_WARPS warps.  out: u32[0] chunks, u32[1] reads, u64[1] body bytes covered (as the sequential walks), mismatch |= 1
+ * when the pieces do not fit together */
+__global__ void __launch_bounds__(32 * WP_WARPS) k_dec_walk_par(const u8* body, u64 len, HeaderDev h, const u64* __restrict__ starts, WalkSeg* slabs,
+                                                                DecChunk* chunks, u32 cap, u32* n_out, u64* consumed, u32* mismatch) {
+    __shared__ u64 s_from[WP_WARPS], s_stop[WP_WARPS], s_end[WP_WARPS];
+    __shared__ u32 s_n[WP_WARPS], s_reads[WP_WARPS], s_use[WP_WARPS];
+    __shared__ u32 s_nbase[WP_WARPS], s_rbase[WP_WARPS];
+    __shared__ u32 s_bad;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u32 head = 18u + ((h.flags & RPQ_ENCODE_N_POS) ? 4u : 0u);
+    if (threadIdx.x == 0) s_bad = 0;
+    /* this warp's piece of the chain: from its start to the next start that exists */
+    u64 from = w == 0 ? 0ull : starts[w];
+    u64 stop = len;
+    for (int j = WP_WARPS - 1; j > w; j--) { const u64 sj = starts[j]; if (sj != ~0ull) stop = sj; }
+    const bool active = from != ~0ull;
+    WalkSeg* slab = slabs + (size_t)w * WP_SLAB;
+    u64 at = active ? from : 0ull; u32 n = 0, reads_sum = 0;
+    bool overflow = false;
+    while (active && at < stop) {
+        u32 reads, fl;
+        const u64 bytes = wp_header_bytes(body, len, h, at, head, reads, fl);
+        if (!bytes) break;                              /* the chain ends here: what follows is not a chunk */
+        if (n >= WP_SLAB) { overflow = true; break; }
+#ifndef RPQ_EMU
+        {
+            const long long pf = (long long)at + 3ll * (long long)bytes + ((long long)lane - 16) * 512;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const long long q = pf + 128 * k; if (q >= 0 && (u64)q + 128 <= len) asm volatile("prefetch.global.L2 [%0];" ::"l"(body + q)); }
+        }
+#endif
+        if (lane == 0) { WalkSeg g; g.in_off = at; g.reads = reads; g.flags = fl; g.bytes = (u32)bytes; g.read_base = reads_sum; slab[n] = g; }
+        n++; reads_sum += reads; at += bytes;
+    }
+    if (lane == 0) { s_from[w] = from; s_stop[w] = stop; s_end[w] = at; s_n[w] = n; s_reads[w] = reads_sum; s_use[w] = 0; if (overflow) s_bad = 1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        /* stitch: every piece must end exactly where the next one starts; a piece that stops short ends the chain (as the
+         * sequential walk would), one that overshoots was aimed at a start that is not a chunk header */
+        u32 nb = 0, rb = 0; u64 end = 0; bool open = true;
+        for (int j = 0; j < WP_WARPS && open; j++) {
+            if (s_from[j] == ~0ull) continue;
+            s_use[j] = 1; s_nbase[j] = nb; s_rbase[j] = rb;
+            nb += s_n[j]; rb += s_reads[j]; end = s_end[j];
+            if (s_end[j] > s_stop[j]) { s_bad = 1; open = false; }
+            else if (s_end[j] < s_stop[j]) open = false;
+        }
+        if (nb > cap) s_bad = 1;
+        n_out[0] = nb; n_out[1] = rb; *consumed = end;
+        if (s_bad) atomicOr(mismatch, 1u);
+    }
+    __syncthreads();
+    if (s_bad || !s_use[w]) return;
+    const u32 nb = s_nbase[w], rb = s_rbase[w];
+    for (u32 k = lane; k < n; k += 32) {
+        const WalkSeg g = slab[k];
+        DecChunk c; memset(&c, 0, sizeof c);
+        c.in_off = g.in_off; c.reads = g.reads; c.flags = g.flags; c.bytes = g.bytes; c.read_base = rb + g.read_base;
+        chunks[nb + k] = c;
+    }
+}
+
 __global__ void __launch_bounds__(128) k_dec_describe(const u8* body, HeaderDev h, DecChunk* chunks, u32 n_chunks, u32* mismatch) {
     const int lane = threadIdx.x & 31;
     const u32 ci = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

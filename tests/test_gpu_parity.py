@@ -133,6 +133,12 @@ def test_persistent_indexer_variant(monkeypatch):
         cd.close()
 
 
+def test_parallel_chunk_walk(monkeypatch):
+    from tests import test_emu_parity as E
+    monkeypatch.setattr(E, "EMU", None)                      # the product library
+    E.test_parallel_chunk_walk(monkeypatch)
+
+
 def test_window_cut_and_blank_lines(codec):
     from tests import test_emu_parity as E
     E.test_window_cut_inside_the_chunk_closing_record(codec)
