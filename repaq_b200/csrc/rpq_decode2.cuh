@@ -177,51 +177,38 @@ __device__ __forceinline__ u64 wp_header_bytes(const u8* body, u64 len, const He
     return (u64)bytes;
 }
 
-/* grid = WP_WARPS - 1 CTAs: CTA j looks for the start of warp j + 1 */
-__global__ void __launch_bounds__(256) k_dec_find_heads(const u8* body, u64 len, HeaderDev h, u64* starts) {
-    __shared__ u32 s_best;
-    const u32 w = blockIdx.x + 1;
+/* grid (WP_FIND_CTAS, WP_WARPS - 1): the CTAs of row j look for the start of warp j + 1, the first header at or after its anchor,
+ * each in its own 16 KiB of a 1 MiB window, all at once; starts[] is preset to ~0 and takes the minimum.  No header in the
+ * window (chunks of several MB): that warp sits out and the one before it walks on. */
+constexpr u32 WP_FIND_CTAS = 64, WP_FIND_SPAN = 16384;
+__global__ void __launch_bounds__(256) k_dec_find_heads(const u8* body, u64 len, HeaderDev h, unsigned long long* starts) {
+    const u32 w = blockIdx.y + 1;
     const u32 head = 18u + ((h.flags & RPQ_ENCODE_N_POS) ? 4u : 0u);
     const u64 anchor = len / WP_WARPS * w;
-    u64 window = len - anchor; if (window > (8ull << 20)) window = 8ull << 20;       /* chunks are 0.1 .. 2 MB at the usual -k */
-    if (threadIdx.x == 0) { s_best = WP_NONE; starts[w] = ~0ull; }
-    __syncthreads();
-    for (u64 base = 0; base < window; base += 8 * blockDim.x) {
-#ifndef RPQ_EMU
-        {   /* the lines of the rounds to come are on their way to L2 (every round would otherwise wait for DRAM) */
-            const u64 q = anchor + base + 16ull * 8 * blockDim.x + 128ull * threadIdx.x;
-            if (threadIdx.x < 8u * blockDim.x / 128u + 1u && q + 128 <= len) asm volatile("prefetch.global.L2 [%0];" ::"l"(body + q));
-            if (base == 0) for (u64 k = 128ull * threadIdx.x; k < 16ull * 8 * blockDim.x; k += 128ull * blockDim.x) if (anchor + k + 128 <= len) asm volatile("prefetch.global.L2 [%0];" ::"l"(body + anchor + k));
-        }
-#endif
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const u64 rel = base + (u64)k * blockDim.x + threadIdx.x;
-            if (rel >= window) continue;
-            const u64 p = anchor + rel;
-            const u8* in = body + p;
-            /* cheap rejections first: 12 flag bits, a read count and column sizes that fit the size the header claims */
-            if (p + head > len || (in[9] & 0xF0u)) continue;
-            u32 reads, fl;
-            const u64 bytes = wp_header_bytes(body, len, h, p, head, reads, fl);
-            if (!bytes || reads > (1u << 26)) continue;
-            const u64 seq = ld32(in + 10), qual = ld32(in + 14);
-            if (seq + qual + head > bytes || seq > 4ull * reads * 65536ull) continue;
-            u32 r2, f2;
-            if (p + bytes != len && !wp_header_bytes(body, len, h, p + bytes, head, r2, f2)) continue;
-            atomicMin(&s_best, (u32)rel);
-        }
-        __syncthreads();
-        const u32 best = s_best;
-        __syncthreads();                             /* nobody updates s_best for the next round before everybody has read it */
-        if (best != WP_NONE) break;                  /* the earliest hit of the earliest round with a hit */
+    const u64 lo = anchor + (u64)blockIdx.x * WP_FIND_SPAN;
+    u64 best = ~0ull;
+    for (u32 k = threadIdx.x; k < WP_FIND_SPAN; k += blockDim.x) {
+        const u64 p = lo + k;
+        if (p + head > len) break;
+        const u8* in = body + p;
+        /* cheap rejections first: 12 flag bits, a read count and column sizes that fit the size the header claims */
+        if (in[9] & 0xF0u) continue;
+        u32 reads, fl;
+        const u64 bytes = wp_header_bytes(body, len, h, p, head, reads, fl);
+        if (!bytes || reads > (1u << 26)) continue;
+        const u64 seq = ld32(in + 10), qual = ld32(in + 14);
+        if (seq + qual + head > bytes || seq > 4ull * reads * 65536ull) continue;
+        u32 r2, f2;
+        if (p + bytes != len && !wp_header_bytes(body, len, h, p + bytes, head, r2, f2)) continue;
+        best = p;
+        break;                                      /* this thread's candidates only grow */
     }
-    if (threadIdx.x == 0 && s_best != WP_NONE) starts[w] = anchor + s_best;
+    if (best != ~0ull) atomicMin(&starts[w], (unsigned long long)best);
 }
 
 /* one CTA of WP_WARPS warps.  out: u32[0] chunks, u32[1] reads, u64[1] body bytes covered (as the sequential walks), mismatch |= 1
  * when the pieces do not fit together */
-__global__ void __launch_bounds__(32 * WP_WARPS) k_dec_walk_par(const u8* body, u64 len, HeaderDev h, const u64* __restrict__ starts, WalkSeg* slabs,
+__global__ void __launch_bounds__(32 * WP_WARPS) k_dec_walk_par(const u8* body, u64 len, HeaderDev h, const unsigned long long* __restrict__ starts, WalkSeg* slabs,
                                                                 DecChunk* chunks, u32 cap, u32* n_out, u64* consumed, u32* mismatch) {
     __shared__ u64 s_from[WP_WARPS], s_stop[WP_WARPS], s_end[WP_WARPS];
     __shared__ u32 s_n[WP_WARPS], s_reads[WP_WARPS], s_use[WP_WARPS];

@@ -281,35 +281,48 @@ def test_blank_lines(codec):
         assert K.compress(b + tail, k=100, codec=codec) == O.compress(b + tail, chunk_bases=100000)
 
 
-def test_parallel_chunk_walk(monkeypatch):
+class _HostAsDevice:
+    """under emulation 'device' memory is host memory"""
+    @staticmethod
+    def put(arr):
+        return arr, arr.ctypes.data
+
+    @staticmethod
+    def get(ptr, n):
+        import ctypes as C
+        return C.string_at(ptr, n) if n else b""
+
+
+def test_parallel_chunk_walk(monkeypatch, lib_path=EMU, mem=_HostAsDevice):
     """k_dec_find_heads + k_dec_walk_par (device-resident bodies of 32 MiB and more; here forced for any size): sixteen warps follow
     the chunk chain from headers found by scanning, the pieces must fit together exactly, and the result must be the sequential
     walk's.  Also: a body with bytes after its last whole chunk (the chain stops short, the exact walk takes over)."""
-    import ctypes as C
     from tools import fqgen
     monkeypatch.setenv("RPQ_DEBUG_PAR_WALK_MIN", "1")
-    cd = K.Codec(lib_path=EMU)
+    cd = K.Codec(lib_path=lib_path)
     try:
         r1, r2 = fqgen.generate(9000, seed=41, paired=True)
         rfq = K.compress(r1, r2, k=100, codec=cd)                      # 27 chunks
-        h, used = K.parse_header(rfq, EMU)
+        h, used = K.parse_header(rfq, lib_path)
         ref1, ref2, infos, _ = cd.decode(rfq[used:], split_pairs=True)  # host walk
         assert len(infos) == 27
         body = np.frombuffer(rfq, dtype=np.uint8)[used:].copy()
-        o = cd.decode_raw(body.ctypes.data, body.size, 1, True, 1)
+        keep, ptr = mem.put(body)
+        o = cd.decode_raw(ptr, body.size, 1, True, 1)
         assert cd.stats().dec_walk == 2                                 # the parallel walk was used and checked out
-        assert (C.string_at(o.out1, o.out1_bytes), C.string_at(o.out2, o.out2_bytes), o.n_chunks) == (ref1, ref2, 27)
+        assert (mem.get(o.out1, o.out1_bytes), mem.get(o.out2, o.out2_bytes), o.n_chunks) == (ref1, ref2, 27)
         # bytes after the last whole chunk: consumed stops there, through the exact walk
         tail = np.concatenate([body, body[:1000]])
-        o = cd.decode_raw(tail.ctypes.data, tail.size, 1, True, 1)
+        keep2, ptr2 = mem.put(tail)
+        o = cd.decode_raw(ptr2, tail.size, 1, True, 1)
         assert cd.stats().dec_walk == 3 and o.consumed == body.size and o.n_chunks == 27
-        assert C.string_at(o.out1, o.out1_bytes) == ref1
+        assert mem.get(o.out1, o.out1_bytes) == ref1
         # one-warp chain for comparison
         monkeypatch.setenv("RPQ_DEBUG_NO_PAR_WALK", "1")
-        cd2 = K.Codec(lib_path=EMU)
+        cd2 = K.Codec(lib_path=lib_path)
         cd2.set_header(h)
-        o = cd2.decode_raw(body.ctypes.data, body.size, 1, True, 1)
-        assert cd2.stats().dec_walk == 1 and C.string_at(o.out1, o.out1_bytes) == ref1
+        o = cd2.decode_raw(ptr, body.size, 1, True, 1)
+        assert cd2.stats().dec_walk == 1 and mem.get(o.out1, o.out1_bytes) == ref1
         cd2.close()
     finally:
         cd.close()
