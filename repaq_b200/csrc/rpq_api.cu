@@ -102,8 +102,7 @@ struct rpq_ctx {
     bool copy_stream_ok = false;
     cudaStream_t side_stream = 0;          /* decode: the fill of the quality plane, under the chunk walk and the table kernels */
     bool side_stream_ok = false;
-    RtEvent side_ev, tab_ev, sw_ev[16];    /* plane filled; tables ready; streams of window w decoded */
-    bool sw_ev_ok = false;
+    RtEvent side_ev;
     RtEvent win_ev[16], cp_ev[16];
     void* pinned_small = nullptr;          /* 64 KiB scratch for scalar read-backs */
     DevBuf host_out, host_out2;            /* pinned host buffers for results */
@@ -235,7 +234,6 @@ extern "C" void rpq_destroy(rpq_ctx* c) {
     c->lanes.clear();
     if (c->copy_stream_ok) { rt_stream_sync(c->copy_stream); rt_stream_destroy(c->copy_stream); for (auto& e : c->win_ev) rt_event_destroy(&e); for (auto& e : c->cp_ev) rt_event_destroy(&e); }
     if (c->side_stream_ok) { rt_stream_sync(c->side_stream); rt_stream_destroy(c->side_stream); rt_event_destroy(&c->side_ev); }
-    if (c->sw_ev_ok) { for (auto& e : c->sw_ev) rt_event_destroy(&e); rt_event_destroy(&c->tab_ev); }
     DevBuf* all[] = {&c->loc, &c->pk, &c->pk_rc, &c->text[0], &c->text[1], &c->nl[0], &c->nl[1], &c->tile_state, &c->counters, &c->rlen, &c->unit_bases, &c->prefix, &c->scan_tmp,
                      &c->ustats, &c->chunk_first, &c->chunks, &c->meta, &c->meta0, &c->ov, &c->seqoff, &c->qualoff, &c->n1off, &c->n2off, &c->soff,
                      &c->errbits, &c->tmpx, &c->tmpy, &c->span_first[0], &c->span_first[1], &c->span_chunk[0], &c->span_chunk[1], &c->dir[0], &c->dir[1],

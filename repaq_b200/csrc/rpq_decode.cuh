@@ -344,8 +344,9 @@ __global__ void __launch_bounds__(32 * DS_WARPS) k_dec_streams(DecBatchDev b, He
     const u32 sh = 8u * (u32)(sa & 3u);
     const u32* Aend = reinterpret_cast<const u32*>((reinterpret_cast<uintptr_t>(b.body + b.body_len) + 3u) & ~(uintptr_t)3);
     auto ldw = [&](u32 k) -> u32 { const u32* w = A + k; return w < Aend ? *w : 0u; };
-    const u64 lim_pos = is_npos ? (nmap_bits < dst_len ? (u64)nmap_bits : (u64)dst_len) : (u64)dst_len;      /* positions >= this are ignored (Q20) */
-    long long last = -1;
+    const u32 lim_pos = is_npos ? (nmap_bits < dst_len ? nmap_bits : dst_len) : dst_len;      /* positions >= this are ignored (Q20) */
+    u32 next = 0;                                         /* 1 + the position of the last element so far (`last` starts at -1); positions
+                                                             of a chunk fit 32 bits, a corrupt stream that wraps stays below lim_pos */
     u32 skip = 0;                                         /* payload bytes at the start of the step that belong to the previous token */
     u32 cura = slen ? ldw((u32)lane) : 0u;
     for (u32 base = 0; base < slen; base += 128) {
@@ -395,18 +396,17 @@ __global__ void __launch_bounds__(32 * DS_WARPS) k_dec_streams(DecBatchDev b, He
             }
         }
         u32 tot; const u32 ex = warp_excl_scan(lane_adv, lane, tot);
-        long long acc = last + (long long)ex;
+        u32 acc = next + ex;                                            /* 1 + the position before this lane's first token */
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             if (adv[k]) {
-                const long long endpos = acc + (long long)adv[k];      /* position of the token's last element */
-                acc = endpos;
-                long long first = run[k] ? endpos - run[k] + 1 : endpos;
-                if (first < 0) first = 0;
-                const long long lastp = endpos < (long long)lim_pos ? endpos : (long long)lim_pos - 1;
-                if (first <= lastp) {
-                    const u32 n = (u32)(lastp - first) + 1u;            /* 1..32 positions */
-                    if (is_npos) { for (u32 j = 0; j < n; j++) { const u64 pos = (u64)first + j; atomicOr(&nmap[pos >> 5], 1u << (pos & 31)); } }
+                const u32 end1 = acc + adv[k];                          /* 1 + the position of the token's last element */
+                acc = end1;
+                const u32 first = run[k] ? end1 - run[k] : end1 - 1u;
+                const u32 stop = end1 < lim_pos ? end1 : lim_pos;
+                if (first < stop) {
+                    const u32 n = stop - first;                         /* 1..32 positions */
+                    if (is_npos) { for (u32 j = 0; j < n; j++) { const u32 pos = first + j; atomicOr(&nmap[pos >> 5], 1u << (pos & 31)); } }
                     else {
                         u8* d = plane + first;
                         d[0] = q; if (n > 1) d[1] = q; if (n > 2) d[2] = q; if (n > 3) d[3] = q;
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(32 * DS_WARPS) k_dec_streams(DecBatchDev b, He
                 }
             }
         }
-        last += tot;
+        next += tot;
         cura = nexta;
     }
 }
