@@ -214,8 +214,18 @@ __global__ void __launch_bounds__(256) k_dec_find_heads(const u8* body, u64 len,
         if (!bytes || reads > (1u << 26)) continue;
         const u64 seq = ld32(in + 10), qual = ld32(in + 14);
         if (seq + qual + head > bytes || seq > 4ull * reads * 65536ull) continue;
-        u32 r2, f2;
-        if (p + bytes != len && !wp_header_bytes(body + p + bytes, len, h, p + bytes, head, r2, f2)) continue;
+        /* a real header leads to another one, four times over (or to the end of the body).  Two hops are not enough: the position
+         * streams of a file with ~40 quality values are dense small bytes, of which a 0.6 GB body holds a handful of places that
+         * pass the tests above and point at another such place */
+        bool chain = true;
+        u64 q = p + bytes;
+        for (int hop = 0; hop < 4 && chain && q != len; hop++) {
+            u32 r2, f2;
+            const u64 b2 = wp_header_bytes(body + q, len, h, q, head, r2, f2);
+            if (!b2 || (body[q + 9] & 0xF0u) || r2 > (1u << 26)) chain = false;
+            q += b2;
+        }
+        if (!chain) continue;
         best = p;
         break;                                      /* this thread's candidates only grow */
     }

@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams4(EncBatchDev b, HeaderDe
     __shared__ u32 s_first[MAX_BINS + 2];
     __shared__ u32 s_warp[S2_THREADS / 32];
     __shared__ u64 s_slot;
+    __shared__ u64 s_eq[S2_THREADS];                    /* every thread's "equals the previous position" mask: run ends without byte loops */
     __shared__ u32 s_tmp, s_redo, s_cross_p;
     const u32 span = blockIdx.x;
     if (span >= *job.n_spans) return;
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams4(EncBatchDev b, HeaderDe
         if (valid < 64u) nm &= (1ull << valid) - 1ull;
     }
 
+    s_eq[tid] = eq;
     /* ---- the list of runs: every thread appends the starts inside its segment; the run that crosses into the span is entry 0 */
     const u64 starts = nm & ~eq;
     const u32 my = (u32)__popcll(starts);
@@ -153,8 +155,18 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams4(EncBatchDev b, HeaderDe
             const u8 v = sm[x0 - sm_lo];
             const u8 l = mode == 0 ? s_lut[v] : (u8)0;
             cls = l == LUT_EXC ? exc_stream : (u32)l;
-            u32 y = x0 + 1;
-            while (y < scan_lim && sm[y - sm_lo] == v) y++;
+            /* the run ends at the first position after x0 whose "equals the previous" bit is clear: from the segment masks (no run
+             * covers a whole segment here), by bytes only for the up to 32 positions past the span that have no mask */
+            const u32 r = x0 - lo, seg = r >> 6;
+            u64 z = (~s_eq[seg] >> (r & 63u)) >> 1;
+            u32 y;
+            if (z) y = x0 + 1u + (u32)(__ffsll((long long)z) - 1);
+            else {
+                y = lo + 64u * (seg + 1u);
+                if (y < hi) y += (u32)(__ffsll((long long)~s_eq[seg + 1u]) - 1);
+            }
+            if (y >= hi) { y = y < hi ? y : (x0 + 1u > hi ? x0 + 1u : hi); while (y < scan_lim && sm[y - sm_lo] == v) y++; }
+            if (y > scan_lim) y = scan_lim;
             rend[k] = (unsigned short)(y - lo);
             rcls[k] = (u8)cls;
         }
