@@ -29,6 +29,8 @@ def main():
     starts = [i for i, ((_, name), _) in enumerate(items) if name.startswith("k_index_lines")][::2]
     if len(starts) >= 2:
         items = items[starts[0]:starts[1]]
+    elif len(starts) == 1:
+        items = items[starts[0]:]                       # the capture ends with the last step: its encode and its decode
     agg = {}
     for (_, name), m in items:
         a = agg.setdefault(name, dict(launches=0, dram_read_bytes=0.0, dram_write_bytes=0.0, us=0.0))
