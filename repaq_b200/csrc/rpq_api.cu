@@ -14,6 +14,7 @@
 #include "rpq_streams2.cuh"
 #include "rpq_streams3.cuh"
 #include "rpq_streams4.cuh"
+#include "rpq_streams5.cuh"
 #include "rpq_meta2.cuh"
 #include "rpq_meta3.cuh"
 #include "rpq_decode.cuh"
@@ -82,9 +83,11 @@ struct rpq_ctx {
     HeaderDev hd;
     /* grow-only device buffers */
     DevBuf loc, pk, pk_rc, text[2], nl[2], tile_state, counters, rlen, unit_bases, prefix, scan_tmp, ustats, chunk_first, chunks, meta, meta0, ov,
-        seqoff, qualoff, n1off, n2off, soff, errbits, tmpx, tmpy, span_first[2], span_chunk[2], dir[2], slots[2], span_slot[2], span_read0[2], redo_list[2], misc, out,
+        seqoff, qualoff, n1off, n2off, soff, errbits, tmpx, tmpy, span_first[2], span_chunk[2], dir[2], slots[2], span_slot[2], span_read0[2], redo_list[2], dense_list, misc, out,
         d_in, d_desc, d_tmp[8], d_tmp2, out2, d_slabs;
+    int streams5 = 1;                      /* RPQ_DEBUG_STREAMS5=0: dense quality spans go to k_streams3 (A/B); =2: k_streams5 codes every quality span (test coverage) */
     bool no_streams4 = false;              /* RPQ_DEBUG_NO_STREAMS4=1: k_streams3 codes every span (test coverage, A/B) */
+    u64 stats_dense_spans = 0;             /* spans k_streams4 handed to k_streams5 */
     u64 stats_redo_spans = 0;              /* spans k_streams4 handed to k_streams3 */
     int index_variant = 1;                 /* 1: CTA-per-tile indexer (default, 1.13 ms per 3.4 GB); RPQ_DEBUG_INDEX=0: persistent CTAs (1.31 ms) */
     u32 fmt_reads = 0;                     /* RPQ_DEBUG_FMT_READS=n: reads per formatter CTA (tuning experiments) */
@@ -205,6 +208,7 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     { const char* e = getenv("RPQ_DEBUG_NO_PAR_WALK"); c->no_par_walk = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_DEBUG_PAR_WALK_MIN"); c->par_walk_min = e ? strtoull(e, nullptr, 10) : (32ull << 20); }
     { const char* e = getenv("RPQ_DEBUG_INDEX"); c->index_variant = e ? atoi(e) : 1; }
+    { const char* e = getenv("RPQ_DEBUG_STREAMS5"); if (e) c->streams5 = atoi(e); }
     { const char* e = getenv("RPQ_DEBUG_NO_STREAMS4"); c->no_streams4 = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_DEBUG_FMT_READS"); c->fmt_reads = e ? (u32)atoi(e) : 0u; }
     { const char* e = getenv("RPQ_NO_PIPELINE"); c->no_pipeline = e && e[0] == '1'; }
@@ -219,6 +223,7 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     cudaFuncSetAttribute(k_streams2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_streams3, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_streams4, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_streams5, cudaFuncAttributeMaxDynamicSharedMemorySize, 205 * 1024);
     cudaFuncSetAttribute(k_meta3, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_dec_format3, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
 #endif
@@ -237,7 +242,7 @@ extern "C" void rpq_destroy(rpq_ctx* c) {
     DevBuf* all[] = {&c->loc, &c->pk, &c->pk_rc, &c->text[0], &c->text[1], &c->nl[0], &c->nl[1], &c->tile_state, &c->counters, &c->rlen, &c->unit_bases, &c->prefix, &c->scan_tmp,
                      &c->ustats, &c->chunk_first, &c->chunks, &c->meta, &c->meta0, &c->ov, &c->seqoff, &c->qualoff, &c->n1off, &c->n2off, &c->soff,
                      &c->errbits, &c->tmpx, &c->tmpy, &c->span_first[0], &c->span_first[1], &c->span_chunk[0], &c->span_chunk[1], &c->dir[0], &c->dir[1],
-                     &c->slots[0], &c->slots[1], &c->span_slot[0], &c->span_slot[1], &c->span_read0[0], &c->span_read0[1], &c->redo_list[0], &c->redo_list[1], &c->misc, &c->out, &c->d_in, &c->d_desc, &c->out2, &c->d_slabs,
+                     &c->slots[0], &c->slots[1], &c->span_slot[0], &c->span_slot[1], &c->span_read0[0], &c->span_read0[1], &c->redo_list[0], &c->redo_list[1], &c->dense_list, &c->misc, &c->out, &c->d_in, &c->d_desc, &c->out2, &c->d_slabs,
                      &c->d_tmp2, &c->d_tmp[0], &c->d_tmp[1], &c->d_tmp[2], &c->d_tmp[3], &c->d_tmp[4], &c->d_tmp[5], &c->d_tmp[6], &c->d_tmp[7]};
     for (DevBuf* b : all) rt_free_device(b->p);
     rt_free_pinned(c->pinned_small);

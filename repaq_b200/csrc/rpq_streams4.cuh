@@ -130,7 +130,10 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams4(EncBatchDev b, HeaderDe
     for (int w = 0; w < S2_THREADS / 32; w++) { const u32 t = s_warp[w]; if (w < warp) base += t; total += t; }
     const u32 n_runs = total;
     if (s_redo || n_runs > (u32)RL_CAP) {
-        if (tid == 0) { const u32 at = atomicAdd(job.redo_count, 1u); job.redo_list[at] = span; }
+        if (tid == 0) {
+            if (!s_redo && mode == 0 && job.dense_list) { const u32 at = atomicAdd(job.dense_count, 1u); job.dense_list[at] = span; }   /* too many runs: k_streams5 */
+            else { const u32 at = atomicAdd(job.redo_count, 1u); job.redo_list[at] = span; }                                           /* long runs: k_streams3 */
+        }
         return;
     }
     {

@@ -163,6 +163,47 @@ def test_stream_coder_generations(monkeypatch):
         cd.close()
 
 
+def _dense_cases(cd, lib_path):
+    """inputs whose quality spans hold more runs than k_streams4's list: BGI-shape (38-42 quality values), also with read-length
+    variation, with exceptions (values that are not in chunk 0's alphabet), a run over the first two positions of a chunk (Q16) and
+    runs of hundreds of equal values inside dense data (those spans go on to k_streams3)"""
+    from tools import fqgen
+    r1, _ = fqgen.generate(30000, seed=5, shape=fqgen.BGI)
+    parity.check_against_oracle(cd, r1)                                         # 3 chunks of 1 M bases
+    parity.check_against_oracle(cd, r1, k=100)
+    r1, _ = fqgen.generate(12000, seed=6, shape=fqgen.BGI, flags=fqgen.VARLEN)
+    parity.check_against_oracle(cd, r1, k=100)
+    lines = bytes(r1).split(b"\n")
+    rnd = np.random.RandomState(3)
+    nrec = (len(lines) - 1) // 4
+    for rec in rnd.choice(np.arange(1500, nrec), 80, replace=False):
+        q = bytearray(lines[4 * rec + 3])
+        kind = rnd.randint(4)
+        if kind == 0 and len(q) > 30: q[3:30] = b"\x7e" * 27                     # '~' is in no BGI alphabet: exception records
+        elif kind == 1: q[:] = bytes([q[0]]) * len(q)                              # a run longer than a segment: k_streams3's
+        elif kind == 2 and len(q) > 12: q[4:12] = bytes([q[4]]) * 8
+        else: q[0:2] = bytes([q[0]]) * 2
+        lines[4 * rec + 3] = bytes(q)
+    q = bytearray(lines[3]); q[0:2] = bytes([q[0]]) * 2; lines[3] = bytes(q)      # Q16: a run over positions 0 and 1 of the chunk
+    parity.check_against_oracle(cd, b"\n".join(lines), k=100)
+
+
+def test_dense_quality_spans(monkeypatch):
+    """k_streams5 takes the spans with more runs than k_streams4 lists (the default), RPQ_DEBUG_STREAMS5=0 leaves them to k_streams3,
+    =2 lets k_streams5 code every quality span of ordinary inputs too: all three must give the reference's bytes"""
+    for knob, names in (("1", ("bgi_se_k100", "bgi_se_varlen_k100")), ("0", ("bgi_se_k100",)),
+                        ("2", ("nova_pe_k1000", "nova_pe_k100_npos", "bgi_se_varlen_k100", "nova_se_late_quality", "kat_pe", "one_read", "nova_pe_300bp_varlen_k100"))):
+        monkeypatch.setenv("RPQ_DEBUG_STREAMS5", knob)
+        cd = K.Codec(lib_path=EMU)
+        try:
+            for name in names:
+                parity.check_encode_golden(cd, name)
+            if knob != "0":
+                _dense_cases(cd, EMU)
+        finally:
+            cd.close()
+
+
 def test_persistent_indexer_variant(monkeypatch):
     """RPQ_DEBUG_INDEX=0 selects the persistent-CTA line indexer (the CTA-per-tile one is the default)"""
     monkeypatch.setenv("RPQ_DEBUG_INDEX", "0")

@@ -156,6 +156,21 @@ def test_parallel_chunk_walk(monkeypatch):
     E.test_parallel_chunk_walk(monkeypatch, lib_path=None, mem=_TorchDevice)
 
 
+def test_dense_quality_spans(monkeypatch):
+    """k_streams5 on the GPU: dense inputs against the oracle (default hand-over from k_streams4) and every quality span of ordinary
+    golden inputs (RPQ_DEBUG_STREAMS5=2)"""
+    from tests import test_emu_parity as E
+    for knob in ("1", "2"):
+        monkeypatch.setenv("RPQ_DEBUG_STREAMS5", knob)
+        cd = K.Codec(device=0)
+        try:
+            for name in ("nova_pe_k1000", "bgi_se_varlen_k100", "nova_se_late_quality", "nova_pe_k100_npos"):
+                parity.check_encode_golden(cd, name)
+            E._dense_cases(cd, None)
+        finally:
+            cd.close()
+
+
 def test_window_cut_and_blank_lines(codec):
     from tests import test_emu_parity as E
     E.test_window_cut_inside_the_chunk_closing_record(codec)
