@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(S5_THREADS) k_streams5(EncBatchDev b, HeaderDe
             if (y >= hi) { y = x0 + 1u > hi ? x0 + 1u : hi; while (y < scan_lim && sm[y - sm_lo] == v) y++; }
             if (y > scan_lim) y = scan_lim;
             rend[k] = (unsigned short)(y - lo);
-            rcls[k] = (u8)cls;
         }
+        rcls[k] = (u8)cls;                                   /* 0xFF: no run starts here (what B and C test) */
         const u32 peers = __match_any_sync(0xffffffffu, cls);
         if (valid && (peers >> lane) <= 1u) tab[(k >> 5) * nstreams + cls] = (unsigned short)k;       /* highest lane of its group */
     }
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(S5_THREADS) k_streams5(EncBatchDev b, HeaderDe
     /* ---- B */
     for (u32 m = 0; m < S5_ROUNDS; m++) {
         const u32 k = m * S5_THREADS + (u32)tid;
-        const bool valid = is_start(k);
-        const u32 cls = valid ? (u32)rcls[k] : 0xFFu;
+        const u32 cls = rcls[k];
+        const bool valid = cls != 0xFFu;
         const u32 peers = __match_any_sync(0xffffffffu, cls);
         const u32 lower = peers & ((1u << lane) - 1u);
         u32 bytes = 0;
@@ -251,8 +251,8 @@ __global__ void __launch_bounds__(S5_THREADS) k_streams5(EncBatchDev b, HeaderDe
     u8* slot = job.slots + s_slot;
     for (u32 m = 0; m < S5_ROUNDS; m++) {
         const u32 k = m * S5_THREADS + (u32)tid;
-        if (!is_start(k)) continue;
         const u32 cls = rcls[k];
+        if (cls == 0xFFu) continue;
         const bool crossing = has_cross && k == 0;
         const u32 p = crossing ? s_cross_p : lo + k;
         const u32 r_end = lo + rend[k];
