@@ -4,7 +4,10 @@
  * File-level rules kept from the reference: header written first (src/repaq.cpp:554-557), Q13 NO_LINE_BREAK thresholds
  * (src/fastqreader.cpp:31-46), trailing-newline trimming on decode (src/repaq.cpp:300-328, 375-413).
  * Compare mode prints the reference's JSON report (src/repaq.cpp:235-259).
- * Not implemented here: .gz input/output, the xz pipe, -v / -f (outside the tier's scope).
+ * -v / -f: every batch is decoded again and checked against its input on the GPU (rpq_compare) after it has been written, and the
+ * first difference is reported on stderr in the words of completeCheckAndOutput (src/repaq.cpp:430-528); like the reference, the
+ * output is written either way.  (-f checks a tenth of the chunks there to save CPU time; here both check everything.)
+ * Not implemented here: .gz input/output, the xz pipe (outside the tier's scope).
  */
 #include <stdint.h>
 #include <stdio.h>
@@ -51,7 +54,7 @@ static void nobreak_rule(const std::vector<char>& f, uint64_t& from, bool& tail)
     else { from = nl ? UINT64_MAX : (n / MiB) * MiB; tail = false; }
 }
 
-struct Opt { std::string in1, in2, out1, out2, rfq_compare, json_compare; bool compress = false, decompress = false, compare = false, interleaved = false, to_stdout = false, from_stdin = false; int k = 1000; int device = 0; };
+struct Opt { std::string in1, in2, out1, out2, rfq_compare, json_compare; bool compress = false, decompress = false, compare = false, interleaved = false, to_stdout = false, from_stdin = false, verify = false; int k = 1000; int device = 0; };
 
 static int do_compress(const Opt& o) {
     std::vector<char> r1 = slurp(o.in1), r2;
@@ -72,6 +75,7 @@ static int do_compress(const Opt& o) {
     if (two) nobreak_rule(r2, from2, t2); else if (o.interleaved) { from2 = from1; t2 = t1; }
     const uint64_t WIN = 3ull << 30;                       /* < 4 GiB of text per file and call */
     uint64_t a = 0, b = 0;
+    rpq_ctx* check = NULL;                                 /* -v / -f: the reference's codec4check */
     for (;;) {
         rpq_encode_in in; memset(&in, 0, sizeof in);
         const uint64_t n1 = r1.size() - a < WIN ? r1.size() - a : WIN, n2 = two ? (r2.size() - b < WIN ? r2.size() - b : WIN) : 0;
@@ -84,10 +88,25 @@ static int do_compress(const Opt& o) {
         rpq_encode_out res;
         if (rpq_encode(ctx, &in, &res)) error_exit(rpq_last_error(ctx));
         spill(o.out1, res.data, res.bytes, true);
+        if (o.verify && res.bytes) {
+            /* the check of completeCheckAndOutput: decode what was just written, compare it read by read with what it was made from */
+            if (!check && (rpq_create(o.device, &check) || rpq_set_header(check, &h))) error_exit("no CUDA device: repaq_b200 has no CPU fallback");
+            rpq_compare_in ci; memset(&ci, 0, sizeof ci);
+            ci.rfq = res.data; ci.rfq_bytes = res.bytes; ci.rfq_mem = RPQ_MEM_HOST; ci.rfq_final = 1;
+            ci.r1 = in.r1; ci.r1_len = in.final ? in.r1_len : res.r1_consumed; ci.r2 = in.r2; ci.r2_len = in.final ? in.r2_len : res.r2_consumed;
+            ci.fq_mem = RPQ_MEM_HOST; ci.fq_final = 1;
+            rpq_compare_out co;
+            if (o.interleaved) fprintf(stderr, "verify: --interleaved_in input is not checked\n");
+            else if (rpq_compare(check, &ci, &co)) error_exit(rpq_last_error(check));
+            else if (co.verdict == RPQ_CMP_RFQ_MORE || co.verdict == RPQ_CMP_FASTQ_MORE) error_exit("encoding error in chunk, the output will be wrong, quit now!");
+            else if (co.verdict != RPQ_CMP_EQUAL)
+                fprintf(stderr, "integrity check failure \nexpected: \n%.*s\ngot:\n%.*s\n", (int)co.fastq_field_len, co.fastq_field, (int)co.rfq_field_len, co.rfq_field);
+        }
         if (in.final) break;
         if (res.r1_consumed == 0) error_exit("a chunk does not fit the 3 GiB batch window; lower --chunk");
         a += res.r1_consumed; b += res.r2_consumed;
     }
+    if (check) rpq_destroy(check);
     rpq_destroy(ctx);
     return 0;
 }
@@ -219,6 +238,7 @@ int main(int argc, char** argv) {
         else if (a == "-r" || a.compare(0, 17, "--rfq_to_compare=") == 0 || a == "--rfq_to_compare") o.rfq_compare = val("rfq_to_compare");
         else if (a == "-j" || a.compare(0, 22, "--json_compare_result=") == 0 || a == "--json_compare_result") o.json_compare = val("json_compare_result");
         else if (a == "-p" || a == "--compare") o.compare = true;
+        else if (a == "-v" || a == "--verify" || a == "-f" || a == "--fast_verify") o.verify = true;
         else if (a == "-c" || a == "--compress") o.compress = true;
         else if (a == "-d" || a == "--decompress") o.decompress = true;
         else if (a == "--interleaved_in") o.interleaved = true;

@@ -61,3 +61,30 @@ def test_cli_error_strings(tmp_path):
 @pytest.mark.parametrize("name", NAMES)
 def test_cli_gpu(tmp_path, name):
     run_cli(GPU_CLI, tmp_path, name)
+
+
+def run_verify(cli, tmp_path):
+    for name, lossy in (("nova_pe_k1000", False), ("names_numeric_edge_pe", True), ("nova_se_k100", False)):
+        c = CASES[name]
+        (tmp_path / "a.fq").write_bytes(c["r1"])
+        cmd = [cli, "-c", "-v", "-i", str(tmp_path / "a.fq"), "-o", str(tmp_path / "o.rfq"), "-k", str(c["k"])]
+        if c["r2"] is not None:
+            (tmp_path / "b.fq").write_bytes(c["r2"])
+            cmd += ["-I", str(tmp_path / "b.fq")]
+        p = subprocess.run(cmd, capture_output=True, check=True)
+        assert (tmp_path / "o.rfq").read_bytes() == golden_rfq(name)
+        assert (b"integrity check failure" in p.stderr) == lossy
+        if lossy:
+            assert b"expected: \n@a:b:c:0000000001:00000000002:000000003:0000000000004 1:N:0:ACGT\ngot:\n@a:b:c:1:2:3:4 1:N:0:ACGT\n" in p.stderr
+
+
+def test_cli_verify_emulated(tmp_path):
+    """-v: the batch is decoded again and compared with its input on the device; a lossy input (leading zeros in the name's numbers
+    are not kept by the format) is reported on stderr in the reference's words and the output is still written"""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
+    run_verify(EMU_CLI, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_verify_gpu(tmp_path):
+    run_verify(GPU_CLI, tmp_path)
