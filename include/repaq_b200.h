@@ -107,6 +107,11 @@ typedef struct rpq_encode_in {
     uint64_t nobreak_from[2];
     uint16_t tail_flags;                  /* OR-ed into the trailing partial chunk only */
     int out_mem;                          /* where the serialised chunks are wanted: RPQ_MEM_HOST or RPQ_MEM_DEVICE */
+    /* offsets of r1 / r2 inside their files (0: the text starts where the file starts).  Only "\r\n" files need them: the
+     * reference's reader refills a 1 MiB buffer and reads a "\r\n" whose '\n' is the last byte of a buffer or the first of the
+     * next as a line end followed by an EMPTY line, where it ends its input (src/fastqreader.cpp:113-116, :180-181): such a file is
+     * refused (RPQ_ERR_FASTQ) instead of being encoded differently from the reference. */
+    uint64_t file_offset[2];
 } rpq_encode_in;
 
 /* scalar fields of RfqChunk (src/rfqchunk.h:52-113) for one encoded / indexed chunk */
@@ -175,6 +180,7 @@ typedef struct rpq_compare_in {
     const char* r2; uint64_t r2_len;          /* mate file (comparePE), or NULL */
     int fq_mem;
     int fq_final;                             /* 1: the FASTQ text ends here */
+    uint64_t fq_offset[2];                    /* offsets of r1 / r2 inside their files (see rpq_encode_in.file_offset) */
 } rpq_compare_in;
 
 typedef struct rpq_compare_out {

@@ -19,7 +19,7 @@ class Header(C.Structure):
 class EncodeIn(C.Structure):
     _fields_ = [("r1", C.c_void_p), ("r1_len", C.c_uint64), ("r2", C.c_void_p), ("r2_len", C.c_uint64),
                 ("mem", C.c_int), ("interleaved", C.c_int), ("chunk_bases", C.c_uint32), ("final", C.c_int),
-                ("nobreak_from", C.c_uint64 * 2), ("tail_flags", C.c_uint16), ("out_mem", C.c_int)]
+                ("nobreak_from", C.c_uint64 * 2), ("tail_flags", C.c_uint16), ("out_mem", C.c_int), ("file_offset", C.c_uint64 * 2)]
 
 
 class ChunkInfo(C.Structure):
@@ -47,7 +47,7 @@ class DecodeOut(C.Structure):
 class CompareIn(C.Structure):
     _fields_ = [("rfq", C.c_void_p), ("rfq_bytes", C.c_uint64), ("rfq_mem", C.c_int), ("rfq_final", C.c_int),
                 ("r1", C.c_void_p), ("r1_len", C.c_uint64), ("r2", C.c_void_p), ("r2_len", C.c_uint64),
-                ("fq_mem", C.c_int), ("fq_final", C.c_int)]
+                ("fq_mem", C.c_int), ("fq_final", C.c_int), ("fq_offset", C.c_uint64 * 2)]
 
 
 class CompareOut(C.Structure):

@@ -82,6 +82,7 @@ static int do_compress(const Opt& o) {
         in.r1 = r1.data() + a; in.r1_len = n1; in.r2 = two ? r2.data() + b : NULL; in.r2_len = n2;
         in.mem = RPQ_MEM_HOST; in.out_mem = RPQ_MEM_HOST; in.interleaved = o.interleaved; in.chunk_bases = chunk_bases;
         in.final = (a + n1 == r1.size()) && (!two || b + n2 == r2.size());
+        in.file_offset[0] = a; in.file_offset[1] = b;
         in.nobreak_from[0] = from1 == UINT64_MAX ? UINT64_MAX : (from1 > a ? from1 - a : 0);
         in.nobreak_from[1] = from2 == UINT64_MAX ? UINT64_MAX : (two ? (from2 > b ? from2 - b : 0) : in.nobreak_from[0]);
         in.tail_flags = (uint16_t)((t1 ? RPQ_NO_LINE_BREAK_AT_END : 0) | (t2 ? RPQ_NO_LINE_BREAK_AT_END_R2 : 0));
@@ -175,6 +176,7 @@ static int do_compare(const Opt& o) {
         in.rfq = (const uint8_t*)rfq.data() + at; in.rfq_bytes = nq; in.rfq_mem = RPQ_MEM_HOST; in.rfq_final = at + nq == rfq.size();
         in.r1 = r1.data() + a; in.r1_len = n1; in.r2 = pe ? (r2.empty() ? "" : r2.data() + b) : NULL; in.r2_len = n2; in.fq_mem = RPQ_MEM_HOST;
         in.fq_final = (a + n1 == r1.size()) && (!pe || b + n2 == r2.size());
+        in.fq_offset[0] = a; in.fq_offset[1] = b;
         rpq_compare_out res;
         if (rpq_compare(ctx, &in, &res)) error_exit(rpq_last_error(ctx));
         if (res.verdict == RPQ_CMP_NEED_FASTQ) {           /* these chunks decode to more reads than 3 GiB of text hold: fewer chunks per call */

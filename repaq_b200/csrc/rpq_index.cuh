@@ -513,4 +513,21 @@ __global__ void k_cut_ends(UnitStats* st, const u32* __restrict__ nl0, const u32
     if (two) st->end[1] = nl1[4ull * last_unit + 3];
 }
 
+/* "\r\n" files: the first line break the reference's reader mis-reads.  It refills a 1 MiB buffer and takes the '\n' after a
+ * '\r' as part of the break only `if (end < mBufDataLen - 1 && mBuf[end] == '\n')` (src/fastqreader.cpp:113-116): a '\n' that is
+ * the LAST byte of a buffer, or the first byte of the next one, is read as a line of its own - an empty line, which ends the
+ * input (:180-181).  A thread per buffer edge inside the text; *first = text offset of the first such '\n' that has anything
+ * after it, else stays ~0. */
+__global__ void k_crlf_edges(const u8* __restrict__ text, u64 len, u64 file_off, int eof, u32* first) {
+    const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 edge = (((file_off >> 20) + 1ull + k) << 20);      /* file offset of the first byte of a buffer */
+    if (edge < file_off + 1) return;
+    const u64 rel = edge - file_off;                             /* the same, inside this text */
+    if (rel > len) return;
+    u64 hit = ~0ull;
+    if (rel >= 2 && text[rel - 1] == '\n' && text[rel - 2] == '\r' && (rel < len || !eof)) hit = rel - 1;            /* last byte of a buffer */
+    else if (rel >= 1 && rel < len && text[rel] == '\n' && text[rel - 1] == '\r' && (rel + 1 < len || !eof)) hit = rel;   /* first byte of the next */
+    if (hit != ~0ull) atomicMin(first, (u32)hit);
+}
+
 }  // namespace rpq

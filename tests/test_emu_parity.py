@@ -367,3 +367,34 @@ def test_parallel_chunk_walk(monkeypatch, lib_path=EMU, mem=_HostAsDevice):
         cd2.close()
     finally:
         cd.close()
+
+
+def test_crlf_on_reader_buffer_edges(codec):
+    r"""The reference's reader (1 MiB refills) reads a "\r\n" whose '\n' is the last byte of a buffer, or the first of the next one,
+    as a break followed by an empty line and ends its input there: the file is silently truncated (the oracle restates that; both
+    facts are checked against the reference binary when it is present).  The CUDA path refuses such a file; a "\r\n" file of the
+    same size without a break on an edge is encoded like the reference."""
+    from oracle import oracle as O
+    from tools import fqgen
+    MIB = 1 << 20
+    r1, _ = fqgen.generate(5000, seed=21, flags=fqgen.CRLF)
+    b = bytes(r1)
+    assert len(b) > MIB and all(b[k * MIB - 1:k * MIB] != b"\n" and b[k * MIB:k * MIB + 1] != b"\n" for k in range(1, len(b) // MIB + 1))
+    whole = O.compress(b, chunk_bases=100000)
+    assert K.compress(b, k=100, codec=codec) == whole
+    lines = b.split(b"\r\n")
+    for target in (MIB - 1, MIB):
+        pos = 0
+        for ln in lines:                                      # the first line break at or after target - 100 ...
+            end = pos + len(ln) + 1
+            if end >= target - 100 and end <= target:
+                break
+            pos = end + 1
+        padded = list(lines)
+        padded[0] = padded[0] + b"x" * (target - end)        # ... moved onto the edge by a longer first name
+        x = b"\r\n".join(padded)
+        assert x[target - 1:target + 1] == b"\r\n"
+        assert len(O.compress(x, chunk_bases=100000)) < len(whole) * 2 // 3        # the reference loses everything after the edge
+        with pytest.raises(K.RepaqError) as e:
+            K.compress(x, k=100, codec=codec)
+        assert e.value.code == -4 and "1 MiB boundary" in str(e.value)

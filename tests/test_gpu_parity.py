@@ -175,6 +175,7 @@ def test_window_cut_and_blank_lines(codec):
     from tests import test_emu_parity as E
     E.test_window_cut_inside_the_chunk_closing_record(codec)
     E.test_blank_lines(codec)
+    E.test_crlf_on_reader_buffer_edges(codec)
 
 
 def test_library_really_ran_on_gpu(codec):
