@@ -273,10 +273,13 @@ __global__ void __launch_bounds__(256) k_emit2(EncBatchDev b, HeaderDev h, u8* o
     for (; W <= w1; W++) boundary_word(W);
 }
 
-/* name1 / name2 / strand arenas for chunks whose parts are not all the same: warp per read (text bytes, coalesced) */
+/* name1 / name2 / strand arenas for chunks whose parts are not all the same: EIGHT LANES per read (text bytes, coalesced in
+ * 8-byte pieces).  Names are a few dozen bytes: a whole warp per read spent ~60 instructions of per-read set-up on one
+ * iteration of copying (0.85 ms for 4 M BGI-shape reads, whose names are all different). */
+constexpr int EN_LANES = 8;
 __global__ void __launch_bounds__(256) k_emit_names(EncBatchDev b, HeaderDev h, u8* out) {
-    const int lane = threadIdx.x & 31;
-    const u32 i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const u32 l8 = threadIdx.x & (EN_LANES - 1);
+    const u32 i = (blockIdx.x * blockDim.x + threadIdx.x) / EN_LANES;
     if (i >= b.n_reads) return;
     const u32 c = chunk_of_read(b, i);
     const ChunkDev& ck = b.chunks[c];
@@ -289,9 +292,9 @@ __global__ void __launch_bounds__(256) k_emit_names(EncBatchDev b, HeaderDev h, 
     u32 f, rec; read_locus(b, i, f, rec);
     const u8* text = b.t[f].text;
     const u8* name = text + lc.x;
-    if (need1) { u8* d = o + ck.off_n1 + b.n1off[i]; for (u32 k = lane; k < m.name1_len; k += 32) d[k] = name[k]; }
-    if (need2) { u8* d = o + ck.off_n2 + b.n2off[i]; const u32 l = (u32)m.name_len - m.name2_off; for (u32 k = lane; k < l; k += 32) d[k] = name[m.name2_off + k]; }
-    if (need3) { const u8* s = text + lc.z; u8* d = o + ck.off_strand + b.soff[i]; for (u32 k = lane; k < m.strand_len; k += 32) d[k] = s[k]; }
+    if (need1) { u8* d = o + ck.off_n1 + b.n1off[i]; for (u32 k = l8; k < m.name1_len; k += EN_LANES) d[k] = name[k]; }
+    if (need2) { u8* d = o + ck.off_n2 + b.n2off[i]; const u32 l = (u32)m.name_len - m.name2_off; for (u32 k = l8; k < l; k += EN_LANES) d[k] = name[m.name2_off + k]; }
+    if (need3) { const u8* s = text + lc.z; u8* d = o + ck.off_strand + b.soff[i]; for (u32 k = l8; k < m.strand_len; k += EN_LANES) d[k] = s[k]; }
 }
 
 }  // namespace rpq
