@@ -28,8 +28,14 @@ constexpr int S5_THREADS = 1024;
 constexpr u32 S5_BLOCKS = ST_SPAN / 32;
 constexpr u32 S5_ROUNDS = ST_SPAN / S5_THREADS;
 
+/* one [block][stream] table holds first the predecessors, then the byte counts; with room for two (up to ~44 streams) the second
+ * one is cleared once instead of block by block between a warp's reads and writes */
+__host__ __device__ inline bool streams5_two_tables(u32 nstreams) {
+    return (size_t)ST_SPAN + 2 * ST_HALO + 16 + (size_t)ST_SPAN * (3 * sizeof(unsigned short) + 1) + 2 * (size_t)S5_BLOCKS * nstreams * sizeof(unsigned short) <= 216u * 1024u;
+}
 __host__ __device__ inline size_t streams5_smem(u32 nstreams) {
-    return (size_t)ST_SPAN + 2 * ST_HALO + 16 + (size_t)ST_SPAN * (3 * sizeof(unsigned short) + 1) + (size_t)S5_BLOCKS * nstreams * sizeof(unsigned short);
+    return (size_t)ST_SPAN + 2 * ST_HALO + 16 + (size_t)ST_SPAN * (3 * sizeof(unsigned short) + 1) +
+           (streams5_two_tables(nstreams) ? 2u : 1u) * (size_t)S5_BLOCKS * nstreams * sizeof(unsigned short);
 }
 
 __global__ void __launch_bounds__(S5_THREADS) k_streams5(EncBatchDev b, HeaderDev h, StreamJob job, const u32* __restrict__ span_chunk, const u32* __restrict__ list) {
@@ -39,7 +45,6 @@ __global__ void __launch_bounds__(S5_THREADS) k_streams5(EncBatchDev b, HeaderDe
     __shared__ u32 s_base[MAX_BINS + 2];
     __shared__ u32 s_first[MAX_BINS + 2];
     __shared__ u64 s_start[ST_SPAN / 64], s_eq[ST_SPAN / 64];
-    __shared__ unsigned short s_wb[S5_THREADS];
     __shared__ u64 s_slot;
     __shared__ u32 s_tmp, s_redo, s_cross_p, s_cross;
     const u32 span = list ? list[blockIdx.x] : blockIdx.x;
@@ -58,8 +63,9 @@ __global__ void __launch_bounds__(S5_THREADS) k_streams5(EncBatchDev b, HeaderDe
     unsigned short* roff = rend + ST_SPAN;                                /* [ST_SPAN] byte offset inside (block, stream) */
     unsigned short* rdm = roff + ST_SPAN;                                 /* [ST_SPAN] distance - 1 of the run's distance token, RL_NONE: none / deferred */
     u8* rcls = reinterpret_cast<u8*>(rdm + ST_SPAN);                      /* [ST_SPAN] stream index */
-    unsigned short* tab = reinterpret_cast<unsigned short*>(rcls + ST_SPAN);   /* [S5_BLOCKS][nstreams]: A/P1 last run start of the stream in / before the
-                                                                                  block; B/P2 bytes of the stream in the block / before it */
+    unsigned short* tab = reinterpret_cast<unsigned short*>(rcls + ST_SPAN);   /* [S5_BLOCKS][nstreams]: A/P1 last run start of the stream in / before the block */
+    const bool two = streams5_two_tables(nstreams);
+    unsigned short* tbytes = two ? tab + (size_t)S5_BLOCKS * nstreams : tab;     /* B/P2 bytes of the stream in the block / before it (aliases tab if there is no room) */
     if (tid < 256) s_lut[tid] = h.lut[tid];
     if (tid == 0) { s_redo = 0; s_cross = 0; }
     for (u32 k = tid; k < 8; k += S5_THREADS) if (sm_hi - sm_lo + k < (u32)(ST_SPAN + 2 * ST_HALO + 16)) sm[sm_hi - sm_lo + k] = h.major;
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__(S5_THREADS) k_streams5(EncBatchDev b, HeaderDe
         }
         if (redo) atomicOr(&s_redo, 1u);
     }
-    for (u32 k = tid; k < S5_BLOCKS * nstreams; k += S5_THREADS) tab[k] = (unsigned short)RL_NONE;
+    for (u32 k = tid; k < S5_BLOCKS * nstreams; k += S5_THREADS) { tab[k] = (unsigned short)RL_NONE; if (two) tbytes[k] = 0; }
     for (u32 k = tid; k < nstreams; k += S5_THREADS) s_first[k] = NONE32;
     __syncthreads();
     if (s_redo) {
@@ -197,17 +203,24 @@ __global__ void __launch_bounds__(S5_THREADS) k_streams5(EncBatchDev b, HeaderDe
                 if (head < stop) bytes += (stop - head + 31u) / 32u;
             }
         }
-        s_wb[tid] = (unsigned short)bytes;
-        __syncwarp();                                        /* every lane has read its predecessor from the table: the block's cells now count bytes */
-        for (u32 st = lane; st < nstreams; st += 32) tab[(k >> 5) * nstreams + st] = 0;
-        __syncwarp();
+        if (!two) {
+            __syncwarp();                                    /* every lane has read its predecessor from the table: the block's cells now count bytes */
+            for (u32 st = lane; st < nstreams; st += 32) tab[(k >> 5) * nstreams + st] = 0;
+            __syncwarp();
+        }
+        /* bytes of the lower lanes of the same stream: bit plane by bit plane, one ballot and one population count each; planes
+         * nobody uses are skipped (a run's tokens are a few bytes; the records of an exception run - below 128 positions, or the
+         * span would not be here - at most 635) */
         u32 myoff = 0;
-        for (u32 lw = lower; lw; lw &= lw - 1u) myoff += s_wb[(tid & ~31) + (__ffs((int)lw) - 1)];
+#pragma unroll
+        for (int bit = 0; bit < 10; bit++) {
+            const u32 plane = __ballot_sync(0xffffffffu, (bytes >> bit) & 1u);
+            if (plane) myoff += (u32)__popc(plane & lower) << bit;
+        }
         if (valid) {
             roff[k] = (unsigned short)myoff;
-            if ((peers >> lane) <= 1u) tab[(k >> 5) * nstreams + cls] = (unsigned short)(myoff + bytes);
+            if ((peers >> lane) <= 1u) tbytes[(k >> 5) * nstreams + cls] = (unsigned short)(myoff + bytes);
         }
-        __syncwarp();
     }
     __syncthreads();
     /* ---- P2: block offsets per stream (a warp per stream, a lane per block), directory */
@@ -215,9 +228,9 @@ __global__ void __launch_bounds__(S5_THREADS) k_streams5(EncBatchDev b, HeaderDe
         u32 acc = 0;
         for (u32 j0 = 0; j0 < S5_BLOCKS; j0 += 32) {
             const u32 j = j0 + (u32)lane;
-            const u32 t = (u32)tab[j * nstreams + st];
+            const u32 t = (u32)tbytes[j * nstreams + st];
             u32 tot; const u32 exs = warp_excl_scan(t, lane, tot);
-            tab[j * nstreams + st] = (unsigned short)(acc + exs);
+            tbytes[j * nstreams + st] = (unsigned short)(acc + exs);
             acc += tot;
         }
         if (lane == 0) {
@@ -257,7 +270,7 @@ __global__ void __launch_bounds__(S5_THREADS) k_streams5(EncBatchDev b, HeaderDe
         const u32 p = crossing ? s_cross_p : lo + k;
         const u32 r_end = lo + rend[k];
         const u32 stop = r_end < hi ? r_end : hi;
-        u8* o = slot + s_base[cls] + tab[(k >> 5) * nstreams + cls] + roff[k];
+        u8* o = slot + s_base[cls] + tbytes[(k >> 5) * nstreams + cls] + roff[k];
         if (cls == exc_stream) {
             const u8 v = sm[(p > lo ? p : lo) - sm_lo];
             for (u32 q = p > lo ? p : lo; q < stop; q++) { o[0] = v; o[1] = (u8)q; o[2] = (u8)(q >> 8); o[3] = (u8)(q >> 16); o[4] = (u8)(q >> 24); o += 5; }
