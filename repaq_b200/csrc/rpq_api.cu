@@ -87,6 +87,8 @@ struct rpq_ctx {
         d_in, d_desc, d_tmp[8], d_tmp2, out2, d_slabs;
     int streams5 = 1;                      /* RPQ_DEBUG_STREAMS5=0: dense quality spans go to k_streams3 (A/B); =2: k_streams5 codes every quality span (test coverage) */
     bool no_streams4 = false;              /* RPQ_DEBUG_NO_STREAMS4=1: k_streams3 codes every span (test coverage, A/B) */
+    bool dense_hint = false;               /* most quality spans of the last batch were dense: the next one goes to k_streams5 directly (k_streams4 would stage
+                                              and count every span only to hand it over) */
     u64 stats_dense_spans = 0;             /* spans k_streams4 handed to k_streams5 */
     u64 stats_redo_spans = 0;              /* spans k_streams4 handed to k_streams3 */
     int index_variant = 1;                 /* 1: CTA-per-tile indexer (default, 1.13 ms per 3.4 GB); RPQ_DEBUG_INDEX=0: persistent CTAs (1.31 ms) */

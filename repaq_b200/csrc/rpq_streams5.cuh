@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(S5_THREADS) k_streams5(EncBatchDev b, HeaderDe
     __shared__ u32 s_first[MAX_BINS + 2];
     __shared__ u64 s_start[ST_SPAN / 64], s_eq[ST_SPAN / 64];
     __shared__ u64 s_slot;
-    __shared__ u32 s_tmp, s_redo, s_cross_p, s_cross;
+    __shared__ u32 s_tmp, s_redo, s_cross_p, s_cross, s_runs;
     const u32 span = list ? list[blockIdx.x] : blockIdx.x;
     if (span >= *job.n_spans) return;
     const u32 c = span_chunk[span];
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(S5_THREADS) k_streams5(EncBatchDev b, HeaderDe
     const bool two = streams5_two_tables(nstreams);
     unsigned short* tbytes = two ? tab + (size_t)S5_BLOCKS * nstreams : tab;     /* B/P2 bytes of the stream in the block / before it (aliases tab if there is no room) */
     if (tid < 256) s_lut[tid] = h.lut[tid];
-    if (tid == 0) { s_redo = 0; s_cross = 0; }
+    if (tid == 0) { s_redo = 0; s_cross = 0; s_runs = 0; }
     for (u32 k = tid; k < 8; k += S5_THREADS) if (sm_hi - sm_lo + k < (u32)(ST_SPAN + 2 * ST_HALO + 16)) sm[sm_hi - sm_lo + k] = h.major;
     {
         u32* s_off = reinterpret_cast<u32*>(arrays);
@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(S5_THREADS) k_streams5(EncBatchDev b, HeaderDe
         }
         s_start[tid] = nm & ~eq;
         s_eq[tid] = eq;
+        if (!list) atomicAdd(&s_runs, (u32)__popcll(nm & ~eq));    /* coding every span of the batch: tell the host how many were not dense */
         bool redo = (nm & eq) == ~0ull;                     /* a run covers the whole segment */
         if (tid == 0 && (nm & eq & 1ull)) {                  /* a run crosses into the span: where it starts */
             const u8 v0 = sm[lo - sm_lo];
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(S5_THREADS) k_streams5(EncBatchDev b, HeaderDe
     for (u32 k = tid; k < S5_BLOCKS * nstreams; k += S5_THREADS) { tab[k] = (unsigned short)RL_NONE; if (two) tbytes[k] = 0; }
     for (u32 k = tid; k < nstreams; k += S5_THREADS) s_first[k] = NONE32;
     __syncthreads();
+    if (!list && tid == 0 && s_runs <= (u32)RL_CAP) atomicAdd(job.dense_count, 1u);     /* a span k_streams4 would have coded itself */
     if (s_redo) {
         if (tid == 0) { const u32 at = atomicAdd(job.redo_count, 1u); job.redo_list[at] = span; }
         return;
