@@ -179,6 +179,7 @@ def test_window_cut_and_blank_lines(codec):
 
 
 def test_library_really_ran_on_gpu(codec):
+    parity.check_encode_golden(codec, "kat_pe")              # the statistics are those of the last call
     s = codec.stats()
     assert s.launches > 0
     assert os.path.basename(_lib.LIB_PATH) == "librepaq_b200.so"
