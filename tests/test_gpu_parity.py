@@ -167,6 +167,8 @@ def test_dense_quality_spans(monkeypatch):
             for name in ("nova_pe_k1000", "bgi_se_varlen_k100", "nova_se_late_quality", "nova_pe_k100_npos"):
                 parity.check_encode_golden(cd, name)
             E._dense_cases(cd, None)
+            if knob == "1":
+                E.test_dense_hint_follows_the_data(cd)
         finally:
             cd.close()
 
