@@ -49,12 +49,18 @@ def sass_lines(kernel):
 def main():
     rep, kernel = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    # a report may hold many kernels: take the first launch of the one asked for
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:^%s$" % kernel, "--launch-count", "1"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hi]
     col = {n: i for i, n in enumerate(hdr)}
-    body = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    body = []
+    for r in rows[hi + 1:]:
+        if r and r[0] == "Address":
+            break                                            # the next launch of the same kernel
+        if len(r) == len(hdr):
+            body.append(r)
     sass = sass_lines(kernel)
     if len(sass) != len(body):
         print("warning: %d instructions in the capture, %d in the library (stale build?)" % (len(body), len(sass)))
