@@ -99,6 +99,31 @@ def cpu_reference_roundtrip(r1, r2, cores, budget_s=None):
                 encode_gbs=total / 1e9 / t_enc, decode_gbs=total / 1e9 / t_dec, seconds=t_enc + t_dec)
 
 
+def bind_near_gpu(gpu):
+    """Runs this rank on the CPUs that are local to its GPU (NVML's affinity mask), so that the pinned buffers it allocates and the
+    threads that feed the copies sit on the GPU's side of the host: with several ranks per host the e2e path is bound by host memory
+    and the PCIe fabric, and a rank on the wrong socket pays for every byte twice.  RPQ_BENCH_NUMA=0 leaves the affinity alone.
+    Returns the previous affinity (restored before the CPU baseline is timed), or None."""
+    if os.environ.get("RPQ_BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = int(vis.split(",")[gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        words = nv.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        near = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        old = os.sched_getaffinity(0)
+        want = near & old
+        if len(want) >= 2 and want != old:
+            os.sched_setaffinity(0, want)
+            return old
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region, sampled in-process through NVML (pynvml) every ~2 ms by a
     thread: the default timed region lasts ~80 ms, too short for `nvidia-smi -lms` to land a sample in it reliably.  Only
@@ -268,6 +293,7 @@ def main():
     from repaq_b200 import codec as K
     from tools import fqgen
 
+    old_affinity = bind_near_gpu(local)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -543,6 +569,8 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
+    if old_affinity is not None:
+        os.sched_setaffinity(0, old_affinity)              # the CPU baseline gets every core of the box
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = host_cores()
         n_pairs = min(args.pairs, 33340 * cores)
@@ -555,7 +583,8 @@ def main():
                     config=dict(workload="configs[1]+[2]: paired-end NovaSeq-shape 150bp, %.2f GB FASTQ per GPU (R1+R2), encode to .rfq then decode back" % (fastq_bytes / 1e9),
                                 pairs_per_gpu=rows * fqgen.ROW_READS, chunk_kb=1000, rfq_bytes_per_gpu=rfq_b, rfq_ratio=rfq_b / fastq_bytes,
                                 l2="inputs (GBs) far larger than the 126 MB L2; no flush needed", generator="tools/fqgen.c seed 2", gen_seconds=round(gen_s, 1),
-                                parallelism="chunk-sharded, one process per GPU; NCCL all_gather of per-chunk lengths only"),
+                                parallelism="chunk-sharded, one process per GPU; NCCL all_gather of per-chunk lengths only",
+                                host_affinity="CPUs local to the rank's GPU (NVML)" if old_affinity is not None else "unchanged"),
                     encode_gbs=job_bytes * args.steps / 1e9 / (enc_ms / 1e3), decode_gbs=job_bytes * args.steps / 1e9 / (dec_ms / 1e3),
                     wall_ms_per_step=wall_ms / args.steps, gpu_launches=int(launches),
                     decode_chunk_walk={1: "one warp on the mSize chain", 2: "16 warps on the mSize chain (k_dec_walk_par)", 3: "exact sequential walk"}.get(state.get("dec_walk"), "host"), clocks=clk, e2e=e2e, roofline=roofline, cpu_baseline=cpu)

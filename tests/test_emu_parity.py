@@ -186,14 +186,16 @@ def _dense_cases(cd, lib_path):
         lines[4 * rec + 3] = bytes(q)
     q = bytearray(lines[3]); q[0:2] = bytes([q[0]]) * 2; lines[3] = bytes(q)      # Q16: a run over positions 0 and 1 of the chunk
     parity.check_against_oracle(cd, b"\n".join(lines), k=100)
-    # 56 quality values: more streams than two [block][stream] tables have room for (k_streams5 then uses one for both purposes)
+    # 56 quality values: more streams than two [block][stream] tables have room for (k_streams5 then uses one for both purposes);
+    # 42: the most that two tables hold, i.e. the largest shared-memory footprint of the kernel
     r1, _ = fqgen.generate(12000, seed=8, shape=fqgen.BGI)
-    lines = bytes(r1).split(b"\n")
-    rnd = np.random.RandomState(4)
-    for rec in range((len(lines) - 1) // 4):
-        q = np.frombuffer(lines[4 * rec + 3], dtype=np.uint8)
-        lines[4 * rec + 3] = (35 + (q.astype(np.int32) + rnd.randint(0, 56, q.size)) % 56).astype(np.uint8).tobytes()
-    parity.check_against_oracle(cd, b"\n".join(lines), k=100)
+    for nvalues in (56, 42):
+        lines = bytes(r1).split(b"\n")
+        rnd = np.random.RandomState(4)
+        for rec in range((len(lines) - 1) // 4):
+            q = np.frombuffer(lines[4 * rec + 3], dtype=np.uint8)
+            lines[4 * rec + 3] = (35 + (q.astype(np.int32) + rnd.randint(0, nvalues, q.size)) % nvalues).astype(np.uint8).tobytes()
+        parity.check_against_oracle(cd, b"\n".join(lines), k=100)
 
 
 def test_dense_quality_spans(monkeypatch):
