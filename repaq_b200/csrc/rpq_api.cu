@@ -107,7 +107,7 @@ struct rpq_ctx {
     bool copy_stream_ok = false;
     cudaStream_t side_stream = 0;          /* decode: the fill of the quality plane, under the chunk walk and the table kernels */
     bool side_stream_ok = false;
-    RtEvent side_ev;
+    RtEvent side_ev, fork_ev;              /* work on the side stream done; the point of the main stream it may start from */
     RtEvent win_ev[16], cp_ev[16];
     void* pinned_small = nullptr;          /* 64 KiB scratch for scalar read-backs */
     DevBuf host_out, host_out2;            /* pinned host buffers for results */
@@ -159,6 +159,13 @@ inline void prof_end(rpq_ctx* c) { if (c->profiling) rt_event_record(&c->prof.ba
 
 #define LAUNCH(ctx, kern, grid, block, smem, ...)                                           \
     do { if ((grid) > 0) { prof_begin(ctx, #kern); RPQ_LAUNCH(kern, grid, block, smem, (ctx)->stream, __VA_ARGS__); prof_end(ctx); (ctx)->launches++; } } while (0)
+
+/* the context's second stream (created on first use): decode fills the quality plane on it, encode runs kernels there that do
+ * not depend on what the main stream is busy with */
+bool side_ready(rpq_ctx* c) {
+    if (!c->side_stream_ok && !rt_stream_create(&c->side_stream)) { c->side_stream_ok = true; rt_event_create(&c->side_ev); rt_event_create(&c->fork_ev); }
+    return c->side_stream_ok;
+}
 
 int check_launch(rpq_ctx* c, const char* where) {
     char buf[256];
@@ -240,7 +247,7 @@ extern "C" void rpq_destroy(rpq_ctx* c) {
     for (rpq_ctx* l : c->lanes) rpq_destroy(l);
     c->lanes.clear();
     if (c->copy_stream_ok) { rt_stream_sync(c->copy_stream); rt_stream_destroy(c->copy_stream); for (auto& e : c->win_ev) rt_event_destroy(&e); for (auto& e : c->cp_ev) rt_event_destroy(&e); }
-    if (c->side_stream_ok) { rt_stream_sync(c->side_stream); rt_stream_destroy(c->side_stream); rt_event_destroy(&c->side_ev); }
+    if (c->side_stream_ok) { rt_stream_sync(c->side_stream); rt_stream_destroy(c->side_stream); rt_event_destroy(&c->side_ev); rt_event_destroy(&c->fork_ev); }
     DevBuf* all[] = {&c->loc, &c->pk, &c->pk_rc, &c->text[0], &c->text[1], &c->nl[0], &c->nl[1], &c->tile_state, &c->counters, &c->rlen, &c->unit_bases, &c->prefix, &c->scan_tmp,
                      &c->ustats, &c->chunk_first, &c->chunks, &c->meta, &c->meta0, &c->ov, &c->seqoff, &c->qualoff, &c->n1off, &c->n2off, &c->soff,
                      &c->errbits, &c->tmpx, &c->tmpy, &c->span_first[0], &c->span_first[1], &c->span_chunk[0], &c->span_chunk[1], &c->dir[0], &c->dir[1],
