@@ -98,6 +98,7 @@ struct ChunkDev {
         off_qual, off_ov, off_npos;
     u32 bytes;            /* serialised size */
     u32 r1_end, r2_end;   /* text offsets just past the last record's final line break */
+    u32 pad0;             /* explicit: the table is copied to the host word by word (no uninitialised padding) */
     u64 out_offset;
 };
 
