@@ -112,6 +112,11 @@ static int do_compress(const Opt& o) {
     return 0;
 }
 
+/* Repaq::decompress / decompressPE (src/repaq.cpp:262-413).  The .rfq is decoded in windows of whole chunks (1 GiB of .rfq by
+ * default, RPQ_CLI_RFQ_WINDOW=<bytes> for tests), so that device and pinned host memory stay bounded whatever the file size.
+ * Whether a chunk is the LAST one of the file (the trailing-newline rule) is only known once the bytes after it have failed to
+ * decode as a chunk, so the last chunk of a window that is not the end of the file is held back and decoded again as the first
+ * chunk of the next window. */
 static int do_decompress(const Opt& o) {
     std::vector<char> rfq = slurp(o.in1);
     char err[768]; rpq_header h; size_t used = 0;
@@ -121,33 +126,47 @@ static int do_decompress(const Opt& o) {
     rpq_ctx* ctx = NULL;
     if (rpq_create(o.device, &ctx)) error_exit("no CUDA device: repaq_b200 has no CPU fallback");
     if (rpq_set_header(ctx, &h)) error_exit(rpq_last_error(ctx));
-    rpq_decode_in in; memset(&in, 0, sizeof in);
-    in.data = (const uint8_t*)rfq.data() + used; in.bytes = rfq.size() - used; in.mem = RPQ_MEM_HOST; in.out_mem = RPQ_MEM_HOST; in.split_pairs = pe;
-    rpq_decode_out res;
-    if (rpq_decode(ctx, &in, &res)) error_exit(rpq_last_error(ctx));
-    if (!pe) {
-        /* Repaq::decompress: only a flagged LAST chunk loses its final newline */
-        uint64_t n = res.out1_bytes;
-        if (res.n_chunks && (res.chunks[res.n_chunks - 1].flags & RPQ_NO_LINE_BREAK_AT_END) && n) n--;
-        spill(o.out1, res.out1, n, false);
-    } else {
-        /* Repaq::decompressPE incl. its `continue` (src/repaq.cpp:395,405): after a flagged chunk that is not the last one,
-         * the rest of that chunk's output and the whole next chunk are never written */
-        spill(o.out1, NULL, 0, false); spill(o.out2, NULL, 0, false);
+    uint64_t window = 1ull << 30;
+    if (const char* e = getenv("RPQ_CLI_RFQ_WINDOW")) { const uint64_t w = strtoull(e, NULL, 10); if (w) window = w; }
+    spill(o.out1, NULL, 0, false);
+    if (pe) spill(o.out2, NULL, 0, false);
+    uint64_t at = used;
+    bool skip_first = false;                               /* decompressPE's `continue`: the chunk after a flagged one is never written */
+    while (at < rfq.size()) {
+        const uint64_t n = rfq.size() - at < window ? rfq.size() - at : window;
+        const bool final = at + n == rfq.size();
+        rpq_decode_in in; memset(&in, 0, sizeof in);
+        in.data = (const uint8_t*)rfq.data() + at; in.bytes = n; in.mem = RPQ_MEM_HOST; in.out_mem = RPQ_MEM_HOST; in.split_pairs = pe;
+        rpq_decode_out res;
+        if (rpq_decode(ctx, &in, &res)) error_exit(rpq_last_error(ctx));
+        if (!final && res.n_chunks < 2) { window *= 2; continue; }          /* a window must hold a chunk to write and one to hold back */
+        if (res.n_chunks == 0) break;                                       /* what is left is not a chunk: the reference stops here too */
+        const uint32_t n_keep = final ? res.n_chunks : res.n_chunks - 1;
         uint64_t a1 = 0, a2 = 0;
-        for (uint32_t i = 0; i < res.n_chunks; i++) {
+        for (uint32_t i = 0; i < n_keep; i++) {
             const rpq_chunk_info& c = res.chunks[i];
-            const bool f1 = c.flags & RPQ_NO_LINE_BREAK_AT_END, f2 = c.flags & RPQ_NO_LINE_BREAK_AT_END_R2, last = i + 1 == res.n_chunks;
-            bool skip_next = false;
-            if (f1) { if (last) spill(o.out1, res.out1 + a1, c.out1_bytes ? c.out1_bytes - 1 : 0, true); else { spill(o.out1, res.out1 + a1, c.out1_bytes, true); skip_next = true; } }
-            else spill(o.out1, res.out1 + a1, c.out1_bytes, true);
-            if (!skip_next) {
-                if (f2) { if (last) spill(o.out2, res.out2 + a2, c.out2_bytes ? c.out2_bytes - 1 : 0, true); else { spill(o.out2, res.out2 + a2, c.out2_bytes, true); skip_next = true; } }
-                else spill(o.out2, res.out2 + a2, c.out2_bytes, true);
+            const bool last = final && i + 1 == res.n_chunks;
+            const bool f1 = (c.flags & RPQ_NO_LINE_BREAK_AT_END) != 0, f2 = (c.flags & RPQ_NO_LINE_BREAK_AT_END_R2) != 0;
+            if (skip_first) { skip_first = false; a1 += c.out1_bytes; a2 += c.out2_bytes; continue; }
+            if (!pe) {
+                /* Repaq::decompress: only a flagged LAST chunk loses its final newline */
+                spill(o.out1, res.out1 + a1, (f1 && last && c.out1_bytes) ? c.out1_bytes - 1 : c.out1_bytes, true);
+            } else {
+                /* Repaq::decompressPE incl. its `continue` (src/repaq.cpp:395,405): after a flagged chunk that is not the last one,
+                 * the rest of that chunk's output and the whole next chunk are never written */
+                bool skip_next = false;
+                if (f1) { if (last) spill(o.out1, res.out1 + a1, c.out1_bytes ? c.out1_bytes - 1 : 0, true); else { spill(o.out1, res.out1 + a1, c.out1_bytes, true); skip_next = true; } }
+                else spill(o.out1, res.out1 + a1, c.out1_bytes, true);
+                if (!skip_next) {
+                    if (f2) { if (last) spill(o.out2, res.out2 + a2, c.out2_bytes ? c.out2_bytes - 1 : 0, true); else { spill(o.out2, res.out2 + a2, c.out2_bytes, true); skip_next = true; } }
+                    else spill(o.out2, res.out2 + a2, c.out2_bytes, true);
+                }
+                skip_first = skip_next;
             }
             a1 += c.out1_bytes; a2 += c.out2_bytes;
-            if (skip_next && i + 1 < res.n_chunks) { i++; a1 += res.chunks[i].out1_bytes; a2 += res.chunks[i].out2_bytes; }
         }
+        if (final) break;
+        at += res.chunks[res.n_chunks - 1].offset;                          /* the held-back chunk starts the next window */
     }
     rpq_destroy(ctx);
     return 0;

@@ -88,3 +88,23 @@ def test_cli_verify_emulated(tmp_path):
 @pytest.mark.gpu
 def test_cli_verify_gpu(tmp_path):
     run_verify(GPU_CLI, tmp_path)
+
+
+@pytest.mark.parametrize("name", ["nova_pe_k100_npos", "nova_pe_nonl_k100", "nova_pe_nonl_r2only_k100", "nova_se_nonl_k100", "nova_se_k100", "pe_demoted_mid_k100", "one_pair"])
+def test_cli_decompress_in_windows(tmp_path, monkeypatch, name):
+    """`-d` decodes the .rfq in windows of whole chunks (here: tiny ones, a few chunks each); the last chunk of a window is held back
+    because only the end of the file tells whether it is the file's last one (trailing-newline rule, and decompressPE's skip)"""
+    import hashlib
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
+    m = MAN[name]
+    (tmp_path / "x.rfq").write_bytes(golden_rfq(name))
+    for window in ("30000", "70000", "1"):
+        monkeypatch.setenv("RPQ_CLI_RFQ_WINDOW", window)
+        subprocess.check_call([EMU_CLI, "-d", "-i", str(tmp_path / "x.rfq"), "-o", str(tmp_path / "d.fq")])
+        d = (tmp_path / "d.fq").read_bytes()
+        assert (len(d), hashlib.sha256(d).hexdigest()) == (m["dec_len"], m["dec_sha256"]), window
+        if "dec1_sha256" in m:
+            subprocess.check_call([EMU_CLI, "-d", "-i", str(tmp_path / "x.rfq"), "-o", str(tmp_path / "d1.fq"), "-O", str(tmp_path / "d2.fq")])
+            d1, d2 = (tmp_path / "d1.fq").read_bytes(), (tmp_path / "d2.fq").read_bytes()
+            assert (len(d1), hashlib.sha256(d1).hexdigest()) == (m["dec1_len"], m["dec1_sha256"]), window
+            assert (len(d2), hashlib.sha256(d2).hexdigest()) == (m["dec2_len"], m["dec2_sha256"]), window
