@@ -183,8 +183,10 @@ static int do_compare(const Opt& o) {
     rpq_ctx* ctx = NULL;
     if (rpq_create(o.device, &ctx)) error_exit("no CUDA device: repaq_b200 has no CPU fallback");
     if (rpq_set_header(ctx, &h)) error_exit(rpq_last_error(ctx));
-    const uint64_t FQ_WIN = 3ull << 30;                    /* < 4 GiB of text per file and call */
+    uint64_t FQ_WIN = 3ull << 30;                          /* < 4 GiB of text per file and call */
     uint64_t rfq_win = 256ull << 20;                       /* chunks decoded per call: ~2 GB of FASTQ at the usual ratios */
+    if (const char* e = getenv("RPQ_CLI_RFQ_WINDOW")) { const uint64_t w = strtoull(e, NULL, 10); if (w) rfq_win = w; }      /* tests: small windows */
+    if (const char* e = getenv("RPQ_CLI_FQ_WINDOW")) { const uint64_t w = strtoull(e, NULL, 10); if (w) FQ_WIN = w; }
     uint64_t at = used, a = 0, b = 0;
     unsigned long long fq_reads = 0, fq_bases = 0, rfq_reads = 0, rfq_bases = 0;
     bool passed = false; std::string msg;
@@ -198,8 +200,9 @@ static int do_compare(const Opt& o) {
         in.fq_offset[0] = a; in.fq_offset[1] = b;
         rpq_compare_out res;
         if (rpq_compare(ctx, &in, &res)) error_exit(rpq_last_error(ctx));
-        if (res.verdict == RPQ_CMP_NEED_FASTQ) {           /* these chunks decode to more reads than 3 GiB of text hold: fewer chunks per call */
-            if (rfq_win <= (4ull << 20)) error_exit("compare: a batch of chunks does not fit the FASTQ window");
+        if (res.verdict == RPQ_CMP_NEED_FASTQ) {           /* these chunks decode to more reads than the window of text holds: more text, or fewer chunks */
+            if (FQ_WIN < (3ull << 30)) { FQ_WIN = FQ_WIN * 2 < (3ull << 30) ? FQ_WIN * 2 : (3ull << 30); continue; }
+            if (rfq_win <= (1ull << 20)) error_exit("compare: a batch of chunks does not fit the FASTQ window");
             rfq_win /= 2; continue;
         }
         fq_reads += res.fastq_reads; fq_bases += res.fastq_bases; rfq_reads += res.rfq_reads; rfq_bases += res.rfq_bases;
@@ -224,6 +227,10 @@ static int do_compare(const Opt& o) {
         if (in.rfq_final) at = rfq.size();                 /* whatever follows the last whole chunk is not a chunk: the reference stops there too */
         else if (res.rfq_consumed == 0) { if (rfq_win >= (2ull << 30)) error_exit("compare: a chunk does not fit the batch window"); rfq_win *= 2; continue; }
         if (at == rfq.size() && in.fq_final) { passed = true; break; }
+        if (res.rfq_consumed == 0 && res.r1_consumed == 0 && !in.fq_final) {          /* the chunks are through and this window of text holds no whole record */
+            if (FQ_WIN >= (3ull << 30)) error_exit("compare: a record does not fit the FASTQ window");
+            FQ_WIN = FQ_WIN * 2 < (3ull << 30) ? FQ_WIN * 2 : (3ull << 30);
+        }
     }
     std::string json = "{\n";
     json += passed ? "\t\"result\":\"passed\",\n" : "\t\"result\":\"failed\",\n";

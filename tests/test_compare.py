@@ -150,3 +150,15 @@ def test_gpu_compare_at_size(gpu_codec):
     rep = json.loads(K.compare(rfq, r1, bad, codec=gpu_codec), strict=False)
     assert rep["result"] == "failed" and rep["msg"].startswith("The RFQ file and FASTQ file have different quality in the 300001 pair. ")
     assert rep["rfq_reads"] == 600002 == rep["fastq_reads"] and rep["rfq_bases"] == 600002 * 150
+
+
+@pytest.mark.parametrize("name", ["same_nova_pe_k1000", "same_nova_se_k100", "pe_seq_r1", "pe_name_r2", "pe_strand_r1_chunk1", "pe_fastq_shorter", "pe_fastq_longer", "pe_fastq_shorter_r2_only",
+                                  "se_qual_longer", "se_fastq_longer", "se_fastq_shorter", "se_no_final_newline", "same_pe_demoted_mid_k100", "same_nova_pe_300bp_varlen_k100"])
+@pytest.mark.parametrize("windows", [("40000", "300000"), ("400000", "5000"), ("1", "1")])
+def test_cli_compare_in_batches(tmp_path, monkeypatch, name, windows):
+    """the driver's compare loop over batches of chunks and windows of FASTQ text (files beyond 4 GiB), here with windows of a few
+    chunks / a few records / less than one of either: the report must not depend on how the files were cut"""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
+    monkeypatch.setenv("RPQ_CLI_RFQ_WINDOW", windows[0])
+    monkeypatch.setenv("RPQ_CLI_FQ_WINDOW", windows[1])
+    run_cli(EMU_CLI, tmp_path, name)
