@@ -73,7 +73,8 @@ static int do_compress(const Opt& o) {
     uint64_t from1, from2 = UINT64_MAX; bool t1, t2 = false;
     nobreak_rule(r1, from1, t1);
     if (two) nobreak_rule(r2, from2, t2); else if (o.interleaved) { from2 = from1; t2 = t1; }
-    const uint64_t WIN = 3ull << 30;                       /* < 4 GiB of text per file and call */
+    uint64_t WIN = 3ull << 30;                             /* < 4 GiB of text per file and call */
+    if (const char* e = getenv("RPQ_CLI_FQ_WINDOW")) { const uint64_t w = strtoull(e, NULL, 10); if (w) WIN = w; }      /* tests: small batches */
     uint64_t a = 0, b = 0;
     rpq_ctx* check = NULL;                                 /* -v / -f: the reference's codec4check */
     for (;;) {
@@ -104,7 +105,11 @@ static int do_compress(const Opt& o) {
                 fprintf(stderr, "integrity check failure \nexpected: \n%.*s\ngot:\n%.*s\n", (int)co.fastq_field_len, co.fastq_field, (int)co.rfq_field_len, co.rfq_field);
         }
         if (in.final) break;
-        if (res.r1_consumed == 0) error_exit("a chunk does not fit the 3 GiB batch window; lower --chunk");
+        if (res.r1_consumed == 0) {                        /* no whole chunk in this batch */
+            if (WIN >= (3ull << 30)) error_exit("a chunk does not fit the 3 GiB batch window; lower --chunk");
+            WIN = WIN * 2 < (3ull << 30) ? WIN * 2 : (3ull << 30);
+            continue;
+        }
         a += res.r1_consumed; b += res.r2_consumed;
     }
     if (check) rpq_destroy(check);

@@ -108,3 +108,23 @@ def test_cli_decompress_in_windows(tmp_path, monkeypatch, name):
             d1, d2 = (tmp_path / "d1.fq").read_bytes(), (tmp_path / "d2.fq").read_bytes()
             assert (len(d1), hashlib.sha256(d1).hexdigest()) == (m["dec1_len"], m["dec1_sha256"]), window
             assert (len(d2), hashlib.sha256(d2).hexdigest()) == (m["dec2_len"], m["dec2_sha256"]), window
+
+
+@pytest.mark.parametrize("name", ["nova_pe_k100_npos", "nova_pe_nonl_k100", "nova_pe_nonl_r2only_k100", "nova_se_nonl_k100", "nova_se_k100", "nova_pe_crlf_k100", "nova_pe_varlen_k100",
+                                  "pe_demoted_lastpair_k100", "nova_interleaved_in_k100", "bgi_se_k100"])
+@pytest.mark.parametrize("window", ["300000", "170001", "1"])
+def test_cli_compress_in_batches(tmp_path, monkeypatch, name, window):
+    """`-c` feeds the library batches of text (3 GiB per file in production, here a few chunks, or less than one so that the window
+    has to grow) and continues where the last whole chunk ended: the .rfq must not depend on where the batches were cut"""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
+    monkeypatch.setenv("RPQ_CLI_FQ_WINDOW", window)
+    c = CASES[name]
+    (tmp_path / "a.fq").write_bytes(c["r1"])
+    cmd = [EMU_CLI, "-c", "-i", str(tmp_path / "a.fq"), "-o", str(tmp_path / "o.rfq"), "-k", str(c["k"])]
+    if c["r2"] is not None:
+        (tmp_path / "b.fq").write_bytes(c["r2"])
+        cmd += ["-I", str(tmp_path / "b.fq")]
+    if c["interleaved"]:
+        cmd += ["--interleaved_in"]
+    subprocess.check_call(cmd)
+    assert (tmp_path / "o.rfq").read_bytes() == golden_rfq(name)
