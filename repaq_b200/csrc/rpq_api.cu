@@ -93,6 +93,7 @@ struct rpq_ctx {
     u64 stats_redo_spans = 0;              /* spans k_streams4 handed to k_streams3 */
     int index_variant = 1;                 /* 1: CTA-per-tile indexer (default, 1.13 ms per 3.4 GB); RPQ_DEBUG_INDEX=0: persistent CTAs (1.31 ms) */
     u32 fmt_reads = 0;                     /* RPQ_DEBUG_FMT_READS=n: reads per formatter CTA (tuning experiments) */
+    bool dec_streams2 = false;             /* RPQ_DEC_STREAMS=2: k_dec_streams2 (CTA per stream) instead of k_dec_streams (warp per stream); not measured on a GPU yet */
     bool no_par_walk = false;              /* RPQ_DEBUG_NO_PAR_WALK=1: the chunk chain of a device-resident body is followed by one warp (A/B) */
     u64 par_walk_min = 0;                  /* RPQ_DEBUG_PAR_WALK_MIN=<bytes>: smallest body the parallel walk is used for (tests) */
     bool force_v1 = false;                 /* RPQ_DEBUG_FORCE_V1=1: take the long-read fallback kernels (test coverage) */
@@ -214,6 +215,7 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     memset(&c->hdr, 0, sizeof c->hdr);
     memset(&c->last_dec, 0, sizeof c->last_dec);
     { const char* e = getenv("RPQ_DEBUG_FORCE_V1"); c->force_v1 = e && e[0] == '1'; }
+    { const char* e = getenv("RPQ_DEC_STREAMS"); c->dec_streams2 = e && e[0] == '2'; }
     { const char* e = getenv("RPQ_DEBUG_NO_PAR_WALK"); c->no_par_walk = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_DEBUG_PAR_WALK_MIN"); c->par_walk_min = e ? strtoull(e, nullptr, 10) : (32ull << 20); }
     { const char* e = getenv("RPQ_DEBUG_INDEX"); c->index_variant = e ? atoi(e) : 1; }

@@ -418,3 +418,22 @@ def test_dense_hint_follows_the_data(codec):
     sparse, _ = fqgen.generate(16000, seed=12)
     for data in (dense, dense, sparse, sparse, dense):
         parity.check_against_oracle(codec, data, k=1000)
+
+
+def test_dec_streams_cta_variant(monkeypatch):
+    """RPQ_DEC_STREAMS=2: k_dec_streams2 (a CTA per stream: token heads from a scan of 4-state maps, positions from a scan of
+    advances) must decode exactly like the default warp-per-stream kernel: golden files (N positions, exceptions, 38 streams, long
+    reads) and streams of many 4 KiB steps against the oracle"""
+    from tools import fqgen
+    monkeypatch.setenv("RPQ_DEC_STREAMS", "2")
+    cd = K.Codec(lib_path=EMU)
+    try:
+        for name in ("nova_pe_k1000", "nova_pe_k100_npos", "bgi_se_k100", "nova_se_late_quality", "nova_pe_300bp_varlen_k100", "kat_pe", "one_read", "names_mixed",
+                     "nova_pe_nonl_k100", "pe_demoted_mid_k100"):
+            parity.check_decode_golden(cd, name)
+        r1, r2 = fqgen.generate(9000, seed=61, paired=True)
+        parity.check_against_oracle(cd, r1, r2)
+        b1, _ = fqgen.generate(30000, seed=62, shape=fqgen.BGI)
+        parity.check_against_oracle(cd, b1)
+    finally:
+        cd.close()
