@@ -427,20 +427,22 @@ __global__ void __launch_bounds__(32 * DS_WARPS) k_dec_streams(DecBatchDev b, He
 }
 
 /*
- * k_dec_streams2 (not the default yet: RPQ_DEC_STREAMS=2): the same decoder with a CTA per (chunk, stream), 16 stream bytes per
- * thread, 4 KiB per step.  k_dec_streams gives a stream to one warp, and a launch takes the time of its longest stream however
+ * k_dec_streams2 (not the default: RPQ_DEC_STREAMS=2): the same decoder with a CTA per (chunk, stream), 32 stream bytes per
+ * thread, 8 KiB per step, the next step's words in flight during a step.  k_dec_streams gives a stream to one warp, and a launch takes the time of its longest stream however
  * few chunks there are (0.8 ms for 180 chunks, 1.7 ms for 1430: profiles/README.md r01_v10); here 8 warps share every stream.
- *   1. every thread tabulates, for its 16 bytes, "first token head at byte e  ->  payload bytes that spill into the next thread"
- *      for e = 0..3 (a backward pass over the 16 token lengths, 2 bits per byte packed in one word): an 8-bit map of the 4 states
+ *   1. every thread tabulates, for its 32 bytes, "first token head at byte e  ->  payload bytes that spill into the next thread"
+ *      for e = 0..3 (a backward pass over the 32 token lengths, 2 bits per byte packed in one 64-bit word): an 8-bit map of the 4 states
  *   2. inclusive scan of the maps under composition (warp shuffles, then the 8 warp totals through shared memory): every thread
  *      knows where its first head is
  *   3. the thread walks its tokens once for the sum of their advances; an exclusive scan of the sums gives its first position
  *   4. it walks them again and writes: single positions, runs of up to 32, or N bits
- * A thread keeps its 20 bytes (16 + 3 of look-ahead) in five shared words of its own (stride 5 words: no bank conflicts, no
- * barrier between staging and use).  grid (chunks, streams).
+ * A thread keeps its 36 bytes (32 + look-ahead) in nine shared words of its own (stride 9 words: no bank conflicts, no barrier
+ * between staging and use).  grid (chunks, streams).  First measurement (16 bytes per thread, no prefetch): 2.41 ms against
+ * 1.71 ms for k_dec_streams (profiles/README.md r01_v12); this version has not been on a GPU yet.
  */
 constexpr int DS2_THREADS = 256;
-constexpr u32 DS2_BPT = 16, DS2_STEP = DS2_THREADS * DS2_BPT;
+constexpr u32 DS2_BPT = 32, DS2_STEP = DS2_THREADS * DS2_BPT;     /* stream bytes per thread and per step (8 KiB) */
+constexpr u32 DS2_WORDS = DS2_BPT / 4 + 1;                        /* a thread's window: its bytes + 4 of look-ahead; odd: conflict-free stride */
 constexpr u32 DS2_IDENT = 0xE4u;                                 /* state s -> s, s = 0..3 */
 __device__ __forceinline__ u32 ds2_compose(u32 f, u32 g) {       /* first f, then g */
     return ((g >> (2u * (f & 3u))) & 3u) | (((g >> (2u * ((f >> 2) & 3u))) & 3u) << 2) | (((g >> (2u * ((f >> 4) & 3u))) & 3u) << 4) |
@@ -450,7 +452,7 @@ __device__ __forceinline__ u32 ds2_tlen(u32 b0) { return !(b0 & 0x80u) ? 1u : !(
 
 __global__ void __launch_bounds__(DS2_THREADS) k_dec_streams2(DecBatchDev b, HeaderDev h, u32 n_qstreams, u32 chunk_base, u32 chunk_end, const u32* __restrict__ order) {
     constexpr int NW = DS2_THREADS / 32;
-    __shared__ u32 s_slot[DS2_THREADS * 5];
+    __shared__ u32 s_slot[DS2_THREADS * DS2_WORDS];
     __shared__ u32 s_wmap[NW], s_wadv[NW];
     const u32 c = chunk_base + blockIdx.x, st = order[blockIdx.y];
     if (c >= chunk_end) return;
@@ -482,40 +484,45 @@ __global__ void __launch_bounds__(DS2_THREADS) k_dec_streams2(DecBatchDev b, Hea
     const u32 nmap_bits = ((ck.seq_kept + 31) / 32 + 1) * 32;
     const u32 lim_pos = is_npos ? (nmap_bits < dst_len ? nmap_bits : dst_len) : dst_len;      /* positions >= this are ignored (Q20) */
     const u32* Aend = reinterpret_cast<const u32*>((reinterpret_cast<uintptr_t>(b.body + b.body_len) + 3u) & ~(uintptr_t)3);
-    u32* sw = s_slot + 5 * tid;
-    const u8* sb = reinterpret_cast<const u8*>(sw);
+    u32* sw = s_slot + DS2_WORDS * tid;
+    /* the aligned words that cover this thread's window of step `base` */
+    auto fetch = [&](u32 base, u32* w) {
+        const u32 p0 = base + DS2_BPT * (u32)tid;
+        const uintptr_t ga = reinterpret_cast<uintptr_t>(stream + p0);
+        const u32* A = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
+#pragma unroll
+        for (u32 k = 0; k <= DS2_WORDS; k++) w[k] = (p0 < slen && A + k < Aend) ? A[k] : 0u;
+    };
     u32 state = 0;                                        /* payload bytes of the previous step's last token still to come */
     u32 next = 0;                                         /* 1 + the position of the last element so far */
+    u32 wcur[DS2_WORDS + 1], wnext[DS2_WORDS + 1];
+    fetch(0, wcur);
     for (u32 base = 0; base < slen; base += DS2_STEP) {
-        /* ---- this thread's bytes [p0, p0 + 20): six aligned words, funnel-shifted; bytes past the stream read as 0 */
+        if (base + DS2_STEP < slen) fetch(base + DS2_STEP, wnext);          /* in flight while this step is scanned */
+        /* ---- this thread's bytes [p0, p0 + 4 * DS2_WORDS): funnel-shifted to its slot; bytes past the stream read as 0 */
         const u32 p0 = base + DS2_BPT * (u32)tid;
         const u32 left = p0 < slen ? slen - p0 : 0u;
         const u32 nv = left < DS2_BPT ? left : DS2_BPT;
         {
-            const uintptr_t ga = reinterpret_cast<uintptr_t>(stream + p0);
-            const u32* A = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
-            const u32 sh = 8u * (u32)(ga & 3u);
-            u32 w[6];
+            const u32 sh = 8u * (u32)(reinterpret_cast<uintptr_t>(stream + p0) & 3u);
 #pragma unroll
-            for (int k = 0; k < 6; k++) w[k] = (left && A + k < Aend) ? A[k] : 0u;
-#pragma unroll
-            for (int k = 0; k < 5; k++) {
-                u32 v = __funnelshift_r(w[k], w[k + 1], sh);
-                const u32 lo = 4u * (u32)k;               /* bytes [lo, lo + 4) of the window */
+            for (u32 k = 0; k < DS2_WORDS; k++) {
+                u32 v = __funnelshift_r(wcur[k], wcur[k + 1], sh);
+                const u32 lo = 4u * k;                    /* bytes [lo, lo + 4) of the window */
                 if (left < lo + 4u) v = left > lo ? v & ((1u << (8u * (left - lo))) - 1u) : 0u;
                 sw[k] = v;
             }
         }
-        /* ---- 1: exit state of a token that starts at byte i, for i = 15 .. 0 (2 bits each) */
-        u32 E = 0;
+        /* ---- 1: exit state of a token that starts at byte i, for i = BPT-1 .. 0 (2 bits each) */
+        u64 E = 0;
 #pragma unroll
         for (int i = (int)DS2_BPT - 1; i >= 0; i--) {
             const u32 b0 = (sw[i >> 2] >> (8 * (i & 3))) & 0xFFu;
             const u32 t = (u32)i + ds2_tlen(b0);
-            const u32 v = t >= DS2_BPT ? t - DS2_BPT : (E >> (2u * t)) & 3u;
-            E |= v << (2 * i);
+            const u32 v = t >= DS2_BPT ? t - DS2_BPT : (u32)(E >> (2u * t)) & 3u;
+            E |= (u64)v << (2 * i);
         }
-        const u32 map = nv == DS2_BPT ? (E & 0xFFu) : DS2_IDENT;            /* threads at / past the end of the stream: nothing follows them */
+        const u32 map = nv == DS2_BPT ? ((u32)E & 0xFFu) : DS2_IDENT;        /* threads at / past the end of the stream: nothing follows them */
         /* ---- 2: where this thread's first head is */
         u32 inc = map;
 #pragma unroll
@@ -573,8 +580,9 @@ __global__ void __launch_bounds__(DS2_THREADS) k_dec_streams2(DecBatchDev b, Hea
                 }
             }
         }
+#pragma unroll
+        for (u32 k = 0; k <= DS2_WORDS; k++) wcur[k] = wnext[k];
     }
-    (void)sb;
 }
 
 /* ------------------------------------------------------------------ record formatter ---- */
