@@ -73,3 +73,19 @@ def test_product_library_is_cuda_only():
     data = open(_lib.LIB_PATH, "rb").read()
     assert b"emu_switch" not in data and b"orc_compress" not in data
     assert b"k_streams" in data            # the CUDA kernels are in there
+
+
+def test_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: include/repaq_b200.h must compile as C99 (plain pointers and sizes, no C++ / CUDA / torch types),
+    and the ctypes mirrors in repaq_b200/_lib.py must have the sizes the C compiler gives the structs"""
+    import ctypes as C
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "repaq_b200.h"\nint main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(rpq_header), sizeof(rpq_encode_in), '
+                   'sizeof(rpq_chunk_info), sizeof(rpq_encode_out), sizeof(rpq_decode_in), sizeof(rpq_decode_out), sizeof(rpq_compare_in), sizeof(rpq_compare_out), sizeof(rpq_stats)); return 0; }\n')
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    from repaq_b200 import _lib
+    mirrors = [_lib.Header, _lib.EncodeIn, _lib.ChunkInfo, _lib.EncodeOut, _lib.DecodeIn, _lib.DecodeOut, _lib.CompareIn, _lib.CompareOut, _lib.Stats]
+    assert sizes == [C.sizeof(m) for m in mirrors]
