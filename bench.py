@@ -440,6 +440,8 @@ def main():
         "k_meta3": head_b + (16 + 44) * n_reads,                                 # record heads in, ReadMeta + packed read out
         "k_streams3": qual_b + 0.6 * rfq_b, "k_streams4": qual_b + 0.6 * rfq_b,  # qualities in, tokens out
         "k_dec_format3": rfq_b + qual_b + fastq_bytes,                           # columns + quality plane in, text out
+        "k_dec_format4": rfq_b + fastq_bytes,                                    # columns (streams included) in, text out
+        "k_dec_qindex": 0.3 * rfq_b,                                             # position streams in, checkpoints out
         "k_dec_coords3": (1 + 8) * n_reads, "k_dec_reads": 48 * n_reads, "k_chunk_finish": 44 * n_reads,
         "k_coords": 9 * n_reads,
     }

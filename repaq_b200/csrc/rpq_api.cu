@@ -19,7 +19,7 @@
 #include "rpq_meta3.cuh"
 #include "rpq_decode.cuh"
 #include "rpq_decode2.cuh"
-#include "rpq_decode3.cuh"
+#include "rpq_decode4.cuh"
 #include "rpq_compare.cuh"
 #include "rpq_host.h"
 
@@ -31,37 +31,6 @@ namespace rpq {
  * (a decoder returning gigabytes of FASTQ beside this encoder), and the host waits for every one of these read-backs. */
 __global__ void __launch_bounds__(256) k_fetch(const u32* __restrict__ src, u32* __restrict__ dst, u32 nwords) {
     for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < nwords; k += gridDim.x * blockDim.x) dst[k] = src[k];
-}
-/* Fill with a byte by a FEW CTAs (16-byte stores): the decoder's quality plane is filled under the chunk walk, a single warp
- * chasing one header per chunk; a copy-engine memset at full HBM speed next to it made every hop of that chain wait in the memory
- * queues (0.68 -> 1.14 ms, profiles/README.md r01_v10), a fill that takes a fraction of the bandwidth does not. */
-__global__ void __launch_bounds__(256) k_fill(uint4* __restrict__ dst, unsigned long long n16, u32 v4) {
-    const uint4 v = make_uint4(v4, v4, v4, v4);
-    const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; k + 3 * nthreads < n16; k += 4 * nthreads) { dst[k] = v; dst[k + nthreads] = v; dst[k + 2 * nthreads] = v; dst[k + 3 * nthreads] = v; }
-    for (; k < n16; k += nthreads) dst[k] = v;
-}
-/* Optional (RPQ_D2H=sm): bulk results leave the same way, a few CTAs streaming 16-byte stores over PCIe (posted writes,
- * 512 contiguous bytes per warp instruction), so that the copy engines only carry host-to-device traffic.  Measured beside an
- * encoder it is slower than the copy engine with one window queued at a time (28.3 against 30.7 GB/s end to end,
- * profiles/README.md r01_v9), so the copy engine is the default.  src and dst must be congruent modulo 16. */
-__global__ void __launch_bounds__(256) k_push(const u8* __restrict__ src, u8* __restrict__ dst, unsigned long long n) {
-    const unsigned long long head = (16u - (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u)) & 15u;
-    const unsigned long long h = head < n ? head : n;
-    const unsigned long long n16 = (n - h) / 16;
-    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (unsigned long long)gridDim.x * blockDim.x;
-    if (tid < h) dst[tid] = src[tid];
-    const uint4* s4 = reinterpret_cast<const uint4*>(src + h);
-    uint4* d4 = reinterpret_cast<uint4*>(dst + h);
-    unsigned long long k = tid;
-    for (; k + 3 * nthreads < n16; k += 4 * nthreads) {                 /* four loads in flight per thread */
-        const uint4 a = s4[k], b = s4[k + nthreads], c = s4[k + 2 * nthreads], d = s4[k + 3 * nthreads];
-        d4[k] = a; d4[k + nthreads] = b; d4[k + 2 * nthreads] = c; d4[k + 3 * nthreads] = d;
-    }
-    for (; k < n16; k += nthreads) d4[k] = s4[k];
-    const unsigned long long done = h + 16 * n16;
-    if (tid < n - done) dst[done + tid] = src[done + tid];
 }
 }  // namespace rpq
 
@@ -84,7 +53,7 @@ struct rpq_ctx {
     /* grow-only device buffers */
     DevBuf loc, pk, pk_rc, text[2], nl[2], tile_state, counters, rlen, unit_bases, prefix, scan_tmp, ustats, chunk_first, chunks, meta, meta0, ov,
         seqoff, qualoff, n1off, n2off, soff, errbits, tmpx, tmpy, span_first[2], span_chunk[2], dir[2], slots[2], span_slot[2], span_read0[2], redo_list[2], dense_list, misc, out,
-        d_in, d_desc, d_tmp[8], d_tmp2, out2, d_slabs;
+        d_in, d_desc, d_tmp[8], d_tmp2, out2, d_slabs, d_ckpt;
     int streams5 = 1;                      /* RPQ_DEBUG_STREAMS5=0: dense quality spans go to k_streams3 (A/B); =2: k_streams5 codes every quality span (test coverage) */
     bool no_streams4 = false;              /* RPQ_DEBUG_NO_STREAMS4=1: k_streams3 codes every span (test coverage, A/B) */
     bool dense_hint = false;               /* most quality spans of the last batch were dense: the next one goes to k_streams5 directly (k_streams4 would stage
@@ -93,20 +62,16 @@ struct rpq_ctx {
     u64 stats_redo_spans = 0;              /* spans k_streams4 handed to k_streams3 */
     int index_variant = 1;                 /* 1: CTA-per-tile indexer (default, 1.13 ms per 3.4 GB); RPQ_DEBUG_INDEX=0: persistent CTAs (1.31 ms) */
     u32 fmt_reads = 0;                     /* RPQ_DEBUG_FMT_READS=n: reads per formatter CTA (tuning experiments) */
-    bool dec_streams2 = false;             /* RPQ_DEC_STREAMS=2: k_dec_streams2 (CTA per stream) instead of k_dec_streams (warp per stream); not measured on a GPU yet */
     bool no_par_walk = false;              /* RPQ_DEBUG_NO_PAR_WALK=1: the chunk chain of a device-resident body is followed by one warp (A/B) */
     u64 par_walk_min = 0;                  /* RPQ_DEBUG_PAR_WALK_MIN=<bytes>: smallest body the parallel walk is used for (tests) */
     bool force_v1 = false;                 /* RPQ_DEBUG_FORCE_V1=1: take the long-read fallback kernels (test coverage) */
-    bool d2h_sm = false;                   /* RPQ_D2H=sm: bulk results leave through k_push (SM stores) instead of the copy engines; measured slower (profiles/README.md r01_v9) */
-    u32 push_ctas = 32;                    /* RPQ_PUSH_CTAS=n */
-    u32 fill_ctas = 64;                    /* RPQ_FILL_CTAS=n: CTAs of the plane fill that runs under the chunk walk (0: copy-engine memset after the tables) */
     u32 d2h_depth = 1;                     /* RPQ_D2H_DEPTH=n: windows of decoded FASTQ whose copies may be queued at a time (0: wait for each) */
     bool no_pipeline = false;              /* RPQ_NO_PIPELINE=1: host batches are never cut into pipelined windows */
     uint64_t pipe_window = 0;              /* RPQ_DEBUG_PIPE_WINDOW=<bytes>: window size of the pipelined host path (tests) */
     std::vector<rpq_ctx*> lanes;           /* sub-contexts (own stream + buffers) of the pipelined host path */
     cudaStream_t copy_stream = 0;          /* decode: device-to-host copies of finished windows */
     bool copy_stream_ok = false;
-    cudaStream_t side_stream = 0;          /* decode: the fill of the quality plane, under the chunk walk and the table kernels */
+    cudaStream_t side_stream = 0;          /* decode: the stream checkpoints (k_dec_qindex) beside the table kernels */
     bool side_stream_ok = false;
     RtEvent side_ev, fork_ev;              /* work on the side stream done; the point of the main stream it may start from */
     RtEvent win_ev[16], cp_ev[16];
@@ -215,7 +180,6 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     memset(&c->hdr, 0, sizeof c->hdr);
     memset(&c->last_dec, 0, sizeof c->last_dec);
     { const char* e = getenv("RPQ_DEBUG_FORCE_V1"); c->force_v1 = e && e[0] == '1'; }
-    { const char* e = getenv("RPQ_DEC_STREAMS"); c->dec_streams2 = e && e[0] == '2'; }
     { const char* e = getenv("RPQ_DEBUG_NO_PAR_WALK"); c->no_par_walk = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_DEBUG_PAR_WALK_MIN"); c->par_walk_min = e ? strtoull(e, nullptr, 10) : (32ull << 20); }
     { const char* e = getenv("RPQ_DEBUG_INDEX"); c->index_variant = e ? atoi(e) : 1; }
@@ -223,10 +187,7 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     { const char* e = getenv("RPQ_DEBUG_NO_STREAMS4"); c->no_streams4 = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_DEBUG_FMT_READS"); c->fmt_reads = e ? (u32)atoi(e) : 0u; }
     { const char* e = getenv("RPQ_NO_PIPELINE"); c->no_pipeline = e && e[0] == '1'; }
-    { const char* e = getenv("RPQ_D2H"); c->d2h_sm = e && e[0] == 's'; }
     { const char* e = getenv("RPQ_D2H_DEPTH"); if (e) c->d2h_depth = (u32)atoi(e) > 8u ? 8u : (u32)atoi(e); }
-    { const char* e = getenv("RPQ_FILL_CTAS"); if (e) c->fill_ctas = (u32)atoi(e); }
-    { const char* e = getenv("RPQ_PUSH_CTAS"); if (e && atoi(e) > 0) c->push_ctas = (u32)atoi(e); }
     { const char* e = getenv("RPQ_DEBUG_PIPE_WINDOW"); c->pipe_window = e ? strtoull(e, nullptr, 10) : 0; }
 #ifndef RPQ_EMU
     cudaFuncSetAttribute(k_index_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, IDX_SMEM);
@@ -236,7 +197,7 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     cudaFuncSetAttribute(k_streams4, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_streams5, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024);    /* 214.1 KB at 43 streams (two tables), + 7.2 KB static <= 227 KB */
     cudaFuncSetAttribute(k_meta3, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(k_dec_format3, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
+    cudaFuncSetAttribute(k_dec_format4, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
 #endif
     *out = c;
     return RPQ_OK;
@@ -253,7 +214,7 @@ extern "C" void rpq_destroy(rpq_ctx* c) {
     DevBuf* all[] = {&c->loc, &c->pk, &c->pk_rc, &c->text[0], &c->text[1], &c->nl[0], &c->nl[1], &c->tile_state, &c->counters, &c->rlen, &c->unit_bases, &c->prefix, &c->scan_tmp,
                      &c->ustats, &c->chunk_first, &c->chunks, &c->meta, &c->meta0, &c->ov, &c->seqoff, &c->qualoff, &c->n1off, &c->n2off, &c->soff,
                      &c->errbits, &c->tmpx, &c->tmpy, &c->span_first[0], &c->span_first[1], &c->span_chunk[0], &c->span_chunk[1], &c->dir[0], &c->dir[1],
-                     &c->slots[0], &c->slots[1], &c->span_slot[0], &c->span_slot[1], &c->span_read0[0], &c->span_read0[1], &c->redo_list[0], &c->redo_list[1], &c->dense_list, &c->misc, &c->out, &c->d_in, &c->d_desc, &c->out2, &c->d_slabs,
+                     &c->slots[0], &c->slots[1], &c->span_slot[0], &c->span_slot[1], &c->span_read0[0], &c->span_read0[1], &c->redo_list[0], &c->redo_list[1], &c->dense_list, &c->misc, &c->out, &c->d_in, &c->d_desc, &c->out2, &c->d_slabs, &c->d_ckpt,
                      &c->d_tmp2, &c->d_tmp[0], &c->d_tmp[1], &c->d_tmp[2], &c->d_tmp[3], &c->d_tmp[4], &c->d_tmp[5], &c->d_tmp[6], &c->d_tmp[7]};
     for (DevBuf* b : all) rt_free_device(b->p);
     rt_free_pinned(c->pinned_small);
@@ -316,13 +277,10 @@ template <class T> int read_back(rpq_ctx* c, const void* dev, T* host, size_t co
     return RPQ_OK;
 }
 
-/* bulk device -> pinned host on `stream`: k_push or the copy engine */
+/* bulk device -> pinned host on `stream` */
 int push_to_host(rpq_ctx* c, void* host, const void* dev, size_t bytes, cudaStream_t stream) {
+    (void)c;
     if (!bytes) return 0;
-    if (c->d2h_sm && ((reinterpret_cast<uintptr_t>(host) ^ reinterpret_cast<uintptr_t>(dev)) & 15u) == 0) {
-        RPQ_LAUNCH(k_push, c->push_ctas, 256, 0, stream, (const u8*)dev, (u8*)host, (unsigned long long)bytes);
-        return 0;
-    }
     return rt_memcpy_d2h(host, dev, bytes, stream);
 }
 

@@ -7,7 +7,7 @@
  * reference's order (read, then field) is the minimum of a 64-bit key.
  */
 #pragma once
-#include "rpq_decode3.cuh"
+#include "rpq_decode4.cuh"
 #include "rpq_index.cuh"
 
 namespace rpq {

@@ -426,165 +426,6 @@ __global__ void __launch_bounds__(32 * DS_WARPS) k_dec_streams(DecBatchDev b, He
     }
 }
 
-/*
- * k_dec_streams2 (not the default: RPQ_DEC_STREAMS=2): the same decoder with a CTA per (chunk, stream), 32 stream bytes per
- * thread, 8 KiB per step, the next step's words in flight during a step.  k_dec_streams gives a stream to one warp, and a launch takes the time of its longest stream however
- * few chunks there are (0.8 ms for 180 chunks, 1.7 ms for 1430: profiles/README.md r01_v10); here 8 warps share every stream.
- *   1. every thread tabulates, for its 32 bytes, "first token head at byte e  ->  payload bytes that spill into the next thread"
- *      for e = 0..3 (a backward pass over the 32 token lengths, 2 bits per byte packed in one 64-bit word): an 8-bit map of the 4 states
- *   2. inclusive scan of the maps under composition (warp shuffles, then the 8 warp totals through shared memory): every thread
- *      knows where its first head is
- *   3. the thread walks its tokens once for the sum of their advances; an exclusive scan of the sums gives its first position
- *   4. it walks them again and writes: single positions, runs of up to 32, or N bits
- * A thread keeps its 36 bytes (32 + look-ahead) in nine shared words of its own (stride 9 words: no bank conflicts, no barrier
- * between staging and use).  grid (chunks, streams).  First measurement (16 bytes per thread, no prefetch): 2.41 ms against
- * 1.71 ms for k_dec_streams (profiles/README.md r01_v12); this version has not been on a GPU yet.
- */
-constexpr int DS2_THREADS = 256;
-constexpr u32 DS2_BPT = 32, DS2_STEP = DS2_THREADS * DS2_BPT;     /* stream bytes per thread and per step (8 KiB) */
-constexpr u32 DS2_WORDS = DS2_BPT / 4 + 1;                        /* a thread's window: its bytes + 4 of look-ahead; odd: conflict-free stride */
-constexpr u32 DS2_IDENT = 0xE4u;                                 /* state s -> s, s = 0..3 */
-__device__ __forceinline__ u32 ds2_compose(u32 f, u32 g) {       /* first f, then g */
-    return ((g >> (2u * (f & 3u))) & 3u) | (((g >> (2u * ((f >> 2) & 3u))) & 3u) << 2) | (((g >> (2u * ((f >> 4) & 3u))) & 3u) << 4) |
-           (((g >> (2u * ((f >> 6) & 3u))) & 3u) << 6);
-}
-__device__ __forceinline__ u32 ds2_tlen(u32 b0) { return !(b0 & 0x80u) ? 1u : !(b0 & 0x40u) ? 2u : !(b0 & 0x20u) ? 1u : 4u; }
-
-__global__ void __launch_bounds__(DS2_THREADS) k_dec_streams2(DecBatchDev b, HeaderDev h, u32 n_qstreams, u32 chunk_base, u32 chunk_end, const u32* __restrict__ order) {
-    constexpr int NW = DS2_THREADS / 32;
-    __shared__ u32 s_slot[DS2_THREADS * DS2_WORDS];
-    __shared__ u32 s_wmap[NW], s_wadv[NW];
-    const u32 c = chunk_base + blockIdx.x, st = order[blockIdx.y];
-    if (c >= chunk_end) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const DecChunk& ck = b.chunks[c];
-    const u8* in = b.body + ck.in_off;
-    const u8* stream; u32 slen; u8 q; bool is_npos = false;
-    if (st < n_qstreams) {
-        if (h.flags & RPQ_DONT_ENCODE_QUAL) return;
-        const u8* qcol = in + ck.off_qual;
-        u32 off = 4u * h.nb;
-        if ((u64)off > ck.qual_size) return;
-        for (u32 k = 0; k < st && k < h.nb; k++) off += ld32(qcol + 4 * k);
-        if (st == h.nb) {
-            /* exceptions: {q, u32 LE pos} until the end of the column (src/rfqcodec.cpp:1034-1043) */
-            u8* plane = b.plane + ck.plane_off;
-            for (u64 p = (u64)off + 5ull * tid; p + 5 <= ck.qual_size; p += 5ull * DS2_THREADS) { const u32 pos = ld32(qcol + p + 1); if (pos < ck.total_len) plane[pos] = qcol[p]; }
-            return;
-        }
-        stream = qcol + off; slen = ld32(qcol + 4 * st); q = h.normal_bins[st];
-        if ((u64)off + slen > ck.qual_size) slen = ck.qual_size > off ? ck.qual_size - off : 0;
-    } else {
-        if (!(h.flags & RPQ_ENCODE_N_POS)) return;
-        stream = in + ck.off_npos; slen = ck.npos_size; q = 'N'; is_npos = true;
-    }
-    const u32 dst_len = ck.total_len;
-    u8* plane = b.plane + ck.plane_off;
-    u32* nmap = b.nmap + ck.nmap_off;
-    const u32 nmap_bits = ((ck.seq_kept + 31) / 32 + 1) * 32;
-    const u32 lim_pos = is_npos ? (nmap_bits < dst_len ? nmap_bits : dst_len) : dst_len;      /* positions >= this are ignored (Q20) */
-    const u32* Aend = reinterpret_cast<const u32*>((reinterpret_cast<uintptr_t>(b.body + b.body_len) + 3u) & ~(uintptr_t)3);
-    u32* sw = s_slot + DS2_WORDS * tid;
-    /* the aligned words that cover this thread's window of step `base` */
-    auto fetch = [&](u32 base, u32* w) {
-        const u32 p0 = base + DS2_BPT * (u32)tid;
-        const uintptr_t ga = reinterpret_cast<uintptr_t>(stream + p0);
-        const u32* A = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
-#pragma unroll
-        for (u32 k = 0; k <= DS2_WORDS; k++) w[k] = (p0 < slen && A + k < Aend) ? A[k] : 0u;
-    };
-    u32 state = 0;                                        /* payload bytes of the previous step's last token still to come */
-    u32 next = 0;                                         /* 1 + the position of the last element so far */
-    u32 wcur[DS2_WORDS + 1], wnext[DS2_WORDS + 1];
-    fetch(0, wcur);
-    for (u32 base = 0; base < slen; base += DS2_STEP) {
-        if (base + DS2_STEP < slen) fetch(base + DS2_STEP, wnext);          /* in flight while this step is scanned */
-        /* ---- this thread's bytes [p0, p0 + 4 * DS2_WORDS): funnel-shifted to its slot; bytes past the stream read as 0 */
-        const u32 p0 = base + DS2_BPT * (u32)tid;
-        const u32 left = p0 < slen ? slen - p0 : 0u;
-        const u32 nv = left < DS2_BPT ? left : DS2_BPT;
-        {
-            const u32 sh = 8u * (u32)(reinterpret_cast<uintptr_t>(stream + p0) & 3u);
-#pragma unroll
-            for (u32 k = 0; k < DS2_WORDS; k++) {
-                u32 v = __funnelshift_r(wcur[k], wcur[k + 1], sh);
-                const u32 lo = 4u * k;                    /* bytes [lo, lo + 4) of the window */
-                if (left < lo + 4u) v = left > lo ? v & ((1u << (8u * (left - lo))) - 1u) : 0u;
-                sw[k] = v;
-            }
-        }
-        /* ---- 1: exit state of a token that starts at byte i, for i = BPT-1 .. 0 (2 bits each) */
-        u64 E = 0;
-#pragma unroll
-        for (int i = (int)DS2_BPT - 1; i >= 0; i--) {
-            const u32 b0 = (sw[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-            const u32 t = (u32)i + ds2_tlen(b0);
-            const u32 v = t >= DS2_BPT ? t - DS2_BPT : (u32)(E >> (2u * t)) & 3u;
-            E |= (u64)v << (2 * i);
-        }
-        const u32 map = nv == DS2_BPT ? ((u32)E & 0xFFu) : DS2_IDENT;        /* threads at / past the end of the stream: nothing follows them */
-        /* ---- 2: where this thread's first head is */
-        u32 inc = map;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const u32 prev = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = ds2_compose(prev, inc); }
-        if (lane == 31) s_wmap[warp] = inc;
-        u32 exm = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) exm = DS2_IDENT;
-        __syncthreads();
-        u32 e_warp = state, e_all = state;
-#pragma unroll
-        for (int k = 0; k < NW; k++) { const u32 m = s_wmap[k]; e_all = (m >> (2u * e_all)) & 3u; if (k < warp) e_warp = e_all; }
-        state = e_all;
-        const u32 e_in = (exm >> (2u * e_warp)) & 3u;
-        /* ---- 3: the sum of this thread's advances */
-        auto token = [&](u32 i, u32& adv, u32& run) {
-            const u32 wi = i >> 2, shb = 8u * (i & 3u);
-            const u32 t = __funnelshift_r(sw[wi], sw[wi + 1], shb);      /* the token's bytes, first byte lowest */
-            const u32 b0 = t & 0xFFu;
-            run = 0;
-            if (!(b0 & 0x80u)) adv = b0 + 1u;
-            else if (!(b0 & 0x40u)) adv = (((b0 & 0x3Fu) << 8) | ((t >> 8) & 0xFFu)) + 1u;
-            else if (!(b0 & 0x20u)) { run = (b0 & 0x1Fu) + 1u; adv = run; }
-            else adv = (((b0 & 0x1Fu) << 24) | (((t >> 8) & 0xFFu) << 16) | (((t >> 16) & 0xFFu) << 8) | ((t >> 24) & 0xFFu)) + 1u;
-            return ds2_tlen(b0);
-        };
-        u32 sum = 0;
-        for (u32 i = e_in; i < nv;) { u32 adv, run; i += token(i, adv, run); sum += adv; }
-        u32 wtot; const u32 ex = warp_excl_scan(sum, lane, wtot);
-        if (lane == 0) s_wadv[warp] = wtot;
-        __syncthreads();
-        u32 acc = next + ex, total = 0;
-#pragma unroll
-        for (int k = 0; k < NW; k++) { const u32 t = s_wadv[k]; if (k < warp) acc += t; total += t; }
-        next += total;
-        /* ---- 4: the positions */
-        for (u32 i = e_in; i < nv;) {
-            u32 adv, run; i += token(i, adv, run);
-            const u32 end1 = acc + adv;                                  /* 1 + the position of the token's last element */
-            acc = end1;
-            const u32 first = run ? end1 - run : end1 - 1u;
-            const u32 stop = end1 < lim_pos ? end1 : lim_pos;
-            if (first < stop) {
-                const u32 n = stop - first;
-                if (is_npos) { for (u32 j = 0; j < n; j++) { const u32 pos = first + j; atomicOr(&nmap[pos >> 5], 1u << (pos & 31)); } }
-                else {
-                    u8* d = plane + first;
-                    d[0] = q; if (n > 1) d[1] = q; if (n > 2) d[2] = q; if (n > 3) d[3] = q;
-                    if (n > 4u) {
-                        u8* w = d + 4; u8* const we = d + n;
-                        while (w < we && (reinterpret_cast<uintptr_t>(w) & 3u)) *w++ = q;
-                        const u32 q4 = 0x01010101u * q;
-                        for (; w + 4 <= we; w += 4) *reinterpret_cast<u32*>(w) = q4;
-                        while (w < we) *w++ = q;
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (u32 k = 0; k <= DS2_WORDS; k++) wcur[k] = wnext[k];
-    }
-}
-
 /* ------------------------------------------------------------------ record formatter ---- */
 constexpr int FMT_WARPS = 8;
 

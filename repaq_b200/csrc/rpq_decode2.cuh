@@ -1,17 +1,11 @@
 /*
- * rpq_decode2.cuh - second-generation decode helpers: the launch configuration of the thread-per-read formatter
- * (k_dec_format3, rpq_decode3.cuh), the warp-cooperative coordinate decoder and the two-step device chunk walk.
+ * rpq_decode2.cuh - second-generation decode helpers: the CTA-per-stream coordinate decoder and the two-step device chunk
+ * walk.
  */
 #pragma once
 #include "rpq_decode.cuh"
 
 namespace rpq {
-
-struct Fmt2Cfg {
-    u32 reads_per_cta;     /* = blockDim.x */
-    u32 plane_cap;         /* shared bytes for the staged quality plane (incl. 16 bytes of alignment slack) */
-    u32 out_cap;           /* shared bytes per output stream staging (incl. 16 bytes of alignment slack) */
-};
 
 }  // namespace rpq
 
