@@ -21,6 +21,8 @@ extern "C" {
 #endif
 
 #define RPQ_OK 0
+#define RPQ_NO_RECORDS 1           /* rpq_make_header: the input holds no record; the reference then writes an EMPTY output file and
+                                     exits 0 (src/repaq.cpp:530-638: nothing is flushed, not even the header) */
 #define RPQ_ERR_CUDA (-1)          /* CUDA runtime / launch failure, or no device */
 #define RPQ_ERR_ARG (-2)           /* bad argument / header not set */
 #define RPQ_ERR_NOMEM (-3)
@@ -96,7 +98,7 @@ void* rpq_stream(rpq_ctx* ctx);
 /* ---- encode: Repaq::compress/compressPE's chunk loop (src/repaq.cpp:546-553,656-663) + RfqCodec::encodeChunk
  * (src/rfqcodec.cpp:147-586) + RfqChunk::write (src/rfqchunk.cpp:230-312) for every chunk of a FASTQ batch. */
 typedef struct rpq_encode_in {
-    const char* r1; uint64_t r1_len;      /* FASTQ text, '\n' or "\r\n" line ends; < 4 GiB per call */
+    const char* r1; uint64_t r1_len;      /* FASTQ text, line breaks as the reference's reader takes them ('\n', '\r', "\r\n"); < 4 GiB per call */
     const char* r2; uint64_t r2_len;      /* mate file, or NULL */
     int mem;                              /* RPQ_MEM_HOST (pageable or pinned) or RPQ_MEM_DEVICE */
     int interleaved;                      /* r1 holds R1,R2,R1,R2,... (--interleaved_in) */
@@ -107,10 +109,10 @@ typedef struct rpq_encode_in {
     uint64_t nobreak_from[2];
     uint16_t tail_flags;                  /* OR-ed into the trailing partial chunk only */
     int out_mem;                          /* where the serialised chunks are wanted: RPQ_MEM_HOST or RPQ_MEM_DEVICE */
-    /* offsets of r1 / r2 inside their files (0: the text starts where the file starts).  Only "\r\n" files need them: the
-     * reference's reader refills a 1 MiB buffer and reads a "\r\n" whose '\n' is the last byte of a buffer or the first of the
-     * next as a line end followed by an EMPTY line, where it ends its input (src/fastqreader.cpp:113-116, :180-181): such a file is
-     * refused (RPQ_ERR_FASTQ) instead of being encoded differently from the reference. */
+    /* offsets of r1 / r2 inside their files (0: the text starts where the file starts).  The reference's reader refills a 1 MiB
+     * buffer and does not take a '\n' that is the first or the last byte of a buffer as the second byte of a line break
+     * (src/fastqreader.cpp:113-116): a "\r\n" there reads as a line end followed by an EMPTY line, where the reader ends its input
+     * (:180-181).  The line index reproduces that, so it needs to know where the buffers lie. */
     uint64_t file_offset[2];
 } rpq_encode_in;
 
@@ -123,7 +125,8 @@ typedef struct rpq_chunk_info {
     uint16_t flags;         /* mFlags */
     uint32_t seq_size, qual_size, npos_size, x_size, y_size;
     uint32_t name1_size, name2_size, strand_size;
-    uint64_t r1_end, r2_end;   /* encode: text offsets just past the chunk's last record */
+    uint64_t r1_end, r2_end;   /* encode: text offset of the first line-break character after the chunk's last record (what Q13 compares
+                                  with nobreak_from); to continue after a batch use rpq_encode_out.r?_consumed, not these */
     uint64_t out1_bytes, out2_bytes;   /* decode: FASTQ bytes this chunk decodes to (R1 / R2 stream) */
 } rpq_chunk_info;
 

@@ -15,6 +15,7 @@ import numpy as np
 from . import _lib
 
 NEVER = (1 << 64) - 1
+NO_RECORDS = 1
 MIB = 1 << 20
 
 NO_LINE_BREAK_AT_END = 1 << 10
@@ -41,15 +42,18 @@ def _buf(x):
 
 
 def make_header(r1, r2=None, interleaved=False, chunk_bases=1000000, lib_path=None):
-    """RfqCodec::makeHeader on the records of the first chunk (host code, as in the reference)."""
+    """RfqCodec::makeHeader on the records of the first chunk (host code, as in the reference).  None: the input holds no
+    record (the reference then writes an empty output, src/repaq.cpp:530-638)."""
     L = _lib.load(lib_path)
     h = _lib.Header()
     err = C.create_string_buffer(512)
     p1, l1, k1 = _buf(r1)
     p2, l2, k2 = _buf(r2)
     if p1 is None:
-        raise RepaqError(-4, "failed to encode, please confirm the input FASTQ file is valid and not empty")
+        return None
     rc = L.rpq_make_header(p1, l1, p2, l2, int(interleaved), chunk_bases, C.byref(h), err, 512)
+    if rc == NO_RECORDS:
+        return None
     if rc:
         raise RepaqError(rc, err.value.decode(errors="replace"))
     return h
@@ -209,7 +213,13 @@ def compare(rfq, r1, r2=None, codec=None, device=0, lib_path=None):
     own = codec is None
     codec = codec or Codec(device, lib_path)
     try:
-        h, used = parse_header(rfq, codec.lib_path)
+        if len(rfq) == 0:
+            # an empty .rfq reads as a default header without chunks (src/rfqheader.cpp:7-43): any header will do for zero chunks
+            h, used = _lib.Header(), 0
+            h.read_length_bytes, h.flags, h.n_base_qual, h.overlap_shift, h.qual_bins = 1, 1 << 7, ord("#"), -24, 1
+            h.qual_buf[0] = ord("F")
+        else:
+            h, used = parse_header(rfq, codec.lib_path)
         codec.set_header(h)
         body = np.frombuffer(rfq, dtype=np.uint8)[used:]
         pb, nb, kb = _buf(body)
@@ -248,6 +258,8 @@ def compress(r1, r2=None, k=1000, interleaved=False, codec=None, device=0, lib_p
     codec = codec or Codec(device, lib_path)
     try:
         h = make_header(r1, r2, interleaved, chunk_bases, lib_path=codec.lib_path)
+        if h is None:
+            return b""                                         # no record: nothing is written, not even the header
         codec.set_header(h)
         a1 = np.frombuffer(r1, dtype=np.uint8) if not isinstance(r1, np.ndarray) else r1
         t1, tail1 = nobreak_rule(a1.size, int(a1[-1]) if a1.size else 0)
@@ -271,6 +283,11 @@ def compress(r1, r2=None, k=1000, interleaved=False, codec=None, device=0, lib_p
 
 def decompress(rfq, pe_out=False, codec=None, device=0, lib_path=None):
     """.rfq file image -> FASTQ image(s), like `repaq -d -i x.rfq -o out1 [-O out2]`."""
+    if len(rfq) == 0:
+        # RfqHeader::read on an empty stream leaves the constructor's defaults (single end, no chunks): src/rfqheader.cpp:7-43
+        if pe_out:
+            raise RepaqError(-2, "The input RFQ file was encoded by single-end FASTQ, you should not specify <out2>")
+        return b""
     own = codec is None
     codec = codec or Codec(device, lib_path)
     try:

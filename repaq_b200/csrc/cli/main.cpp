@@ -63,7 +63,9 @@ static int do_compress(const Opt& o) {
     const uint32_t chunk_bases = (uint32_t)(o.k < 100 ? 100 : o.k) * 1000u;        /* src/main.cpp:69 */
     char err[768];
     rpq_header h;
-    if (rpq_make_header(r1.data(), r1.size(), two ? r2.data() : NULL, r2.size(), o.interleaved, chunk_bases, &h, err, sizeof err)) error_exit(err);
+    const int hrc = rpq_make_header(r1.data(), r1.size(), two ? r2.data() : NULL, r2.size(), o.interleaved, chunk_bases, &h, err, sizeof err);
+    if (hrc == RPQ_NO_RECORDS) { spill(o.out1, NULL, 0, false); return 0; }      /* no record: an empty output, as the reference leaves it */
+    if (hrc) error_exit(err);
     uint8_t hb[17 + 128];
     const size_t hn = rpq_header_write(&h, hb, sizeof hb);
     spill(o.out1, hb, hn, false);

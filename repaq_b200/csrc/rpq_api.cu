@@ -53,14 +53,13 @@ struct rpq_ctx {
     /* grow-only device buffers */
     DevBuf loc, pk, pk_rc, text[2], nl[2], tile_state, counters, rlen, unit_bases, prefix, scan_tmp, ustats, chunk_first, chunks, meta, meta0, ov,
         seqoff, qualoff, n1off, n2off, soff, errbits, tmpx, tmpy, span_first[2], span_chunk[2], dir[2], slots[2], span_slot[2], span_read0[2], redo_list[2], dense_list, misc, out,
-        d_in, d_desc, d_tmp[8], d_tmp2, out2, d_slabs, d_ckpt;
+        d_in, d_desc, d_tmp[8], d_tmp2, out2, d_slabs, d_ckpt, d_dir, canon[2], nl2[2], canon_len, canon_pre;
     int streams5 = 1;                      /* RPQ_DEBUG_STREAMS5=0: dense quality spans go to k_streams3 (A/B); =2: k_streams5 codes every quality span (test coverage) */
     bool no_streams4 = false;              /* RPQ_DEBUG_NO_STREAMS4=1: k_streams3 codes every span (test coverage, A/B) */
     bool dense_hint = false;               /* most quality spans of the last batch were dense: the next one goes to k_streams5 directly (k_streams4 would stage
                                               and count every span only to hand it over) */
     u64 stats_dense_spans = 0;             /* spans k_streams4 handed to k_streams5 */
     u64 stats_redo_spans = 0;              /* spans k_streams4 handed to k_streams3 */
-    int index_variant = 1;                 /* 1: CTA-per-tile indexer (default, 1.13 ms per 3.4 GB); RPQ_DEBUG_INDEX=0: persistent CTAs (1.31 ms) */
     u32 fmt_reads = 0;                     /* RPQ_DEBUG_FMT_READS=n: reads per formatter CTA (tuning experiments) */
     bool no_par_walk = false;              /* RPQ_DEBUG_NO_PAR_WALK=1: the chunk chain of a device-resident body is followed by one warp (A/B) */
     u64 par_walk_min = 0;                  /* RPQ_DEBUG_PAR_WALK_MIN=<bytes>: smallest body the parallel walk is used for (tests) */
@@ -157,7 +156,8 @@ void build_header_dev(const rpq_header& h, HeaderDev& d) {
 /* ================================================================== header (host) ==== */
 extern "C" int rpq_make_header(const char* r1, uint64_t r1_len, const char* r2, uint64_t r2_len, int interleaved, uint32_t chunk_bases,
                                rpq_header* out, char* err, size_t err_cap) {
-    if (!r1 || !out) return RPQ_ERR_ARG;
+    if (!out) return RPQ_ERR_ARG;
+    if (!r1 || !r1_len) { if (err && err_cap) snprintf(err, err_cap, "the input holds no FASTQ record"); return RPQ_NO_RECORDS; }
     return host_make_header(r1, r1_len, r2, r2_len, interleaved, chunk_bases, out, err, err_cap);
 }
 extern "C" size_t rpq_header_write(const rpq_header* h, uint8_t* out, size_t cap) { return host_header_write(h, out, cap); }
@@ -182,7 +182,6 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     { const char* e = getenv("RPQ_DEBUG_FORCE_V1"); c->force_v1 = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_DEBUG_NO_PAR_WALK"); c->no_par_walk = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_DEBUG_PAR_WALK_MIN"); c->par_walk_min = e ? strtoull(e, nullptr, 10) : (32ull << 20); }
-    { const char* e = getenv("RPQ_DEBUG_INDEX"); c->index_variant = e ? atoi(e) : 1; }
     { const char* e = getenv("RPQ_DEBUG_STREAMS5"); if (e) c->streams5 = atoi(e); }
     { const char* e = getenv("RPQ_DEBUG_NO_STREAMS4"); c->no_streams4 = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_DEBUG_FMT_READS"); c->fmt_reads = e ? (u32)atoi(e) : 0u; }
@@ -191,7 +190,6 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     { const char* e = getenv("RPQ_DEBUG_PIPE_WINDOW"); c->pipe_window = e ? strtoull(e, nullptr, 10) : 0; }
 #ifndef RPQ_EMU
     cudaFuncSetAttribute(k_index_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, IDX_SMEM);
-    cudaFuncSetAttribute(k_index_lines_tilecta, cudaFuncAttributeMaxDynamicSharedMemorySize, IDX_SMEM_TILECTA);
     cudaFuncSetAttribute(k_streams2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_streams3, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_streams4, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -214,7 +212,7 @@ extern "C" void rpq_destroy(rpq_ctx* c) {
     DevBuf* all[] = {&c->loc, &c->pk, &c->pk_rc, &c->text[0], &c->text[1], &c->nl[0], &c->nl[1], &c->tile_state, &c->counters, &c->rlen, &c->unit_bases, &c->prefix, &c->scan_tmp,
                      &c->ustats, &c->chunk_first, &c->chunks, &c->meta, &c->meta0, &c->ov, &c->seqoff, &c->qualoff, &c->n1off, &c->n2off, &c->soff,
                      &c->errbits, &c->tmpx, &c->tmpy, &c->span_first[0], &c->span_first[1], &c->span_chunk[0], &c->span_chunk[1], &c->dir[0], &c->dir[1],
-                     &c->slots[0], &c->slots[1], &c->span_slot[0], &c->span_slot[1], &c->span_read0[0], &c->span_read0[1], &c->redo_list[0], &c->redo_list[1], &c->dense_list, &c->misc, &c->out, &c->d_in, &c->d_desc, &c->out2, &c->d_slabs, &c->d_ckpt,
+                     &c->slots[0], &c->slots[1], &c->span_slot[0], &c->span_slot[1], &c->span_read0[0], &c->span_read0[1], &c->redo_list[0], &c->redo_list[1], &c->dense_list, &c->misc, &c->out, &c->d_in, &c->d_desc, &c->out2, &c->d_slabs, &c->d_ckpt, &c->d_dir, &c->canon[0], &c->canon[1], &c->nl2[0], &c->nl2[1], &c->canon_len, &c->canon_pre,
                      &c->d_tmp2, &c->d_tmp[0], &c->d_tmp[1], &c->d_tmp[2], &c->d_tmp[3], &c->d_tmp[4], &c->d_tmp[5], &c->d_tmp[6], &c->d_tmp[7]};
     for (DevBuf* b : all) rt_free_device(b->p);
     rt_free_pinned(c->pinned_small);
@@ -292,7 +290,7 @@ int fetch_table(rpq_ctx* c, const void* dev, size_t bytes) {
     return RPQ_OK;
 }
 
-int index_text(rpq_ctx* c, int f, const u8* d_text, u64 len, IndexCounters* hc, bool eof) {
+int index_text(rpq_ctx* c, int f, const u8* d_text, u64 len, u64 file_off, IndexCounters* hc, bool eof) {
     const u32 tiles = (u32)((len + IDX_TILE - 1) / IDX_TILE);
     if (!ensure(c, c->tile_state, sizeof(u64) * (tiles + 1)) || !ensure(c, c->counters, sizeof(IndexCounters) * 2)) return RPQ_ERR_NOMEM;
     size_t cap = (size_t)(len / 16) + 4096;
@@ -302,13 +300,33 @@ int index_text(rpq_ctx* c, int f, const u8* d_text, u64 len, IndexCounters* hc, 
         IndexCounters* dc = c->counters.as<IndexCounters>() + f;
         rt_memset(c->tile_state.p, 0, sizeof(u64) * (tiles + 1), c->stream);
         rt_memset(dc, 0, sizeof(IndexCounters), c->stream);
-        if (c->index_variant == 1) LAUNCH(c, k_index_lines_tilecta, tiles, IDX_THREADS, IDX_SMEM_TILECTA, d_text, len, c->nl[f].as<u32>(), (u32)cap, c->tile_state.as<u64>(), dc);
-        else LAUNCH(c, k_index_lines, std::min<u32>(tiles, 3u * (u32)rt_sm_count()), IDX_THREADS, IDX_SMEM, d_text, len, c->nl[f].as<u32>(), (u32)cap, c->tile_state.as<u64>(), dc, tiles);
+        LAUNCH(c, k_index_lines, tiles, IDX_THREADS, IDX_SMEM, d_text, len, file_off, c->nl[f].as<u32>(), (u32)cap, c->tile_state.as<u64>(), dc);
         LAUNCH(c, k_index_finish, 1, 32, 0, d_text, len, c->nl[f].as<u32>(), (u32)cap, dc, eof ? 1 : 0);
         if (int rc = read_back(c, dc, hc)) return rc;
-        if ((size_t)hc->n_nl + 1 <= cap) return RPQ_OK;
+        if ((size_t)hc->n_nl + 2 <= cap) return RPQ_OK;
         cap = (size_t)hc->n_nl + 16;           /* pathological line density: index again with room for every line */
     }
+    return RPQ_OK;
+}
+
+/* A text with line breaks of one and of two bytes (blank lines the reference's reader swallows, a "\r\n" on an edge of its
+ * buffer, mixed line ends): the lines the reader delivers are copied into a text of plain '\n' breaks, with its own index;
+ * *text / *len are replaced.  The original index stays in c->nl[f] (offsets reported to the caller come from it). */
+int canon_text(rpq_ctx* c, int f, const u8** text, u64* len, IndexCounters* hc) {
+    const u32 n = hc->n_lines;
+    if (!n) return RPQ_OK;
+    if (!ensure(c, c->canon_len, 4 * (size_t)n) || !ensure(c, c->canon_pre, 8 * (size_t)n) || !ensure(c, c->nl2[f], 4 * (size_t)n + 64) ||
+        !ensure(c, c->scan_tmp, rt_scan_tmp_bytes(n)))
+        return RPQ_ERR_NOMEM;
+    LAUNCH(c, k_canon_lens, (n + 255) / 256, 256, 0, *text, *len, (const u32*)c->nl[f].as<u32>(), n, hc->n_nl, c->canon_len.as<u32>());
+    rt_inclusive_sum_u32_u64(c->canon_len.as<u32>(), c->canon_pre.as<u64>(), n, c->scan_tmp.p, c->scan_tmp.cap, c->stream);
+    u64 total = 0;
+    if (int rc = read_back(c, c->canon_pre.as<u64>() + (n - 1), &total)) return rc;
+    if (!ensure(c, c->canon[f], total + 64)) return RPQ_ERR_NOMEM;
+    LAUNCH(c, k_canon_copy, (n + 7) / 8, 256, 0, *text, (const u32*)c->nl[f].as<u32>(), (const u32*)c->canon_len.as<u32>(), (const u64*)c->canon_pre.as<u64>(), n,
+           c->canon[f].as<u8>(), c->nl2[f].as<u32>());
+    *text = c->canon[f].as<u8>(); *len = total;
+    hc->n_nl = n; hc->n_w2 = 0; hc->crlf = 0;
     return RPQ_OK;
 }
 

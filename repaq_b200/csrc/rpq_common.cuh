@@ -54,11 +54,23 @@ struct TextDev {
     u64 len;
     const u32* nl;     /* nl[j] = offset of the '\n' that ends line j (a virtual one at len (+crlf) if the file lacks it) */
     u32 n_lines;
-    u32 crlf;          /* 1: every line ends "\r\n" */
+    u32 crlf;          /* 1: every line break has two bytes ("\r\n") */
+    /* a text with line breaks of both lengths is indexed, then copied line by line into a text of plain '\n' breaks that all later
+     * kernels work on (k_canon_*); these are the original and its index, for offsets that are reported to the caller */
+    const u8* otext;
+    const u32* onl;
 };
 
 __device__ __forceinline__ u32 line_start(const TextDev& t, u32 j) { return j == 0 ? 0u : t.nl[j - 1] + 1u; }
 __device__ __forceinline__ u32 line_end(const TextDev& t, u32 j) { return t.nl[j] - t.crlf; }
+/* offset, in the text the caller passed, of the first break character after line j / of the last byte of that break */
+__device__ __forceinline__ u32 caller_break_last(const TextDev& t, u32 j) { return t.onl ? t.onl[j] : t.nl[j]; }
+__device__ __forceinline__ u32 caller_break_first(const TextDev& t, u32 j) {
+    if (!t.onl) return t.nl[j] - t.crlf;
+    const u32 e = t.onl[j], start = j ? t.onl[j - 1] + 1u : 0u;
+    const bool two = t.otext[e] == '\n' && e > start && (t.otext[e - 1] == '\n' || t.otext[e - 1] == '\r');
+    return e - (two ? 1u : 0u);
+}
 
 /* result of FastqMeta::parse for one read, 16 bytes */
 struct ReadMeta {
@@ -97,7 +109,7 @@ struct ChunkDev {
     u32 off_readlen, off_n1len, off_n2len, off_slen, off_lane, off_tile, off_x, off_y, off_n1, off_n2, off_strand, off_seq,
         off_qual, off_ov, off_npos;
     u32 bytes;            /* serialised size */
-    u32 r1_end, r2_end;   /* text offsets just past the last record's final line break */
+    u32 r1_end, r2_end;   /* text offsets of the first break character after the last record's quality line (Q13 compares them with nobreak_from) */
     u32 pad0;             /* explicit: the table is copied to the host word by word (no uninitialised padding) */
     u64 out_offset;
 };

@@ -207,75 +207,92 @@ struct Fmt4Cfg {
     u32 n_streams;         /* checkpoint layout: streams per chunk (quality streams + exceptions + N positions) */
 };
 
-/* the positions [first, end1) of a token, clipped to the tile [lo, hi), as bytes `q` at tile[pos - org] */
-__device__ __forceinline__ void qx_put_bytes(u8* tile, u32 org, u32 lo, u32 hi, u32 first, u32 end1, u8 q) {
-    const u32 a = first > lo ? first : lo, z = end1 < hi ? end1 : hi;
-    for (u32 p = a; p < z; p++) tile[p - org] = q;
-}
+/*
+ * The tile directory: for every formatter tile (G reads of one chunk) and stream, which steps of the stream hold tokens for the
+ * tile's positions.  Every step has its checkpoint, so the formatter decodes the steps of all its streams independently and in
+ * parallel - no search and no token chain inside the formatter.  For the exception records: the records of the tile.
+ */
+struct TileDir {
+    u32 off;            /* the stream's first byte, from the chunk's first byte (exceptions: the tile's first record) */
+    u32 len;            /* stream bytes (exceptions: records of the tile) */
+    u32 ck;             /* checkpoint of the first step, from the chunk's first checkpoint */
+    u32 step0, n_steps; /* steps [step0, step0 + n_steps) */
+    u32 pad[3];
+};
+/* tiles of chunk c lie at tile index read_base / G + c (+ tile): disjoint, since a chunk of n reads has at most n / G + 1 tiles */
+__device__ __forceinline__ u64 tile_index(const DecChunk& ck, u32 c, u32 G) { return (u64)(ck.read_base / G) + c; }
+inline size_t tile_dir_entries(u32 n_reads, u32 n_chunks, u32 G, u32 n_streams) { return ((size_t)n_reads / G + n_chunks + 2) * n_streams; }
 
-/* decode the part of stream `s` that covers positions [lo, hi) into the tile (or, bits: into the N bitmap) - one warp */
-template <bool BITS>
-__device__ inline void qx_decode_range(const DecBatchDev& b, const QStream& s, const uint2* __restrict__ ck, u32 lo, u32 hi, u32 lim_pos, u8 q, u8* tile, u32* bits, u32 org, int lane) {
-    if (!s.len || hi <= lo) return;
-    if (hi > lim_pos) hi = lim_pos;                       /* positions >= lim_pos are ignored (Q20) */
+/* grid (chunks / QX_WARPS, streams): a warp per (chunk, stream), a lane per tile */
+__global__ void __launch_bounds__(32 * QX_WARPS) k_dec_tiledir(DecBatchDev b, HeaderDev h, u32 G, u32 n_qstreams, u32 n_streams, const uint2* __restrict__ ckpt, TileDir* __restrict__ dir) {
+    const u32 c = blockIdx.x * QX_WARPS + (threadIdx.x >> 5);
+    if (c >= b.n_chunks) return;
+    const u32 task = blockIdx.y;
+    const u32 st = task < n_qstreams ? task : (u32)h.nb + 1u;
+    const int lane = threadIdx.x & 31;
+    const DecChunk& ck = b.chunks[c];
+    const QStream s = qx_stream(b, h, ck, st, lane);
+    const uint2* e = ckpt + qx_chunk_base(ck, c, n_streams) + s.ck;
     const u32 n_ck = (s.len + QX_STEP - 1) / QX_STEP;
-    /* the last checkpoint whose position is <= lo: the tokens before it cover positions below lo only */
-    u32 a = 0, z = n_ck;
-    while (z - a > 1u) {
-        const u32 stride = (z - a + 31u) / 32u;
-        const u32 idx = a + (u32)lane * stride;
-        const bool ok = idx < z && ck[idx].y <= lo;
-        const u32 m = (u32)__popc(__ballot_sync(0xffffffffu, ok));         /* monotone: lanes 0..m-1 (lane 0 always) */
-        a += (m ? m - 1u : 0u) * stride;
-        z = a + stride < z ? a + stride : z;
-    }
-    const QCursor S = qx_cursor(b, s);
-    const uint2 e = ck[a];
-    u32 skip = e.x, next = e.y;
-    u32 base = a * QX_STEP;
-    u32 cura = S.ldw((base >> 2) + (u32)lane);
-    for (; base < S.slen && next < hi; base += QX_STEP) {
-        const u32 nexta = base + QX_STEP < S.slen + 8 ? S.ldw((base >> 2) + 32u + (u32)lane) : 0u;
-        qx_step(S, base, cura, nexta, skip, next, lane, [&](u32 first, u32 end1) {
-            if (BITS) { const u32 x = first > lo ? first : lo, y = end1 < hi ? end1 : hi; for (u32 p = x; p < y; p++) atomicOr(&bits[(p - org) >> 5], 1u << ((p - org) & 31u)); }
-            else qx_put_bytes(tile, org, lo, hi, first, end1, q);
-        });
-        cura = nexta;
+    const u32 n_tiles = (ck.reads + G - 1) / G;
+    const bool compact = st == (u32)h.nb + 1u;             /* the N positions count compacted bases */
+    const u32* offs = compact ? b.seqoff : b.qualoff;
+    const u32 total = compact ? ck.seq_kept : ck.total_len;
+    TileDir* out = dir + tile_index(ck, c, G) * n_streams + task;
+    const u32 base_off = (u32)(s.p ? (u64)(s.p - (b.body + ck.in_off)) : 0u);
+    for (u32 t = (u32)lane; t < n_tiles; t += 32) {
+        const u32 r0 = t * G, r1 = r0 + G < ck.reads ? r0 + G : ck.reads;
+        const u32 lo = offs[ck.read_base + r0];
+        u32 hi = r1 < ck.reads ? offs[ck.read_base + r1] : total;
+        if (hi > ck.total_len) hi = ck.total_len;           /* positions >= the chunk's length are ignored (Q20) */
+        TileDir d; d.off = base_off; d.len = s.len; d.ck = s.ck; d.step0 = 0; d.n_steps = 0; d.pad[0] = d.pad[1] = d.pad[2] = 0;
+        if (st == h.nb) {
+            /* exception records {q, u32 LE pos} in increasing position (checked by k_dec_qindex): those with lo <= pos < hi */
+            const u32 n = s.len / 5u;
+            auto below = [&](u32 lim) { u32 a = 0, z = n; while (a < z) { const u32 m = (a + z) >> 1; if (ld32(s.p + 5ull * m + 1) < lim) a = m + 1; else z = m; } return a; };
+            const u32 f = n ? below(lo) : 0u, g = n ? below(hi) : 0u;
+            d.off = base_off + 5u * f; d.len = g > f ? g - f : 0u;
+        } else if (n_ck && hi > lo) {
+            /* the last step whose entry position is <= lo (the tokens before it lie below lo) ... */
+            u32 a = 0, z = n_ck;
+            while (z - a > 1u) { const u32 m = (a + z) >> 1; if (e[m].y <= lo) a = m; else z = m; }
+            /* ... to the last step whose entry position is < hi */
+            u32 a2 = a, z2 = n_ck;
+            while (z2 - a2 > 1u) { const u32 m = (a2 + z2) >> 1; if (e[m].y < hi) a2 = m; else z2 = m; }
+            d.step0 = a; d.n_steps = a2 - a + 1u; d.ck = s.ck + a;
+        }
+        out[(size_t)t * n_streams] = d;
     }
 }
 
-/* exception records {q, u32 LE pos}, increasing pos (checked by k_dec_qindex), for positions [lo, hi) - one warp */
-__device__ inline void qx_exceptions(const QStream& s, u32 lo, u32 hi, u32 lim_pos, u8* tile, u32 org, int lane) {
-    const u32 n = s.len / 5u;
-    if (!n || hi <= lo) return;
-    if (hi > lim_pos) hi = lim_pos;
-    u32 a = 0, z = n;                                     /* records [0, a) lie below lo, records [z, n) do not */
-    while (z > a) {
-        const u32 stride = (z - a + 31u) / 32u;
-        const u32 idx = a + (u32)lane * stride;
-        const bool below = idx < z && ld32(s.p + 5ull * idx + 1) < lo;
-        const u32 m = (u32)__popc(__ballot_sync(0xffffffffu, below));      /* monotone: lanes 0..m-1 */
-        if (m == 0) break;                               /* record a is the first one at or above lo */
-        const u32 nz = a + m * stride;                   /* the sample after the last one below lo (if there is one) is not below */
-        a += (m - 1u) * stride + 1u;
-        if (nz < z) z = nz;
-    }
-    for (u32 k = a + (u32)lane; ; k += 32) {
-        bool more = k < n;
-        if (more) { const u32 pos = ld32(s.p + 5ull * k + 1); if (pos < hi) { if (pos >= lo) tile[pos - org] = s.p[5ull * k]; } else more = false; }
-        if (!__all_sync(0xffffffffu, more)) break;
-    }
+/* one step (128 stream bytes) of a position stream into the tile: the positions [lo, hi) as bytes `q` at tile[pos - org], or
+ * (BITS) as bits of the N bitmap - one warp */
+template <bool BITS>
+__device__ __forceinline__ void qx_decode_step(const DecBatchDev& b, const u8* stream, u32 slen, u32 step, uint2 entry, u32 lo, u32 hi, u8 q, u8* tile, u32* bits, u32 org, int lane) {
+    QStream s; s.p = stream; s.len = slen; s.ck = 0;
+    const QCursor S = qx_cursor(b, s);
+    u32 skip = entry.x, next = entry.y;
+    const u32 base = step * QX_STEP;
+    const u32 cura = S.ldw((base >> 2) + (u32)lane);
+    const u32 nexta = base + QX_STEP < S.slen + 8 ? S.ldw((base >> 2) + 32u + (u32)lane) : 0u;
+    qx_step(S, base, cura, nexta, skip, next, lane, [&](u32 first, u32 end1) {
+        const u32 x = first > lo ? first : lo, y = end1 < hi ? end1 : hi;
+        if (BITS) { for (u32 p = x; p < y; p++) atomicOr(&bits[(p - org) >> 5], 1u << ((p - org) & 31u)); }
+        else { for (u32 p = x; p < y; p++) tile[p - org] = q; }
+    });
 }
 
 /*
  * k_dec_format4: grid (tiles per chunk, chunks of the window); CTA = G reads of one chunk, two threads per read in different
  * warps as in k_dec_format3.  Shared: quality tile | N bitmap | record staging per output stream.
  */
-__global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h, Fmt4Cfg cfg, u32 chunk_first, const uint2* __restrict__ ckpt) {
+__global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h, Fmt4Cfg cfg, u32 chunk_first, const uint2* __restrict__ ckpt, const TileDir* __restrict__ dir) {
     RPQ_DYN_SMEM(dyn);
     __shared__ u64 s_start[2], s_end[2];
     __shared__ u32 s_lut_fwd[256], s_lut_rc[256];
     __shared__ u32 s_task;
+    __shared__ TileDir s_dir[MAX_BINS + 3];
+    __shared__ u32 s_pre[MAX_BINS + 4];                /* tasks before each stream */
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 G = cfg.reads_per_cta;
     const u32 c = chunk_first + blockIdx.y;
@@ -313,6 +330,11 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
     }
     if (tid < 2) { s_start[tid] = ~0ull; s_end[tid] = 0; }
     if (tid == 0) s_task = 0;
+    {
+        const u32 nt = (raw_qual ? 0u : (u32)h.nb + 1u) + (npos_mode ? 1u : 0u);
+        const TileDir* src = dir + (tile_index(ck, c, G) + blockIdx.x) * cfg.n_streams;
+        for (u32 k = tid; k < nt * (u32)(sizeof(TileDir) / 4); k += blockDim.x) reinterpret_cast<u32*>(s_dir)[k] = reinterpret_cast<const u32*>(src)[k];
+    }
     /* allQual(seqLen, majorQual()) (src/rfqcodec.cpp:1089) for this tile; DONT_ENCODE_QUAL: the column itself (:1003-1007) */
     if (!raw_qual) {
         const u32 m4 = 0x01010101u * h.major;
@@ -326,6 +348,12 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
     for (u32 k = tid; k < cfg.nbits_words; k += blockDim.x) s_nbits[k] = 0;
     __syncthreads();
 
+    if (tid == 0) {
+        const u32 nq0 = raw_qual ? 0u : (u32)h.nb + 1u, nt = nq0 + (npos_mode ? 1u : 0u);
+        u32 acc = 0;
+        for (u32 t = 0; t < nt; t++) { s_pre[t] = acc; acc += (nq0 && t == nq0 - 1u) ? (s_dir[t].len + 31u) / 32u : s_dir[t].n_steps; }
+        s_pre[nt] = acc;
+    }
     const bool active = rt < (int)n_here;
     const u32 i = i_first + rt;
     u32 r = 0, rl = 0, stream = 0, olen = 0;
@@ -343,21 +371,30 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
     }
     __syncthreads();
 
-    /* ---- position streams of the tile: the warps of the sequence half start at once, the others join when the name lines are done */
+    /* ---- position streams of the tile: every (stream, step) the directory lists is a task of its own; the warps of the sequence
+     * half start at once, the others join when the name lines are done */
     const u32 n_q = raw_qual ? 0u : (u32)h.nb + 1u;                    /* quality streams + exception records */
     const u32 n_tasks = n_q + (npos_mode ? 1u : 0u);
     auto stream_tasks = [&]() {
+        const u32 total = s_pre[n_tasks];
+        const u8* cbase = b.body + ck.in_off;
+        const uint2* cck = ckpt + qx_chunk_base(ck, c, cfg.n_streams);
         for (;;) {
-            u32 t = 0;
-            if (lane == 0) t = atomicAdd(&s_task, 1u);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            if (t >= n_tasks) break;
+            u32 k = 0;
+            if (lane == 0) k = atomicAdd(&s_task, 1u);
+            k = __shfl_sync(0xffffffffu, k, 0);
+            if (k >= total) break;
+            u32 t = 0;                                                 /* the stream of task k: the last one with s_pre[t] <= k */
+            { u32 a = 0, z = n_tasks; while (z - a > 1u) { const u32 m = (a + z) >> 1; if (s_pre[m] <= k) a = m; else z = m; } t = a; }
+            const TileDir& d = s_dir[t];
+            const u32 j = k - s_pre[t];
             const u32 st = t < n_q ? t : (u32)h.nb + 1u;
-            const QStream s = qx_stream(b, h, ck, st, lane);
-            const uint2* e = ckpt + qx_chunk_base(ck, c, cfg.n_streams) + s.ck;
-            if (st < h.nb) qx_decode_range<false>(b, s, e, P0, P1, ck.total_len, h.normal_bins[st], s_plane, nullptr, porg, lane);
-            else if (st == h.nb) qx_exceptions(s, P0, P1, ck.total_len, s_plane, porg, lane);
-            else qx_decode_range<true>(b, s, e, C0, C1, ck.total_len, 0, nullptr, s_nbits, corg, lane);
+            if (st == h.nb) {
+                /* 32 exception records per task (src/rfqcodec.cpp:1034-1043) */
+                const u32 rec = 32u * j + (u32)lane;
+                if (rec < d.len) { const u8* p = cbase + d.off + 5ull * rec; const u32 pos = ld32(p + 1); if (pos >= P0 && pos < P1 && pos < ck.total_len) s_plane[pos - porg] = p[0]; }
+            } else if (st < h.nb) qx_decode_step<false>(b, cbase + d.off, d.len, d.step0 + j, cck[d.ck + j], P0, P1 < ck.total_len ? P1 : ck.total_len, h.normal_bins[st], s_plane, nullptr, porg, lane);
+            else qx_decode_step<true>(b, cbase + d.off, d.len, d.step0 + j, cck[d.ck + j], C0, C1 < ck.total_len ? C1 : ck.total_len, 0, nullptr, s_nbits, corg, lane);
         }
     };
     if (half == 0) stream_tasks();

@@ -381,10 +381,10 @@ __global__ void __launch_bounds__(FIN_THREADS) k_chunk_finish(EncBatchDev b, Hea
     {
         const u32 last = first + count - 1;
         u32 f, rec; read_locus(b, last, f, rec);
-        const u32 e_last = b.t[f].nl[4 * rec + 3] - b.t[f].crlf;     /* first break character after the last quality line */
+        const u32 e_last = caller_break_first(b.t[f], 4 * rec + 3);    /* first break character after the last quality line */
         if (b.is_pe && b.two_files) {
             u32 f1, rec1; read_locus(b, last - 1, f1, rec1);
-            ck.r1_end = b.t[0].nl[4 * rec1 + 3] - b.t[0].crlf; ck.r2_end = e_last;
+            ck.r1_end = caller_break_first(b.t[0], 4 * rec1 + 3); ck.r2_end = e_last;
         } else { ck.r1_end = e_last; ck.r2_end = e_last; }
     }
 }

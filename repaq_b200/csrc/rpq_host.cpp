@@ -52,19 +52,23 @@ HostMeta host_meta_parse(const char* name, int len) {
     return m;
 }
 
-/* ---- records of the first chunk ("\n" or "\r\n" line ends, input stops at the first empty line) */
+/* ---- records of the first chunk, read as FastqReader::getLine reads them (src/fastqreader.cpp:94-156): a line ends at the first
+ * '\r' or '\n'; a '\n' right after that byte belongs to the break unless it is the first or the last byte of one of the
+ * reader's 1 MiB buffers (the text is taken to start where the file starts) or the last byte of the input; input stops at the
+ * first empty line (:180-181) */
 struct Rec { const char* name; int name_len; const char* seq; int seq_len; const char* qual; int qual_len; };
 
 struct LineCursor {
     const char* p; uint64_t len, at;
     bool next(const char*& s, int& n) {
         if (at >= len) return false;
-        const char* nl = (const char*)memchr(p + at, '\n', len - at);
-        uint64_t e = nl ? (uint64_t)(nl - p) : len;
-        uint64_t le = e;
-        if (le > at && p[le - 1] == '\r') le--;
-        s = p + at; n = (int)(le - at);
-        at = e + 1;
+        uint64_t e = at;
+        while (e < len && p[e] != '\r' && p[e] != '\n') e++;
+        s = p + at; n = (int)(e - at);
+        e++;
+        const uint64_t in_buf = e & ((1ull << 20) - 1);
+        if (e + 1 < len && p[e] == '\n' && in_buf != 0 && in_buf != (1ull << 20) - 1) e++;
+        at = e;
         return true;
     }
     bool record(Rec& r) {
@@ -91,7 +95,7 @@ int host_make_header(const char* r1, uint64_t l1, const char* r2, uint64_t l2, i
         else { reads.push_back(x); total += x.seq_len; }
         if (total >= chunk_bases) break;
     }
-    if (reads.empty()) { set_err(err, err_cap, "failed to encode, please confirm the input FASTQ file is valid and not empty"); return RPQ_ERR_FASTQ; }
+    if (reads.empty()) { set_err(err, err_cap, "the input holds no FASTQ record"); return RPQ_NO_RECORDS; }
 
     bool has = true; int maxlen = 0;
     bool support = true; int diff_pos = 0; char diff_char = '\0';

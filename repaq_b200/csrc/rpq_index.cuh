@@ -5,8 +5,8 @@
  * src/fastqreader.cpp:94-156, the '\n' scan at :100-105) and the chunk-cut loop of Repaq::compress / compressPE
  * (src/repaq.cpp:546-553, 656-663: append record, total += bases, flush when total >= chunkSize).
  *
- * Supported line ends: all "\n" or all "\r\n" (the reference additionally accepts lone '\r' and silently swallows
- * an empty line after a break; those inputs are rejected here with RPQ_ERR_FASTQ).
+ * Line breaks are the reference reader's: '\n', '\r', "\r\n", and a '\n' directly after any break (a swallowed blank
+ * line), with its 1 MiB buffer-edge exception (k_index_lines).
  */
 #pragma once
 #include "rpq_common.cuh"
@@ -22,17 +22,18 @@ constexpr int IDX_SMEM = IDX_TILE;                            /* the tile */
 
 struct IndexCounters {
     u32 ticket;     /* dynamic tile id */
-    u32 n_nl;       /* '\n' bytes */
-    u32 n_cr;       /* '\r' bytes */
-    u32 n_crlf;     /* '\n' preceded by '\r' */
+    u32 n_nl;       /* line breaks */
+    u32 n_w2;       /* line breaks of two bytes (the second one a swallowed '\n') */
+    u32 pad0;
     /* written by k_index_finish */
     u32 n_lines;
-    u32 crlf;
-    u32 bad_eol;    /* mixed or lone '\r' line ends */
+    u32 crlf;       /* 1: every line break has two bytes */
+    u32 irregular;  /* breaks of one AND of two bytes: the text goes through k_canon_* first */
     u32 pad;
 };
 
 constexpr u64 TS_AGG = 1ull << 62, TS_PREFIX = 2ull << 62, TS_MASK = 3ull << 62;
+constexpr u64 RD_BUF = 1ull << 20;                           /* FQ_BUF_SIZE of the reference's reader (src/fastqreader.cpp:5) */
 
 /* exact per-byte equality, SIMD in a register: bit 7 of every byte of the result is set iff that byte of v equals c.
  * ((v ^ cccc) & 0x7f7f7f7f) + 0x7f7f7f7f carries into bit 7 iff the low seven bits differ; bit 7 itself must be clear in v
@@ -52,190 +53,38 @@ __device__ __forceinline__ u32 pack8(u32 lo, u32 hi) { return ((lo >> 4) | hi) *
 __device__ __forceinline__ u32 mask16(u32 m0, u32 m1, u32 m2, u32 m3) {
     return (pack8(m0, m1) >> 24) | ((pack8(m2, m3) >> 16) & 0xFF00u);
 }
+__device__ __forceinline__ bool is_brk(u8 c) { return c == '\n' || c == '\r'; }
+
+/* may the '\n' at file offset q be taken as the second byte of a line break?  Not if it is the first or the last byte of one
+ * of the reader's 1 MiB buffers: `if (end < mBufDataLen - 1 && mBuf[end] == '\n')` (src/fastqreader.cpp:113-116) */
+__device__ __forceinline__ bool rd_may_swallow(u64 q) { const u64 r = q & (RD_BUF - 1); return r != 0 && r != RD_BUF - 1; }
 
 /*
- * One pass over the text: positions of every '\n', in order.  Persistent CTAs take 64 KiB tiles by ticket.  A tile is brought into
- * shared memory by one TMA bulk copy per warp (4 KiB); a thread owns 128 contiguous bytes (its pieces read in a lane-rotated
- * order, so that the 128-bit shared loads of a quarter warp fall into eight different bank groups), turns them into eight exact
- * 16-bit newline masks (kept in two 64-bit registers) with SIMD-in-register compares, and counts.  The tile's count is published
- * at once; its rank base - the chained scan over tiles with a decoupled look-back, the whole CTA probing 512 predecessors per
- * round - is only resolved one tile LATER, after the next tile has been counted and published, and then the positions are
- * written: by then the predecessors (which were all in the same phase) have published their counts.  Nothing that can wait
- * sits between taking a ticket and publishing that tile's count, so a wait never cascades.
- * '\r' is only tested for ("any in these 16 bytes"); files that have them take the exact path.
+ * One pass over the text: the line breaks as FastqReader::getLine sees them (reference src/fastqreader.cpp:94-156), in order.
+ * A line ends at the first '\r' or '\n'; a '\n' that directly follows the byte that ended a line is taken as part of that
+ * break (so "\r\n" is one break - but so is "\n\n": a single blank line is invisible to the reference), unless it is the first
+ * or last byte of a 1 MiB reader buffer.  With T = "byte is \r or \n", A(q) = '\n' at q & T(q-1) & may_swallow(q), a byte is
+ * swallowed iff A(q) & !A(q-1) (exact for the first three bytes of a run of break characters; a longer run contains an empty
+ * line, where the input ends anyway), and a line ends at E = T & !swallowed.  nl[] receives, per line, the offset of the LAST
+ * byte of its break, so that the next line starts one byte later.
+ * A CTA per 64 KiB tile, brought into shared memory by one TMA bulk copy per warp (4 KiB); a thread owns 128 contiguous bytes
+ * (its pieces read in a lane-rotated order, so that the 128-bit shared loads of a quarter warp fall into eight different bank
+ * groups), turns them into exact 128-bit masks with SIMD-in-register compares, and counts.  The rank base of a tile is the
+ * chained scan over tiles with a decoupled look-back (warp 0).  Rows without '\r' and without two break characters in a row
+ * (every row of a plain file) never leave the '\n' mask.
  */
-__global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines(const u8* __restrict__ text, u64 len, u32* __restrict__ nl, u32 nl_cap,
-                                                               u64* tile_state, IndexCounters* ctr, u32 n_tiles) {
-    RPQ_DYN_SMEM(dyn);
-    __shared__ u32 s_tile;
-    __shared__ u32 s_wtot[IDX_THREADS / 32];
-    __shared__ u32 s_un[IDX_THREADS / 32], s_pr[IDX_THREADS / 32], s_sum;
-    __shared__ u32 s_cr, s_crlf;
-#ifndef RPQ_EMU
-    __shared__ __align__(8) unsigned long long s_mbar[IDX_THREADS / 32];
-#endif
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_cr = 0; s_crlf = 0; }
-#ifndef RPQ_EMU
-    if (tid < IDX_THREADS / 32) {
-        asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"((u32)__cvta_generic_to_shared(&s_mbar[tid])) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    u32 parity = 0;
-#endif
-    u8* row = dyn + (size_t)tid * IDX_ROW;
-    volatile u64* st = tile_state;
-
-    /* the tile whose positions are still to be written */
-    bool pending = false;
-    u32 p_tile = 0, p_off = 0, p_btot = 0, p_base = 0;
-    u64 p_lo = 0, p_hi = 0;
-
-    for (;;) {
-        __syncthreads();                                       /* everybody is done with the tile buffer (and with s_tile, s_wtot) */
-        if (tid == 0) s_tile = atomicAdd(&ctr->ticket, 1u);
-        __syncthreads();
-        const u32 tile = s_tile;
-        const bool have = tile < n_tiles;
-        const u64 tbase = (u64)tile * IDX_TILE;
-        const u64 wbase = tbase + (u64)warp * IDX_WARP_BYTES;
-        const u32 wbytes = (!have || wbase >= len) ? 0u : (len - wbase >= IDX_WARP_BYTES ? (u32)IDX_WARP_BYTES : (u32)(((len - wbase) + 15) & ~15ull));
-        /* ---- start the copy of the next tile */
-#ifdef RPQ_EMU
-        for (u32 k = lane; k < wbytes; k += 32) { const u64 p = wbase + k; dyn[(size_t)warp * IDX_WARP_BYTES + k] = p < len ? text[p] : 0; }
-        __syncwarp();
-#else
-        const u32 mbar = (u32)__cvta_generic_to_shared(&s_mbar[warp]);
-        if (wbytes && lane == 0) {
-            const u32 dst = (u32)__cvta_generic_to_shared(dyn + (size_t)warp * IDX_WARP_BYTES);
-            asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(mbar), "r"(wbytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(text + wbase), "r"(wbytes), "r"(mbar) : "memory");
-        }
-#endif
-        u32 cnt = 0, btot = 0, off_in_tile = 0;
-        u64 lo = 0, hi = 0;
-        u64 p0 = 0;
-        if (have) {
-
-        /* ---- the new tile: wait for its bytes */
-#ifndef RPQ_EMU
-        if (wbytes) {
-            u32 done = 0;
-            while (!done)
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-            parity ^= 1u;
-        }
-#endif
-        p0 = tbase + (u64)tid * IDX_ROW;                /* first byte of this thread's row */
-        const int lim = p0 >= len ? 0 : (len - p0 >= IDX_ROW ? IDX_ROW : (int)(len - p0));
-        if (lim < IDX_ROW) for (int i = lim; i < IDX_ROW; i++) row[i] = 0;     /* the end of the text: zeros match nothing */
-
-        /* ---- masks and counts */
-        u32 ncr = 0, ncrlf = 0;
-#pragma unroll
-        for (int k = 0; k < IDX_PIECES; k++) {
-            const int kk = (k + lane) & (IDX_PIECES - 1);
-            const uint4 v = *reinterpret_cast<const uint4*>(row + 16 * kk);
-            const u32 m = mask16(eq_lowascii(v.x, 0x0A0A0A0Au), eq_lowascii(v.y, 0x0A0A0A0Au), eq_lowascii(v.z, 0x0A0A0A0Au), eq_lowascii(v.w, 0x0A0A0A0Au));
-            const u32 nocr = ne_lowascii(v.x, 0x0D0D0D0Du) & ne_lowascii(v.y, 0x0D0D0D0Du) & ne_lowascii(v.z, 0x0D0D0D0Du) & ne_lowascii(v.w, 0x0D0D0D0Du);
-            const u64 placed = (u64)m << (16 * (kk & 3));
-            if (kk & 4) hi |= placed; else lo |= placed;
-            cnt += (u32)__popc(m);
-            if (~nocr & 0x80808080u) {
-                const u32 c = mask16(eq_lowascii(v.x, 0x0D0D0D0Du), eq_lowascii(v.y, 0x0D0D0D0Du), eq_lowascii(v.z, 0x0D0D0D0Du), eq_lowascii(v.w, 0x0D0D0D0Du));
-                ncr += (u32)__popc(c);
-                ncrlf += (u32)__popc(m & (c << 1));
-            }
-            if (m & 1u) {                                        /* a newline at the first byte of a piece: look one byte back */
-                const u64 p = p0 + 16u * (u32)kk;
-                u8 prev = 0;
-                if (kk > 0 || lane > 0) prev = row[16 * kk - 1];  /* rows of a warp are contiguous in shared memory */
-                else if (p > 0) prev = text[p - 1];
-                if (prev == '\r') ncrlf++;
-            }
-        }
-        u32 wtot;
-        const u32 ex_in_warp = warp_excl_scan(cnt, lane, wtot);
-        ncr = warp_sum(ncr); ncrlf = warp_sum(ncrlf);
-        if (lane == 0) { s_wtot[warp] = wtot; if (ncr) atomicAdd(&s_cr, ncr); if (ncrlf) atomicAdd(&s_crlf, ncrlf); }
-        __syncthreads();
-        u32 wpre = 0;
-#pragma unroll
-        for (int w = 0; w < IDX_THREADS / 32; w++) { const u32 t = s_wtot[w]; btot += t; if (w < warp) wpre += t; }
-        if (tid == 0 && tile > 0) { st[tile] = TS_AGG | btot; __threadfence(); }     /* published before anything below can wait */
-        off_in_tile = wpre + ex_in_warp;
-        }
-        /* ---- finish the pending tile: rank base by look-back, then the positions */
-        if (pending) {
-            u32 prefix = 0;
-            if (p_tile > 0) {
-                int j = (int)p_tile - 1;                         /* newest predecessor not yet accounted for */
-                for (;;) {
-                    const int idx = j - tid;
-                    u64 sv = 2ull << 62;                          /* before tile 0: an empty prefix (TS_PREFIX | 0) */
-                    if (idx >= 0) sv = st[idx];
-                    const u32 unset = __ballot_sync(0xffffffffu, (sv & TS_MASK) == 0);
-                    const u32 pre = __ballot_sync(0xffffffffu, (sv & TS_MASK) == TS_PREFIX);
-                    if (lane == 0) { s_un[warp] = unset; s_pr[warp] = pre; }
-                    if (tid == 0) s_sum = 0;
-                    __syncthreads();
-                    int first_unset = IDX_THREADS, first_pre = IDX_THREADS;
-#pragma unroll
-                    for (int w = IDX_THREADS / 32 - 1; w >= 0; w--) {
-                        const u32 u = s_un[w], q = s_pr[w];
-                        if (u) first_unset = 32 * w + __ffs((int)u) - 1;
-                        if (q) first_pre = 32 * w + __ffs((int)q) - 1;
-                    }
-                    /* usable predecessors: those before the first unset one, up to and including the first prefix */
-                    const int upto = first_pre < first_unset ? first_pre + 1 : first_unset;
-                    const u32 v = warp_sum(tid < upto ? (u32)sv : 0u);
-                    if (lane == 0 && v) atomicAdd(&s_sum, v);
-                    __syncthreads();
-                    prefix += s_sum;
-                    if (first_pre < first_unset) break;
-                    j -= upto;
-                    if (upto == 0) RPQ_SPIN_HINT();
-                    __syncthreads();
-                }
-            }
-            if (tid == 0) {
-                __threadfence();
-                st[p_tile] = TS_PREFIX | (u64)(prefix + p_btot);
-                if ((u64)(p_tile + 1) * IDX_TILE >= len) ctr->n_nl = prefix + p_btot;     /* the last tile knows the total */
-            }
-            u32 o = prefix + p_off;
-            u64 m = p_lo;
-            while (m) { const int bb = __ffsll((long long)m) - 1; m &= m - 1; if (o < nl_cap) nl[o] = p_base + (u32)bb; o++; }
-            m = p_hi;
-            while (m) { const int bb = __ffsll((long long)m) - 1; m &= m - 1; if (o < nl_cap) nl[o] = p_base + 64u + (u32)bb; o++; }
-            pending = false;
-        }
-        if (!have) break;
-        pending = true; p_tile = tile; p_off = off_in_tile; p_btot = btot; p_base = (u32)p0; p_lo = lo; p_hi = hi;
-    }
-    if (tid == 0) {
-        if (s_cr) atomicAdd(&ctr->n_cr, s_cr);
-        if (s_crlf) atomicAdd(&ctr->n_crlf, s_crlf);
-    }
-}
-
-/* The previous arrangement, kept for A/B runs (RPQ_DEBUG_INDEX=1): a CTA per tile, the rank base resolved by warp 0 right after the
- * tile was counted (the other 15 warps wait at a barrier for the look-back). */
-constexpr int IDX_SMEM_TILECTA = IDX_TILE + IDX_THREADS * 16;
-__global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines_tilecta(const u8* __restrict__ text, u64 len, u32* __restrict__ nl, u32 nl_cap,
+__global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines(const u8* __restrict__ text, u64 len, u64 file_off, u32* __restrict__ nl, u32 nl_cap,
                                                                u64* tile_state, IndexCounters* ctr) {
     RPQ_DYN_SMEM(dyn);
     __shared__ u32 s_tile;
     __shared__ u32 s_wtot[IDX_THREADS / 32];
     __shared__ u32 s_prefix;
-    __shared__ u32 s_cr, s_crlf;
+    __shared__ u32 s_w2;
 #ifndef RPQ_EMU
     __shared__ __align__(8) unsigned long long s_mbar[IDX_THREADS / 32];
 #endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_tile = atomicAdd(&ctr->ticket, 1u); s_cr = 0; s_crlf = 0; }
+    if (tid == 0) { s_tile = atomicAdd(&ctr->ticket, 1u); s_w2 = 0; }
 #ifndef RPQ_EMU
     if (tid < IDX_THREADS / 32) {
         asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"((u32)__cvta_generic_to_shared(&s_mbar[tid])) : "memory");
@@ -246,7 +95,6 @@ __global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines_tilecta(const u8
     const u32 tile = s_tile;
     const u64 tbase = (u64)tile * IDX_TILE;
     u8* row = dyn + (size_t)tid * IDX_ROW;
-    unsigned short* my_masks = reinterpret_cast<unsigned short*>(dyn + IDX_TILE) + (size_t)tid * IDX_PIECES;
 
     /* ---- stage */
     const u64 wbase = tbase + (u64)warp * IDX_WARP_BYTES;
@@ -273,33 +121,61 @@ __global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines_tilecta(const u8
     const int lim = p0 >= len ? 0 : (len - p0 >= IDX_ROW ? IDX_ROW : (int)(len - p0));
     if (lim < IDX_ROW) for (int i = lim; i < IDX_ROW; i++) row[i] = 0;     /* the end of the text: zeros match nothing */
 
-    /* ---- masks and counts */
-    u32 cnt = 0, ncr = 0, ncrlf = 0;
+    /* ---- masks of the row: '\n' and (rarely) '\r' */
+    u64 nlo = 0, nhi = 0, clo = 0, chi = 0;
 #pragma unroll
     for (int k = 0; k < IDX_PIECES; k++) {
         const int kk = (k + lane) & (IDX_PIECES - 1);
         const uint4 v = *reinterpret_cast<const uint4*>(row + 16 * kk);
         const u32 m = mask16(eq_lowascii(v.x, 0x0A0A0A0Au), eq_lowascii(v.y, 0x0A0A0A0Au), eq_lowascii(v.z, 0x0A0A0A0Au), eq_lowascii(v.w, 0x0A0A0A0Au));
         const u32 nocr = ne_lowascii(v.x, 0x0D0D0D0Du) & ne_lowascii(v.y, 0x0D0D0D0Du) & ne_lowascii(v.z, 0x0D0D0D0Du) & ne_lowascii(v.w, 0x0D0D0D0Du);
-        my_masks[kk] = (unsigned short)m;
-        cnt += (u32)__popc(m);
+        const u64 placed = (u64)m << (16 * (kk & 3));
+        if (kk & 4) nhi |= placed; else nlo |= placed;
         if (~nocr & 0x80808080u) {
             const u32 c = mask16(eq_lowascii(v.x, 0x0D0D0D0Du), eq_lowascii(v.y, 0x0D0D0D0Du), eq_lowascii(v.z, 0x0D0D0D0Du), eq_lowascii(v.w, 0x0D0D0D0Du));
-            ncr += (u32)__popc(c);
-            ncrlf += (u32)__popc(m & (c << 1));
-        }
-        if (m & 1u) {                                        /* a newline at the first byte of a piece: look one byte back */
-            const u64 p = p0 + 16u * (u32)kk;
-            u8 prev = 0;
-            if (kk > 0 || lane > 0) prev = row[16 * kk - 1];  /* rows of a warp are contiguous in shared memory */
-            else if (p > 0) prev = text[p - 1];
-            if (prev == '\r') ncrlf++;
+            const u64 pc = (u64)c << (16 * (kk & 3));
+            if (kk & 4) chi |= pc; else clo |= pc;
         }
     }
+    /* ---- line ends E and, per line end, whether the byte after it belongs to the break (swn) */
+    auto byte_at = [&](long long rel) -> u8 {                /* text[p0 + rel], rel in [-2, 128]: this warp's shared copy, or the text */
+        const long long q = (long long)p0 + rel;
+        if (q < 0 || (u64)q >= len) return 0;
+        const long long in_warp = q - (long long)wbase;
+        return (in_warp >= 0 && in_warp < IDX_WARP_BYTES) ? dyn[(size_t)warp * IDX_WARP_BYTES + in_warp] : text[q];
+    };
+    u64 elo = nlo | clo, ehi = nhi | chi, swn_lo = 0, swn_hi = 0;
+    {
+        const u64 tlo = elo, thi = ehi;
+        u64 alo = nlo & (tlo << 1), ahi = nhi & ((thi << 1) | (tlo >> 63));
+        if ((nlo & 1ull) && is_brk(byte_at(-1))) alo |= 1ull;
+        if ((alo | ahi) != 0) {                                /* a '\n' right after a break character */
+            /* not at the first or the last byte of a reader buffer: at most one buffer edge near the row */
+            const u64 abs0 = file_off + p0;
+            const u64 edge = (abs0 + IDX_ROW) & ~(RD_BUF - 1);   /* the largest multiple of 1 MiB <= abs0 + 128 */
+            if (edge >= abs0 && edge > 0) {
+                const u32 r = (u32)(edge - abs0);                /* 0..128: clear positions r and r - 1 */
+                if (r < 64u) alo &= ~(1ull << r); else if (r < 128u) ahi &= ~(1ull << (r - 64u));
+                if (r >= 1u && r - 1u < 64u) alo &= ~(1ull << (r - 1u)); else if (r >= 65u) ahi &= ~(1ull << (r - 65u));
+            }
+            /* A at the byte before the row */
+            const u8 b1 = byte_at(-1);
+            const u64 a_prev = (p0 >= 1 && b1 == '\n' && is_brk(byte_at(-2)) && rd_may_swallow(file_off + p0 - 1)) ? 1ull : 0ull;
+            const u64 slo = alo & ~((alo << 1) | a_prev), shi = ahi & ~((ahi << 1) | (alo >> 63));     /* swallowed */
+            elo = tlo & ~slo; ehi = thi & ~shi;
+            swn_lo = (slo >> 1) | (shi << 63); swn_hi = shi >> 1;
+        }
+        if (ehi >> 63) {                                       /* a line ends at the row's last byte: is the next byte swallowed? */
+            const u64 q = p0 + IDX_ROW;
+            if (q < len && byte_at(IDX_ROW) == '\n' && rd_may_swallow(file_off + q) && !(ahi >> 63)) swn_hi |= 1ull << 63;
+        }
+    }
+    const u32 cnt = (u32)(__popcll(elo) + __popcll(ehi));
+    const u32 w2 = (u32)(__popcll(swn_lo & elo) + __popcll(swn_hi & ehi));
     u32 wtot;
     const u32 ex_in_warp = warp_excl_scan(cnt, lane, wtot);
-    ncr = warp_sum(ncr); ncrlf = warp_sum(ncrlf);
-    if (lane == 0) { s_wtot[warp] = wtot; if (ncr) atomicAdd(&s_cr, ncr); if (ncrlf) atomicAdd(&s_crlf, ncrlf); }
+    const u32 w2w = warp_sum(w2);
+    if (lane == 0) { s_wtot[warp] = wtot; if (w2w) atomicAdd(&s_w2, w2w); }
     __syncthreads();
     u32 btot = 0, wpre = 0;
 #pragma unroll
@@ -332,46 +208,77 @@ __global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines_tilecta(const u8
             __threadfence();
             st[tile] = TS_PREFIX | (u64)(prefix + btot);
             s_prefix = prefix;
-            if (s_cr) atomicAdd(&ctr->n_cr, s_cr);
-            if (s_crlf) atomicAdd(&ctr->n_crlf, s_crlf);
+            if (s_w2) atomicAdd(&ctr->n_w2, s_w2);
             if ((u64)(tile + 1) * IDX_TILE >= len) ctr->n_nl = prefix + btot;     /* the last tile knows the total */
         }
     }
     __syncthreads();
 
-    /* ---- positions: the eight masks of this thread, in text order */
+    /* ---- positions, in text order: the last byte of every break */
     if (cnt) {
         u32 o = s_prefix + wpre + ex_in_warp;
-        const uint4 mm = *reinterpret_cast<const uint4*>(my_masks);
         const u32 base = (u32)p0;
-        u32 w[4] = {mm.x, mm.y, mm.z, mm.w};
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            u32 m = w[q];
-            while (m) {
-                const int bb = __ffs((int)m) - 1;
-                m &= m - 1;
-                if (o < nl_cap) nl[o] = base + 32u * q + (u32)bb;
-                o++;
-            }
-        }
+        u64 m = elo;
+        while (m) { const int bb = __ffsll((long long)m) - 1; m &= m - 1; if (o < nl_cap) nl[o] = base + (u32)bb + (u32)((swn_lo >> bb) & 1ull); o++; }
+        m = ehi;
+        while (m) { const int bb = __ffsll((long long)m) - 1; m &= m - 1; if (o < nl_cap) nl[o] = base + 64u + (u32)bb + (u32)((swn_hi >> bb) & 1ull); o++; }
     }
 }
 
+/* is the break that ends a line at text offset e (its last byte) two bytes long?  Only a swallowed '\n' can follow the byte that
+ * ended the line, and a line holds no break characters itself. */
+__device__ __forceinline__ bool brk_is_two(const u8* text, u32 line_start, u32 e) { return text[e] == '\n' && e > line_start && is_brk(text[e - 1]); }
+
 /* line-end mode, the virtual final newline, line count.  eof: the text ends where the input ends, so an unterminated last line
- * is a line (FastqReader::getLine returns it, src/fastqreader.cpp:107-120); otherwise the text is a window of a longer input
- * and the unterminated tail belongs to a record of the next window. */
+ * is a line (FastqReader::getLine returns it, src/fastqreader.cpp:107-120); otherwise the text is a window of a longer input:
+ * the unterminated tail belongs to a record of the next window, and so does a line whose one-byte break is the window's last
+ * byte (whether a '\n' after it belongs to the break is for the next window to see). */
 __global__ void k_index_finish(const u8* text, u64 len, u32* nl, u32 nl_cap, IndexCounters* ctr, int eof) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const u32 n = ctr->n_nl;
-    u32 crlf = 0, bad = 0;
-    if (ctr->n_cr) { crlf = 1; if (ctr->n_cr != ctr->n_crlf || ctr->n_crlf != n) bad = 1; }
+    u32 n = ctr->n_nl, w2 = ctr->n_w2;
+    if (n && n <= nl_cap && nl[n - 1] == (u32)(len - 1)) {
+        const u32 start = n > 1 ? nl[n - 2] + 1u : 0u;
+        const bool two = brk_is_two(text, start, (u32)(len - 1));
+        if (!eof && !two) n--;
+        else if (eof && two && w2 == 1 && text[len - 2] == '\n' && n < nl_cap) {
+            /* a text of one-byte breaks that ends "\n\n": the reference's reader never takes the LAST byte of its input as the
+             * second byte of a break (end < mBufDataLen - 1), it reads an empty last line - which changes nothing, but keeps the
+             * text regular */
+            nl[n - 1] = (u32)(len - 2); nl[n] = (u32)(len - 1); n++; w2 = 0;
+        }
+    }
+    const u32 crlf = (n && w2 == n) ? 1u : 0u;
     u32 lines = n;
-    if (eof && len > 0 && text[len - 1] != '\n') {
+    if (eof && len > 0 && !is_brk(text[len - 1])) {
         if (n < nl_cap) nl[n] = (u32)len + crlf;       /* so that line_end() == len */
         lines = n + 1;
     }
-    ctr->n_lines = lines; ctr->crlf = crlf; ctr->bad_eol = bad;
+    ctr->n_nl = n; ctr->n_w2 = w2;
+    ctr->n_lines = lines; ctr->crlf = crlf; ctr->irregular = (w2 != 0 && w2 != n) ? 1u : 0u;
+}
+
+/* ---- irregular texts (line breaks of one and of two bytes: blank lines the reader swallows, a "\r\n" on a reader-buffer edge,
+ * mixed line ends): the lines are copied into a text of plain "\n" breaks, exactly the lines the reference's reader delivers,
+ * and everything after the index works on that copy. */
+__global__ void k_canon_lens(const u8* __restrict__ text, u64 len, const u32* __restrict__ nl, u32 n_lines, u32 n_brk, u32* __restrict__ out_len) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_lines) return;
+    const u32 start = j ? nl[j - 1] + 1u : 0u;
+    u32 end;
+    if (j < n_brk) { const u32 e = nl[j]; end = e - (brk_is_two(text, start, e) ? 1u : 0u); }
+    else end = (u32)len;                               /* the unterminated last line */
+    out_len[j] = end - start + 1u;                     /* content + '\n' */
+}
+__global__ void k_canon_copy(const u8* __restrict__ text, const u32* __restrict__ nl, const u32* __restrict__ lens, const u64* __restrict__ pre, u32 n_lines,
+                             u8* __restrict__ out, u32* __restrict__ nl_out) {
+    const int lane = threadIdx.x & 31;
+    const u32 j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= n_lines) return;
+    const u32 start = j ? nl[j - 1] + 1u : 0u;
+    const u32 n = lens[j] - 1u;
+    const u64 dst = pre[j] - lens[j];
+    for (u32 k = lane; k < n; k += 32) out[dst + k] = text[start + k];
+    if (lane == 0) { out[dst + n] = '\n'; nl_out[j] = (u32)(dst + n); }
 }
 
 /* per-unit (read, or pair) statistics */
@@ -503,31 +410,14 @@ __global__ void k_cut(const u64* __restrict__ prefix, u32 n_units, u32 chunk_bas
 }
 
 /* where the text covered by the chunks ends (one launch behind k_cut, so that the host reads everything back at once) */
-__global__ void k_cut_ends(UnitStats* st, const u32* __restrict__ nl0, const u32* __restrict__ nl1, int two, int pe) {
+__global__ void k_cut_ends(UnitStats* st, EncBatchDev b, int two, int pe) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     st->end[0] = st->end[1] = 0;
     if (st->units_in_chunks == 0) return;
     const u32 last_unit = st->units_in_chunks - 1;
     const u32 rec0 = two ? last_unit : (pe ? 2 * last_unit + 1 : last_unit);
-    st->end[0] = nl0[4ull * rec0 + 3];
-    if (two) st->end[1] = nl1[4ull * last_unit + 3];
-}
-
-/* "\r\n" files: the first line break the reference's reader mis-reads.  It refills a 1 MiB buffer and takes the '\n' after a
- * '\r' as part of the break only `if (end < mBufDataLen - 1 && mBuf[end] == '\n')` (src/fastqreader.cpp:113-116): a '\n' that is
- * the LAST byte of a buffer, or the first byte of the next one, is read as a line of its own - an empty line, which ends the
- * input (:180-181).  A thread per buffer edge inside the text; *first = text offset of the first such '\n' that has anything
- * after it, else stays ~0. */
-__global__ void k_crlf_edges(const u8* __restrict__ text, u64 len, u64 file_off, int eof, u32* first) {
-    const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const u64 edge = (((file_off >> 20) + 1ull + k) << 20);      /* file offset of the first byte of a buffer */
-    if (edge < file_off + 1) return;
-    const u64 rel = edge - file_off;                             /* the same, inside this text */
-    if (rel > len) return;
-    u64 hit = ~0ull;
-    if (rel >= 2 && text[rel - 1] == '\n' && text[rel - 2] == '\r' && (rel < len || !eof)) hit = rel - 1;            /* last byte of a buffer */
-    else if (rel >= 1 && rel < len && text[rel] == '\n' && text[rel - 1] == '\r' && (rel + 1 < len || !eof)) hit = rel;   /* first byte of the next */
-    if (hit != ~0ull) atomicMin(first, (u32)hit);
+    st->end[0] = caller_break_last(b.t[0], 4 * rec0 + 3);
+    if (two) st->end[1] = caller_break_last(b.t[1], 4 * last_unit + 3);
 }
 
 }  // namespace rpq

@@ -119,38 +119,6 @@ def test_large_roundtrip_property(codec):
     assert rfq[: len(ref)] == ref
 
 
-def test_persistent_indexer_variant(monkeypatch):
-    """RPQ_DEBUG_INDEX=0: the persistent-CTA line indexer must index exactly like the default CTA-per-tile one"""
-    from tools import fqgen
-    monkeypatch.setenv("RPQ_DEBUG_INDEX", "0")
-    cd = K.Codec(device=0)
-    try:
-        for name in ("nova_pe_k1000", "nova_pe_crlf_k100", "bgi_se_varlen_k100", "nova_pe_nonl_k100"):
-            parity.check_encode_golden(cd, name)
-        r1, r2 = fqgen.generate(200000, seed=58, paired=True)
-        parity.check_against_oracle(cd, r1, r2)
-    finally:
-        cd.close()
-
-
-class _TorchDevice:
-    """torch only provides the device memory"""
-    @staticmethod
-    def put(arr):
-        import torch
-        t = torch.from_numpy(arr.copy()).cuda()
-        return t, t.data_ptr()
-
-    @staticmethod
-    def get(ptr, n):
-        if not n:
-            return b""
-        host = np.empty(n, dtype=np.uint8)
-        rc = C.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(C.c_void_p(host.ctypes.data), C.c_void_p(ptr), C.c_size_t(n), 2)
-        assert rc == 0
-        return host.tobytes()
-
-
 def test_parallel_chunk_walk(monkeypatch):
     from tests import test_emu_parity as E
     E.test_parallel_chunk_walk(monkeypatch, lib_path=None, mem=_TorchDevice)
@@ -178,6 +146,7 @@ def test_window_cut_and_blank_lines(codec):
     E.test_window_cut_inside_the_chunk_closing_record(codec)
     E.test_blank_lines(codec)
     E.test_crlf_on_reader_buffer_edges(codec)
+    E.test_lone_cr_and_mixed_line_ends(codec)
 
 
 def test_library_really_ran_on_gpu(codec):
