@@ -826,6 +826,13 @@ int orc_compress(const char* r1, size_t l1, const char* r2, size_t l2, int inter
 
 /* src/repaq.cpp:262-333 (decompress), :335-413 (decompressPE) */
 int orc_decompress(const uint8_t* rfq, size_t len, int pe_out, char** out1, size_t* l1, char** out2, size_t* l2) {
+    if (len == 0) {
+        /* RfqHeader::read on an empty stream: every ifs.read() fails and the constructor's values stay (src/rfqheader.cpp:7-43) -
+         * "RFQ", ALGORITHM_VER, flags 0: a single-end file without chunks (what `repaq -c` leaves for an input without records) */
+        if (pe_out) return fail("The input RFQ file was encoded by single-end FASTQ, you should not specify <out2>");
+        *out1 = NULL; *l1 = 0; *out2 = NULL; *l2 = 0;
+        return 0;
+    }
     orc_header h; size_t at = orc_header_read(rfq, len, &h);
     if (!at) return -1;
     if (pe_out && !(h.flags & ORC_PAIRED_END)) return fail("The input RFQ file was encoded by single-end FASTQ, you should not specify <out2>");

@@ -196,6 +196,7 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     cudaFuncSetAttribute(k_streams5, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024);    /* 214.1 KB at 43 streams (two tables), + 7.2 KB static <= 227 KB */
     cudaFuncSetAttribute(k_meta3, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_dec_format4, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
+    cudaFuncSetAttribute(k_dec_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
 #endif
     *out = c;
     return RPQ_OK;

@@ -282,17 +282,109 @@ __device__ __forceinline__ void qx_decode_step(const DecBatchDev& b, const u8* s
     });
 }
 
+/* the shared-memory image of a tile's qualities and N positions, as k_dec_planes leaves it in HBM (one slot per tile) and
+ * k_dec_format4 stages it: plane_cap bytes of qualities (position p of the chunk at byte p - (P0 & ~15)), then the N bitmap */
+__device__ __forceinline__ u32 slot_bytes(const Fmt4Cfg& cfg) { return cfg.plane_cap + 4u * cfg.nbits_words; }
+
 /*
- * k_dec_format4: grid (tiles per chunk, chunks of the window); CTA = G reads of one chunk, two threads per read in different
- * warps as in k_dec_format3.  Shared: quality tile | N bitmap | record staging per output stream.
+ * k_dec_planes: grid (tiles per chunk, chunks), 128 threads.  A tile's qualities: allQual(seqLen, majorQual()) (reference
+ * src/rfqcodec.cpp:1089), then every (stream, step) the tile directory lists as a task of its own - the steps of all streams are
+ * decoded independently and in parallel from their checkpoints (decodeSingleQualByCol :957-1007, exceptions :1034-1043, N
+ * positions :856-858) - and the finished tile goes to its slot with 16-byte stores.  Small CTAs (a tile is 19 KB for 128 reads of
+ * 150 bases): eleven per SM, the loads of a step are hidden behind the other CTAs' steps.
  */
-__global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h, Fmt4Cfg cfg, u32 chunk_first, const uint2* __restrict__ ckpt, const TileDir* __restrict__ dir) {
+constexpr int PL_THREADS = 128;
+__global__ void __launch_bounds__(PL_THREADS) k_dec_planes(DecBatchDev b, HeaderDev h, Fmt4Cfg cfg, u32 chunk_first, const uint2* __restrict__ ckpt, const TileDir* __restrict__ dir, u8* __restrict__ planes) {
     RPQ_DYN_SMEM(dyn);
-    __shared__ u64 s_start[2], s_end[2];
-    __shared__ u32 s_lut_fwd[256], s_lut_rc[256];
     __shared__ u32 s_task;
     __shared__ TileDir s_dir[MAX_BINS + 3];
     __shared__ u32 s_pre[MAX_BINS + 4];                /* tasks before each stream */
+    const int tid = threadIdx.x, lane = tid & 31;
+    const u32 G = cfg.reads_per_cta;
+    const u32 c = chunk_first + blockIdx.y;
+    const DecChunk& ck = b.chunks[c];
+    const u32 r0 = blockIdx.x * G;
+    if (r0 >= ck.reads) return;
+    const u32 n_here = ck.reads - r0 < G ? ck.reads - r0 : G;
+    u8* s_plane = dyn;
+    u32* s_nbits = reinterpret_cast<u32*>(dyn + cfg.plane_cap);
+    const u8* in = b.body + ck.in_off;
+    const bool raw_qual = (h.flags & RPQ_DONT_ENCODE_QUAL) != 0;
+    const bool npos_mode = (h.flags & RPQ_ENCODE_N_POS) != 0;
+    /* ---- the tile's ranges: quality positions [P0, P1) and compacted bases [C0, C1) of the chunk */
+    const u32 i_first = ck.read_base + r0, i_last = i_first + n_here - 1u;
+    const u32 P0 = b.qualoff[i_first], P1 = b.qualoff[i_last] + b.rlen[i_last];
+    const u32 C0 = b.seqoff[i_first], C1 = r0 + n_here < ck.reads ? b.seqoff[i_last + 1u] : ck.seq_kept;
+    const u32 porg = P0 & ~15u, corg = C0 & ~31u;
+    const u32 plane_bytes = ((P1 - porg + 15u) >> 4) << 4;
+    const u32 n_q = raw_qual ? 0u : (u32)h.nb + 1u;                    /* quality streams + exception records */
+    const u32 n_tasks = n_q + (npos_mode ? 1u : 0u);
+    if (tid == 0) s_task = 0;
+    {
+        const TileDir* src = dir + (tile_index(ck, c, G) + blockIdx.x) * cfg.n_streams;
+        for (u32 k = tid; k < n_tasks * (u32)(sizeof(TileDir) / 4); k += blockDim.x) reinterpret_cast<u32*>(s_dir)[k] = reinterpret_cast<const u32*>(src)[k];
+    }
+    /* allQual(seqLen, majorQual()) (src/rfqcodec.cpp:1089) for this tile; DONT_ENCODE_QUAL: the column itself (:903-908) */
+    if (!raw_qual) {
+        const u32 m4 = 0x01010101u * h.major;
+        const uint4 fill = make_uint4(m4, m4, m4, m4);
+        for (u32 k = tid; k < plane_bytes / 16u; k += blockDim.x) reinterpret_cast<uint4*>(s_plane)[k] = fill;
+    } else {
+        const u8* qcol = in + ck.off_qual;
+        const u32 have = ck.qual_size < ck.total_len ? ck.qual_size : ck.total_len;       /* positions the column holds; the rest keeps the major quality */
+        for (u32 p = porg + tid; p < porg + plane_bytes; p += blockDim.x) s_plane[p - porg] = p < have ? qcol[p] : h.major;
+    }
+    for (u32 k = tid; k < cfg.nbits_words; k += blockDim.x) s_nbits[k] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        u32 acc = 0;
+        for (u32 t = 0; t < n_tasks; t++) { s_pre[t] = acc; acc += (n_q && t == n_q - 1u) ? (s_dir[t].len + 31u) / 32u : s_dir[t].n_steps; }
+        s_pre[n_tasks] = acc;
+    }
+    __syncthreads();
+    auto stream_tasks = [&]() {
+        const u32 total = s_pre[n_tasks];
+        const u8* cbase = b.body + ck.in_off;
+        const uint2* cck = ckpt + qx_chunk_base(ck, c, cfg.n_streams);
+        for (;;) {
+            u32 k = 0;
+            if (lane == 0) k = atomicAdd(&s_task, 1u);
+            k = __shfl_sync(0xffffffffu, k, 0);
+            if (k >= total) break;
+            u32 t = 0;                                                 /* the stream of task k: the last one with s_pre[t] <= k */
+            { u32 a = 0, z = n_tasks; while (z - a > 1u) { const u32 m = (a + z) >> 1; if (s_pre[m] <= k) a = m; else z = m; } t = a; }
+            const TileDir& d = s_dir[t];
+            const u32 j = k - s_pre[t];
+            const u32 st = t < n_q ? t : (u32)h.nb + 1u;
+            if (st == h.nb) {
+                /* 32 exception records per task (src/rfqcodec.cpp:1034-1043) */
+                const u32 rec = 32u * j + (u32)lane;
+                if (rec < d.len) { const u8* p = cbase + d.off + 5ull * rec; const u32 pos = ld32(p + 1); if (pos >= P0 && pos < P1 && pos < ck.total_len) s_plane[pos - porg] = p[0]; }
+            } else if (st < h.nb) qx_decode_step<false>(b, cbase + d.off, d.len, d.step0 + j, cck[d.ck + j], P0, P1 < ck.total_len ? P1 : ck.total_len, h.normal_bins[st], s_plane, nullptr, porg, lane);
+            else qx_decode_step<true>(b, cbase + d.off, d.len, d.step0 + j, cck[d.ck + j], C0, C1 < ck.total_len ? C1 : ck.total_len, 0, nullptr, s_nbits, corg, lane);
+        }
+    };
+    stream_tasks();
+    __syncthreads();
+    /* ---- the tile to its slot */
+    {
+        uint4* dst = reinterpret_cast<uint4*>(planes + (size_t)(tile_index(ck, c, G) + blockIdx.x) * slot_bytes(cfg));
+        const uint4* src = reinterpret_cast<const uint4*>(dyn);
+        const u32 nq16 = plane_bytes / 16u, nb16 = cfg.nbits_words / 4u, boff = cfg.plane_cap / 16u;
+        for (u32 k = tid; k < nq16; k += blockDim.x) dst[k] = src[k];
+        for (u32 k = tid; k < nb16; k += blockDim.x) dst[boff + k] = src[boff + k];
+    }
+}
+
+/*
+ * k_dec_format4: grid (tiles per chunk, chunks of the window); CTA = G reads of one chunk, two threads per read in different
+ * warps.  Shared: quality tile | N bitmap (the tile's slot, one TMA bulk copy, awaited only where the qualities are first needed:
+ * the name lines are formatted while it is in flight) | record staging per output stream.
+ */
+__global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h, Fmt4Cfg cfg, u32 chunk_first, const u8* __restrict__ planes) {
+    RPQ_DYN_SMEM(dyn);
+    __shared__ u64 s_start[2], s_end[2];
+    __shared__ u32 s_lut_fwd[256], s_lut_rc[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 G = cfg.reads_per_cta;
     const u32 c = chunk_first + blockIdx.y;
@@ -329,31 +421,8 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
         s_lut_fwd[v] = f; s_lut_rc[v] = r;
     }
     if (tid < 2) { s_start[tid] = ~0ull; s_end[tid] = 0; }
-    if (tid == 0) s_task = 0;
-    {
-        const u32 nt = (raw_qual ? 0u : (u32)h.nb + 1u) + (npos_mode ? 1u : 0u);
-        const TileDir* src = dir + (tile_index(ck, c, G) + blockIdx.x) * cfg.n_streams;
-        for (u32 k = tid; k < nt * (u32)(sizeof(TileDir) / 4); k += blockDim.x) reinterpret_cast<u32*>(s_dir)[k] = reinterpret_cast<const u32*>(src)[k];
-    }
-    /* allQual(seqLen, majorQual()) (src/rfqcodec.cpp:1089) for this tile; DONT_ENCODE_QUAL: the column itself (:1003-1007) */
-    if (!raw_qual) {
-        const u32 m4 = 0x01010101u * h.major;
-        const uint4 fill = make_uint4(m4, m4, m4, m4);
-        for (u32 k = tid; k < plane_bytes / 16u; k += blockDim.x) reinterpret_cast<uint4*>(s_plane)[k] = fill;
-    } else {
-        const u8* qcol = in + ck.off_qual;
-        const u32 have = ck.qual_size < ck.total_len ? ck.qual_size : ck.total_len;       /* positions the column holds; the rest keeps the major quality */
-        for (u32 p = porg + tid; p < porg + plane_bytes; p += blockDim.x) s_plane[p - porg] = p < have ? qcol[p] : h.major;
-    }
-    for (u32 k = tid; k < cfg.nbits_words; k += blockDim.x) s_nbits[k] = 0;
     __syncthreads();
 
-    if (tid == 0) {
-        const u32 nq0 = raw_qual ? 0u : (u32)h.nb + 1u, nt = nq0 + (npos_mode ? 1u : 0u);
-        u32 acc = 0;
-        for (u32 t = 0; t < nt; t++) { s_pre[t] = acc; acc += (nq0 && t == nq0 - 1u) ? (s_dir[t].len + 31u) / 32u : s_dir[t].n_steps; }
-        s_pre[nt] = acc;
-    }
     const bool active = rt < (int)n_here;
     const u32 i = i_first + rt;
     u32 r = 0, rl = 0, stream = 0, olen = 0;
@@ -371,33 +440,36 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
     }
     __syncthreads();
 
-    /* ---- position streams of the tile: every (stream, step) the directory lists is a task of its own; the warps of the sequence
-     * half start at once, the others join when the name lines are done */
-    const u32 n_q = raw_qual ? 0u : (u32)h.nb + 1u;                    /* quality streams + exception records */
-    const u32 n_tasks = n_q + (npos_mode ? 1u : 0u);
-    auto stream_tasks = [&]() {
-        const u32 total = s_pre[n_tasks];
-        const u8* cbase = b.body + ck.in_off;
-        const uint2* cck = ckpt + qx_chunk_base(ck, c, cfg.n_streams);
-        for (;;) {
-            u32 k = 0;
-            if (lane == 0) k = atomicAdd(&s_task, 1u);
-            k = __shfl_sync(0xffffffffu, k, 0);
-            if (k >= total) break;
-            u32 t = 0;                                                 /* the stream of task k: the last one with s_pre[t] <= k */
-            { u32 a = 0, z = n_tasks; while (z - a > 1u) { const u32 m = (a + z) >> 1; if (s_pre[m] <= k) a = m; else z = m; } t = a; }
-            const TileDir& d = s_dir[t];
-            const u32 j = k - s_pre[t];
-            const u32 st = t < n_q ? t : (u32)h.nb + 1u;
-            if (st == h.nb) {
-                /* 32 exception records per task (src/rfqcodec.cpp:1034-1043) */
-                const u32 rec = 32u * j + (u32)lane;
-                if (rec < d.len) { const u8* p = cbase + d.off + 5ull * rec; const u32 pos = ld32(p + 1); if (pos >= P0 && pos < P1 && pos < ck.total_len) s_plane[pos - porg] = p[0]; }
-            } else if (st < h.nb) qx_decode_step<false>(b, cbase + d.off, d.len, d.step0 + j, cck[d.ck + j], P0, P1 < ck.total_len ? P1 : ck.total_len, h.normal_bins[st], s_plane, nullptr, porg, lane);
-            else qx_decode_step<true>(b, cbase + d.off, d.len, d.step0 + j, cck[d.ck + j], C0, C1 < ck.total_len ? C1 : ck.total_len, 0, nullptr, s_nbits, corg, lane);
-        }
+    /* ---- the tile's slot: one TMA bulk copy */
+    const u32 slot_n = slot_bytes(cfg);
+    const u8* slot = planes + (size_t)(tile_index(ck, c, G) + blockIdx.x) * slot_n;
+#ifdef RPQ_EMU
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(slot);
+        uint4* dst = reinterpret_cast<uint4*>(s_plane);
+        for (u32 k = tid; k < plane_bytes / 16u; k += blockDim.x) dst[k] = src[k];
+        for (u32 k = tid; k < cfg.nbits_words / 4u; k += blockDim.x) dst[cfg.plane_cap / 16u + k] = src[cfg.plane_cap / 16u + k];
+    }
+    __syncthreads();
+    auto plane_ready = [&]() {};
+#else
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const u32 mbar = (u32)__cvta_generic_to_shared(&s_mbar);
+    if (tid == 0) {
+        const u32 nbytes = cfg.nbits_words ? slot_n : plane_bytes;
+        asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(mbar), "r"(nbytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((u32)__cvta_generic_to_shared(s_plane)), "l"(slot), "r"(nbytes), "r"(mbar) : "memory");
+    }
+    __syncthreads();                                           /* the barrier object is initialised for everybody */
+    auto plane_ready = [&]() {
+        u32 done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar) : "memory");
     };
-    if (half == 0) stream_tasks();
+#endif
 
     u8* o = nullptr; u32 ls = 0, name_end = 0;
     if (active) {
@@ -434,8 +506,7 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
             o_str[ls + 1 + rl] = '\n';
         } else o[name_end + rl] = '\n';
     }
-    if (half == 1) stream_tasks();
-    __syncthreads();                                               /* the quality tile and the N bitmap are complete */
+    plane_ready();                                                 /* the quality tile and the N bitmap are there */
 
     if (active) {
         const bool il = (fl & RPQ_PE_INTERLEAVED) != 0;

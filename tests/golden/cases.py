@@ -69,6 +69,34 @@ def _numeric_edge_names(name2):
     return b"".join(n + name2 + rec for n in names)
 
 
+def _requalify(r1, n_values, seed, n_with_quality=None, n_rate=0.0):
+    """the records of r1 with qualities drawn from `n_values` distinct characters ('!' upwards); every value occurs in the first
+    reads.  n_with_quality: that character is given to N bases only, and only it (the N-from-quality header), with N bases
+    injected at n_rate."""
+    rng = np.random.RandomState(seed)
+    alphabet = [33 + k for k in range(n_values + (1 if n_with_quality else 0)) if 33 + k != n_with_quality][:n_values - (1 if n_with_quality else 0)]
+    out = []
+    first = True
+    for rec in records(r1):
+        seq = bytearray(rec[1])
+        n = len(seq)
+        q = np.array(alphabet, dtype=np.uint8)[rng.randint(0, len(alphabet), n)]
+        runs = rng.rand(n) < 0.5                                   # half of the positions repeat their predecessor: runs
+        for i in range(1, n):
+            if runs[i]:
+                q[i] = q[i - 1]
+        if first:
+            q[:len(alphabet)] = alphabet[:n] if n < len(alphabet) else alphabet
+            first = False
+        if n_with_quality:
+            for i in range(n):
+                if seq[i] == ord("N") or rng.rand() < n_rate:
+                    seq[i] = ord("N")
+                    q[i] = n_with_quality
+        out.append([rec[0], bytes(seq), rec[2], bytes(bytearray(q))])
+    return join(out)
+
+
 def build_cases():
     """-> list of dict(name, r1, r2|None, k (chunk kilobases), interleaved)"""
     cases = []
@@ -161,4 +189,35 @@ def build_cases():
         if i % 2:
             r[2] = b"+" + r[0][1:]
     add("se_strand_varies_k100", join(recs), k=100)
+
+    # quality alphabets around the 64-value edge of RfqHeader::makeQualityTable (src/rfqheader.cpp:203-234): 63 values + the 0xFF bin
+    # = 64 bins, the largest column-coded header (63 streams); 64 values = DONT_ENCODE_QUAL, the raw quality column of
+    # src/rfqcodec.cpp:612-615 / :903-908; 64 values one of which is the N quality = 64 bins with BOTH flags set (raw wins)
+    base, _ = fqgen.generate(2100, seed=41)
+    add("qual63_se_k100", _requalify(base, 63, 1), k=100)
+    add("qual64_se_k100", _requalify(base, 64, 2), k=100)
+    add("qual64_nqual_se_k100", _requalify(base, 64, 3, n_with_quality=ord("#"), n_rate=0.004), k=100)
+    add("qual63_nqual_se_k100", _requalify(base, 63, 4, n_with_quality=ord("#"), n_rate=0.004), k=100)
+    add("qual65_se_k100", _requalify(base, 65, 5), k=100)
+    add("qual90_se_k100", _requalify(base, 90, 6), k=100)
+    p1, p2 = fqgen.generate(900, seed=42, paired=True)
+    add("qual70_pe_k100", _requalify(p1, 70, 7), _requalify(p2, 70, 8), k=100)       # raw column with reversed R2 qualities, overlaps
+    add("qual64_nqual_pe_k100", _requalify(p1, 64, 9, n_with_quality=ord("#"), n_rate=0.004), _requalify(p2, 64, 10, n_with_quality=ord("#"), n_rate=0.004), k=100)
+
+    # the reference's reader (src/fastqreader.cpp:94-156): lone '\r' line ends, blank lines it swallows, a mix of all three breaks,
+    # no record at all (an EMPTY output file, src/repaq.cpp:530-638), an empty line that ends the input early
+    r1, r2 = fqgen.generate(900, seed=43, paired=True)
+    b1, b2 = bytes(r1), bytes(r2)
+    add("reader_cr_se_k100", b1.replace(b"\n", b"\r"), k=100)
+    add("reader_cr_pe_k100", b1.replace(b"\n", b"\r"), b2.replace(b"\n", b"\r"), k=100)
+    lines = b1.split(b"\n")[:-1]
+    add("reader_mixed_breaks_se_k100", b"".join(ln + (b"\n", b"\r", b"\r\n")[i % 3] for i, ln in enumerate(lines)), k=100)
+    recs = records(b1)
+    add("reader_blank_lines_se_k100", b"".join(b"\n".join(r) + (b"\n\n" if i % 7 == 3 else b"\n") for i, r in enumerate(recs)), k=100)
+    add("reader_blank_inside_record_pe_k100", b1.replace(b"\n+\n", b"\n\n+\n", 40), b2, k=100)
+    add("reader_two_blank_lines_se_k100", join(recs[:500]) + b"\n\n" + join(recs[500:]), k=100)    # the second one is an empty line: input ends
+    add("reader_empty_se", b"")
+    add("reader_empty_pe", b"", b"")
+    add("reader_leading_blank_se", b"\n" + KAT_A1)
+    add("reader_r2_shorter_pe_k100", b1, join(records(b2)[:700]), k=100)              # pairs end with the shorter file
     return cases

@@ -47,6 +47,11 @@ def check_decode_golden(codec, name):
     rfq = golden_rfq(name)
     d = K.decompress(rfq, pe_out=False, codec=codec)
     assert (len(d), sha(d)) == (m["dec_len"], m["dec_sha256"])
+    if m.get("pe_decode_error"):
+        import pytest
+        with pytest.raises(K.RepaqError) as e:
+            K.decompress(rfq, pe_out=True, codec=codec)
+        assert "encoded by single-end FASTQ" in str(e.value)
     if "dec1_sha256" in m:
         d1, d2 = K.decompress(rfq, pe_out=True, codec=codec)
         assert (len(d1), sha(d1)) == (m["dec1_len"], m["dec1_sha256"])

@@ -119,6 +119,24 @@ def test_large_roundtrip_property(codec):
     assert rfq[: len(ref)] == ref
 
 
+class _TorchDevice:
+    """torch only provides the device memory"""
+    @staticmethod
+    def put(arr):
+        import torch
+        t = torch.from_numpy(arr.copy()).cuda()
+        return t, t.data_ptr()
+
+    @staticmethod
+    def get(ptr, n):
+        if not n:
+            return b""
+        host = np.empty(n, dtype=np.uint8)
+        rc = C.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(C.c_void_p(host.ctypes.data), C.c_void_p(ptr), C.c_size_t(n), 2)
+        assert rc == 0
+        return host.tobytes()
+
+
 def test_parallel_chunk_walk(monkeypatch):
     from tests import test_emu_parity as E
     E.test_parallel_chunk_walk(monkeypatch, lib_path=None, mem=_TorchDevice)

@@ -63,6 +63,9 @@ def test_oracle_decode_matches_reference(name):
     assert sha(rfq) == m["rfq_sha256"]
     d = O.decompress(rfq, pe_out=False)
     assert (len(d), sha(d)) == (m["dec_len"], m["dec_sha256"])
+    if m.get("pe_decode_error"):
+        with pytest.raises(O.OracleError):
+            O.decompress(rfq, pe_out=True)
     if "dec1_sha256" in m:
         d1, d2 = O.decompress(rfq, pe_out=True)
         assert (len(d1), sha(d1)) == (m["dec1_len"], m["dec1_sha256"])

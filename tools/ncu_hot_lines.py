@@ -90,6 +90,9 @@ def main():
     print("%-24s %10s %6s %6s %5s  %s" % ("file:line", "warp inst", "inst%", "smpl%", "thr", "source"))
     for loc, (ins, smp, thr) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
         print("%-24s %10d %6.2f %6.2f %5.1f  %s" % ("%s:%d" % loc, ins, 100.0 * ins / max(1, tot_i), 100.0 * smp / max(1, tot_s), thr / max(1, ins), src(loc)))
+    print("---- by stall samples")
+    for loc, (ins, smp, thr) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+        print("%-24s %10d %6.2f %6.2f %5.1f  %s" % ("%s:%d" % loc, ins, 100.0 * ins / max(1, tot_i), 100.0 * smp / max(1, tot_s), thr / max(1, ins), src(loc)))
 
 
 if __name__ == "__main__":
