@@ -37,7 +37,7 @@ def test_header_roundtrip_and_matches_oracle():
         assert used == len(hb) and K.header_bytes(h2) == hb
 
 
-@pytest.mark.parametrize("case", [c for c in build_cases() if not c["name"].startswith("name")][:40], ids=lambda c: c["name"])
+@pytest.mark.parametrize("case", [c for c in build_cases() if not c["name"].startswith("name")], ids=lambda c: c["name"])
 def test_host_make_header_matches_reference_on_goldens(case):
     from tests.conftest import golden_rfq
     import json
@@ -45,6 +45,9 @@ def test_host_make_header_matches_reference_on_goldens(case):
     if man[case["name"]].get("error"):
         pytest.skip("reference rejects this input")
     h = K.make_header(case["r1"], case["r2"], case["interleaved"], max(100, case["k"]) * 1000)
+    if man[case["name"]]["rfq_len"] == 0:
+        assert h is None                     # no record: the reference leaves an empty output (RPQ_NO_RECORDS)
+        return
     assert golden_rfq(case["name"]).startswith(K.header_bytes(h))
 
 
