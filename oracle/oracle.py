@@ -43,6 +43,8 @@ def lib():
         L.orc_meta_parse.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(Meta)]
         L.orc_compress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_uint32,
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.orc_compress_with_header.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_uint32,
+                                               C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.orc_decompress.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.orc_free.argtypes = [C.c_void_p]
@@ -79,6 +81,20 @@ def compress(r1, r2=None, chunk_bases=1000000, interleaved=False) -> bytes:
     p1, l1 = _as_buf(r1)
     p2, l2 = (None, 0) if r2 is None else _as_buf(r2)
     rc = lib().orc_compress(p1, l1, p2, l2, int(interleaved), chunk_bases, C.byref(out), C.byref(n))
+    if rc:
+        raise OracleError(lib().orc_last_error().decode())
+    data = C.string_at(out.value, n.value) if n.value else b""
+    lib().orc_free(out)
+    return data
+
+
+def compress_with_header(header: bytes, r1, r2=None, chunk_bases=1000000, interleaved=False) -> bytes:
+    """the chunks of r1 (/r2) encoded with the given serialised file header - no header in the result"""
+    out = C.c_void_p()
+    n = C.c_size_t()
+    p1, l1 = _as_buf(r1)
+    p2, l2 = (None, 0) if r2 is None else _as_buf(r2)
+    rc = lib().orc_compress_with_header(header, len(header), p1, l1, p2, l2, int(interleaved), chunk_bases, C.byref(out), C.byref(n))
     if rc:
         raise OracleError(lib().orc_last_error().decode())
     data = C.string_at(out.value, n.value) if n.value else b""

@@ -779,14 +779,15 @@ static void rv_push(readvec* rv, const orc_read* r) {
 static void rv_clear(readvec* rv) { for (size_t i = 0; i < rv->n; i++) free(rv->own[i]); rv->n = 0; }
 
 /* src/repaq.cpp:530-638 (compress), :640-759 (compressPE); FastqReaderPair::read src/fastqreader.cpp:287-299 */
-int orc_compress(const char* r1, size_t l1, const char* r2, size_t l2, int interleaved, uint32_t chunk_bases,
-                 uint8_t** out, size_t* out_len) {
+static int compress_impl(const char* r1, size_t l1, const char* r2, size_t l2, int interleaved, uint32_t chunk_bases,
+                         const orc_header* fixed, uint8_t** out, size_t* out_len) {
     const int is_pe = (r2 != NULL) || interleaved;
     orc_reader* a = orc_reader_open(r1, l1);
     orc_reader* b = (r2 != NULL) ? orc_reader_open(r2, l2) : NULL;
     sink o = {0, 0, 0};
     readvec rv = {0, 0, 0, 0};
     orc_header h; int have_header = 0;
+    if (fixed) { h = *fixed; have_header = 1; }       /* a later part of a sharded file: the header of chunk 0 is given, only chunks are written */
     uint32_t total = 0; int rc = 0;
     for (;;) {
         orc_read x, y; int got = orc_reader_next(a, &x);
@@ -822,6 +823,21 @@ int orc_compress(const char* r1, size_t l1, const char* r2, size_t l2, int inter
     if (rc) { free(o.p); return rc; }
     *out = o.p; *out_len = o.n;
     return 0;
+}
+
+int orc_compress(const char* r1, size_t l1, const char* r2, size_t l2, int interleaved, uint32_t chunk_bases,
+                 uint8_t** out, size_t* out_len) {
+    return compress_impl(r1, l1, r2, l2, interleaved, chunk_bases, NULL, out, out_len);
+}
+
+/* The chunks of a text encoded with a GIVEN file header (serialised, as RfqHeader::write leaves it): what Repaq::compress writes
+ * after the header for these records when its first chunk - the one the header is made from, src/repaq.cpp:554-566 - was
+ * somewhere else.  Checker for chunk-sharded encodes: every rank encodes with rank 0's header. */
+int orc_compress_with_header(const uint8_t* header, size_t header_len, const char* r1, size_t l1, const char* r2, size_t l2, int interleaved,
+                             uint32_t chunk_bases, uint8_t** out, size_t* out_len) {
+    orc_header h;
+    if (!orc_header_read(header, header_len, &h)) return -1;
+    return compress_impl(r1, l1, r2, l2, interleaved, chunk_bases, &h, out, out_len);
 }
 
 /* src/repaq.cpp:262-333 (decompress), :335-413 (decompressPE) */

@@ -121,6 +121,9 @@ size_t orc_decode_chunk(const orc_header* h, const uint8_t* in, size_t len, orc_
  * interleaved != 0). chunk_bases = Options::chunkSize. */
 int orc_compress(const char* r1, size_t l1, const char* r2, size_t l2, int interleaved, uint32_t chunk_bases,
                  uint8_t** out, size_t* out_len);
+/* the chunks only, encoded with a given serialised file header (chunk-sharded encodes: every part uses the header of chunk 0) */
+int orc_compress_with_header(const uint8_t* header, size_t header_len, const char* r1, size_t l1, const char* r2, size_t l2, int interleaved,
+                             uint32_t chunk_bases, uint8_t** out, size_t* out_len);
 /* Repaq::decompress (pe_out == 0) / decompressPE (pe_out != 0) (src/repaq.cpp:262-413) */
 int orc_decompress(const uint8_t* rfq, size_t len, int pe_out, char** out1, size_t* l1, char** out2, size_t* l2);
 

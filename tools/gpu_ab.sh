@@ -9,8 +9,8 @@ i=0
 for KV in "$@"; do
   i=$((i+1))
   echo "== bench [$KV]"
-  if [ "$KV" = "-" ]; then timeout 900 python bench.py --no-e2e --no-cpu > gpurun_out/ab_$i.log 2>&1
-  else env $KV timeout 900 python bench.py --no-e2e --no-cpu > gpurun_out/ab_$i.log 2>&1; fi
+  if [ "$KV" = "-" ]; then timeout 900 python bench.py --no-e2e --no-cpu --no-extra > gpurun_out/ab_$i.log 2>&1
+  else env $KV timeout 900 python bench.py --no-e2e --no-cpu --no-extra > gpurun_out/ab_$i.log 2>&1; fi
   echo "rc=$? $KV" >> gpurun_out/ab_$i.log
   tail -c 1800 gpurun_out/ab_$i.log
 done

@@ -14,7 +14,7 @@ echo "== bench reference arm"; timeout 900 python bench.py --impl reference --st
 echo "== other shapes"; timeout 600 python tools/shape_probe.py 4000000 > gpurun_out/shapes.log 2>&1; echo "rc=$?"; cut -c1-400 gpurun_out/shapes.log
 echo "== ncu dram counters, full size"
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:^k_ -s ${SKIP:-150} -c ${CNT:-130} --csv --log-file gpurun_out/traffic_full.csv \
-    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-roofline > gpurun_out/ncu_traffic.log 2>&1; echo "rc=$?"
+    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-roofline --no-extra > gpurun_out/ncu_traffic.log 2>&1; echo "rc=$?"
 for K in ${NCU_KERNELS:-k_streams4 k_dec_format3 k_meta3 k_dec_streams}; do
-  echo "== ncu full $K"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -f -o gpurun_out/prof_$K python bench.py --pairs 600000 --steps 1 --warmup 3 --no-e2e --no-cpu --no-roofline > gpurun_out/ncu_$K.log 2>&1; echo "rc=$?"
+  echo "== ncu full $K"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -f -o gpurun_out/prof_$K python bench.py --pairs 600000 --steps 1 --warmup 3 --no-e2e --no-cpu --no-roofline --no-extra > gpurun_out/ncu_$K.log 2>&1; echo "rc=$?"
 done
