@@ -617,6 +617,72 @@ void orc_decoded_free(orc_decoded* d) { free(d->text); free(d->read_end); memset
 static size_t put_dec(char* p, uint32_t v) { char t[12]; int n = 0; do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v); for (int i = 0; i < n; i++) p[i] = t[n - 1 - i]; return (size_t)n; }
 
 /* RfqChunk::read (src/rfqchunk.cpp:161-228, arena sizes derived :63-109) + RfqCodec::decodeChunk (src/rfqcodec.cpp:1049-1260) */
+/* ---- the quality run-length coder that ALGORITHM_VER 2 never selects (Q7: makeQualityTable always sets DONT_ENCODE_QUAL or
+ * ENCODE_QUAL_BY_COL), restated so that a header with neither flag decodes as the reference decodes it. */
+/* RfqHeader::makeQualBitTable / computeNormalQualBits: src/rfqheader.cpp:103-128 (tables zeroed by the constructor's memset, :8) */
+static void rle_tables(const orc_header* h, signed char bit2qual[256], signed char qual2bit[256], int* nq_bits) {
+    memset(bit2qual, 0, 256); memset(qual2bit, 0, 256);
+    for (int i = 0; i < h->qual_bins; i++) {
+        const uint8_t q = h->qual_buf[i];
+        const int bit = i > 0 ? 2 * i - 1 : 0;
+        qual2bit[q] = (signed char)bit; bit2qual[(uint8_t)bit] = (signed char)q;
+    }
+    int mx = h->qual_bins * 2 - 3; if (mx < 1) mx = 1;
+    *nq_bits = mx >= 64 ? 1 : mx >= 32 ? 2 : mx >= 16 ? 3 : mx >= 8 ? 4 : mx >= 4 ? 5 : mx >= 2 ? 6 : 7;
+}
+/* RfqCodec::decodeQualByRunLenCoding: src/rfqcodec.cpp:919-955.  The outer `while (decoded < len)` walks the column again from its
+ * first byte when it runs out before len positions are filled; an empty column never terminates there (reported as an error). */
+static int rle_decode(const orc_header* h, const uint8_t* col, uint32_t col_size, char* qual, uint32_t len) {
+    signed char b2q[256], q2b[256]; int nq_bits;
+    rle_tables(h, b2q, q2b, &nq_bits);
+    const int mq_bits = 7;                                       /* majorQualNumBits(): src/rfqheader.cpp:255-257 */
+    uint8_t nq_mask = 0;
+    for (int b = 0; b < 8 - nq_bits; b++) nq_mask |= (uint8_t)(1 << b);
+    if (len && !col_size) { fail("quality run-length column is empty"); return -1; }
+    uint32_t decoded = 0;
+    while (decoded < len) {
+        for (uint32_t i = 0; i < col_size; i++) {
+            const uint8_t e = col[i];
+            signed char q; uint8_t num;
+            if ((e & 1) == 0) { q = 0; num = (uint8_t)(e >> (8 - mq_bits)); }
+            else { q = (signed char)(e & nq_mask); num = (uint8_t)(e >> (8 - nq_bits)); }
+            num = (uint8_t)(num + 1);
+            const char v = (char)b2q[(uint8_t)q];
+            for (uint32_t f = decoded; f < decoded + num && f < len; f++) qual[f] = v;
+            decoded += num;
+            if (decoded >= len) break;
+        }
+    }
+    return 0;
+}
+/* RfqCodec::encodeQualRunLenCoding: src/rfqcodec.cpp:767-824 (test-vector construction only: no header the reference makes selects it) */
+size_t orc_rle_encode(const orc_header* h, const uint8_t* qual, uint32_t len, uint8_t* out) {
+    signed char b2q[256], q2b[256]; int nq_bits;
+    rle_tables(h, b2q, q2b, &nq_bits);
+    const int mq_bits = 7, mq_max = 1 << mq_bits, nq_max = 1 << nq_bits;
+    const char mq = (char)b2q[0];
+    size_t n = 0;
+    if (!len) return 0;
+    char cur = (char)qual[0]; uint32_t first = 0;
+    for (uint32_t i = 1; i <= len; i++) {
+        int restart = i == len;
+        if (!restart) {
+            const char q = (char)qual[i];
+            if (q != cur) restart = 1;
+            else if (cur == mq && (int)(i - first) >= mq_max) restart = 1;
+            else if (cur != mq && (int)(i - first) >= nq_max) restart = 1;
+        }
+        if (restart) {
+            const uint8_t num = (uint8_t)(i - first - 1);
+            const uint8_t bit = (uint8_t)q2b[(uint8_t)cur];
+            out[n++] = (uint8_t)(bit | (uint8_t)(num << (8 - (cur == mq ? mq_bits : nq_bits))));
+            first = i;
+            if (i < len) cur = (char)qual[i];
+        }
+    }
+    return n;
+}
+
 size_t orc_decode_chunk(const orc_header* h, const uint8_t* in, size_t len, orc_decoded* out) {
     memset(out, 0, sizeof *out);
     src_t s = {in, len, 0, 0};
@@ -712,7 +778,7 @@ size_t orc_decode_chunk(const orc_header* h, const uint8_t* in, size_t len, orc_
                 c += 5;
                 if (pos < L) qual[pos] = q;
             }
-        }
+        } else if (rle_decode(h, qualb, qual_size, qual, L)) { free(seq); free(qual); return 0; }
     }
     if (!(h->flags & ORC_ENCODE_N_POS))                              /* :1093-1100 */
         for (uint32_t i = 0; i < L; i++) if (qual[i] == (char)h->n_base_qual) seq[i] = 'N';

@@ -149,6 +149,9 @@ void build_header_dev(const rpq_header& h, HeaderDev& d) {
     d.nb = (u8)nb;
     for (int i = 0; i < 256; i++) d.lut[i] = (i == d.major) ? LUT_SKIP : LUT_EXC;
     for (int i = nb - 1; i >= 0; i--) { d.normal_bins[i] = nbuf[i]; d.lut[nbuf[i]] = (u8)i; }
+    /* the tables of the quality run-length coder (decode only, row a10): makeQualBitTable / computeNormalQualBits */
+    for (int i = 0; i < h.qual_bins; i++) { const int bit = i > 0 ? 2 * i - 1 : 0; if (bit < 128) d.rle_b2q[bit] = h.qual_buf[i < 128 ? i : 127]; }
+    { int mx = (int)h.qual_bins * 2 - 3; if (mx < 1) mx = 1; d.rle_nq_bits = (u8)(mx >= 64 ? 1 : mx >= 32 ? 2 : mx >= 16 ? 3 : mx >= 8 ? 4 : mx >= 4 ? 5 : mx >= 2 ? 6 : 7); }
 }
 
 }  // namespace
@@ -257,8 +260,6 @@ extern "C" int rpq_set_header(rpq_ctx* c, const rpq_header* h) {
     if (!c || !h) return RPQ_ERR_ARG;
     if (h->read_length_bytes != 1 && h->read_length_bytes != 2 && h->read_length_bytes != 4)
         return fail(c, RPQ_ERR_HEADER, "header incorrect: read length bytes should be 1/2/4");
-    if (!(h->flags & RPQ_DONT_ENCODE_QUAL) && !(h->flags & RPQ_ENCODE_QUAL_BY_COL))
-        return fail(c, RPQ_ERR_HEADER, "header selects the quality run-length coder, which ALGORITHM_VER 2 never produces");
     c->hdr = *h; c->have_hdr = true;
     build_header_dev(*h, c->hd);
     return RPQ_OK;

@@ -36,6 +36,8 @@ struct HeaderDev {
     u8 nb;                    /* normalQualBins() */
     u8 normal_bins[MAX_BINS + 1];  /* normalQualBuf() order = stream order */
     u8 lut[256];              /* quality byte -> stream index | LUT_SKIP | LUT_EXC */
+    u8 rle_b2q[128];          /* mBit2QualTable (src/rfqheader.cpp:103-115): code of the quality run-length coder -> quality */
+    u8 rle_nq_bits;           /* mNormalQualNumBits (src/rfqheader.cpp:117-128) */
 };
 
 /* error bits raised by kernels (per batch) */

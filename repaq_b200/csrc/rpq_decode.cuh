@@ -426,6 +426,57 @@ __global__ void __launch_bounds__(32 * DS_WARPS) k_dec_streams(DecBatchDev b, He
     }
 }
 
+/*
+ * decodeQualByRunLenCoding (src/rfqcodec.cpp:919-955): the coder no header made under ALGORITHM_VER 2 selects (Q7), kept so that a
+ * header with neither DONT_ENCODE_QUAL nor ENCODE_QUAL_BY_COL decodes as the reference decodes it.  Every column byte is a run:
+ * bit 0 clear = the major quality, run length in the upper 7 bits; else code = low (8 - nq_bits) bits, run in the upper nq_bits;
+ * lengths count from 1.  A column that runs out before the chunk's positions are filled is walked again from its first byte.
+ * One CTA per chunk: total run length, then a scan of the runs and the fills.  Works on the plane of the long-read path.
+ */
+__global__ void __launch_bounds__(256) k_dec_rle(DecBatchDev b, HeaderDev h) {
+    __shared__ u32 s_w[8];
+    __shared__ u32 s_carry;
+    const DecChunk& ck = b.chunks[blockIdx.x];
+    const u8* col = b.body + ck.in_off + ck.off_qual;
+    const u32 n = ck.qual_size, len = ck.total_len;
+    u8* plane = b.plane + ck.plane_off;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!len) return;
+    if (!n) { if (tid == 0) atomicOr(b.err, ERRBIT_RFQ); return; }       /* the reference never returns from this one */
+    const u32 nq_mask = (1u << (8u - h.rle_nq_bits)) - 1u;
+    auto run_of = [&](u32 e) -> u32 { return ((e & 1u) ? (e >> (8u - h.rle_nq_bits)) : (e >> 1)) + 1u; };
+    /* ---- total positions of one walk over the column */
+    u32 mine = 0;
+    for (u32 k = tid; k < n; k += 256) mine += run_of(col[k]);
+    mine = warp_sum(mine);
+    if (lane == 0) s_w[warp] = mine;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    u32 T = 0;
+    for (int q = 0; q < 8; q++) T += s_w[q];
+    __syncthreads();
+    /* ---- runs -> positions */
+    for (u32 base = 0; base < n; base += 256) {
+        const u32 k = base + (u32)tid;
+        const u32 e = k < n ? col[k] : 0u;
+        const u32 run = k < n ? run_of(e) : 0u;
+        u32 wt; const u32 ex = warp_excl_scan(run, lane, wt);
+        if (lane == 0) s_w[warp] = wt;
+        __syncthreads();
+        u32 start = s_carry + ex;
+        for (int q = 0; q < warp; q++) start += s_w[q];
+        if (run) {
+            const u8 v = h.rle_b2q[(e & 1u) ? (e & nq_mask) & 127u : 0u];
+            for (u64 p0 = start; p0 < len; p0 += T)                        /* this walk of the column, and every later one */
+                for (u32 f = 0; f < run && p0 + f < len; f++) plane[p0 + f] = v;
+        }
+        __syncthreads();
+        if (tid == 0) { u32 t = s_carry; for (int q = 0; q < 8; q++) t += s_w[q]; s_carry = t; }
+        __syncthreads();
+        if (s_carry >= len) break;                                         /* like the reference: stop once len positions are decoded */
+    }
+}
+
 /* ------------------------------------------------------------------ record formatter ---- */
 constexpr int FMT_WARPS = 8;
 

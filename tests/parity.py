@@ -71,3 +71,17 @@ def check_against_oracle(codec, r1, r2=None, k=1000, interleaved=False, roundtri
     if roundtrip:
         assert dec == ((r1b, r2b) if pe else r1b)
     return len(exp)
+
+
+RLE_MAN = json.load(open(os.path.join(ROOT, "tests", "golden", "rle_manifest.json")))
+
+
+def check_decode_rle_golden(codec, name):
+    """row a10: the quality run-length coder (decode only), against what the reference binary decodes"""
+    m = RLE_MAN[name]
+    rfq = golden_rfq(name)
+    d = K.decompress(rfq, pe_out=False, codec=codec)
+    assert (len(d), sha(d)) == (m["dec_len"], m["dec_sha256"])
+    if "dec1_sha256" in m:
+        d1, d2 = K.decompress(rfq, pe_out=True, codec=codec)
+        assert (sha(d1), sha(d2)) == (m["dec1_sha256"], m["dec2_sha256"])

@@ -37,6 +37,11 @@ def test_decode_golden(codec, name):
     parity.check_decode_golden(codec, name)
 
 
+@pytest.mark.parametrize("name", sorted(parity.RLE_MAN))
+def test_decode_run_length_quality_golden(codec, name):
+    parity.check_decode_rle_golden(codec, name)
+
+
 def test_seeded_pe_against_oracle(codec):
     from tools import fqgen
     r1, r2 = fqgen.generate(9000, seed=31, paired=True)

@@ -35,6 +35,11 @@ def test_decode_golden(codec, name):
     parity.check_decode_golden(codec, name)
 
 
+@pytest.mark.parametrize("name", sorted(parity.RLE_MAN))
+def test_decode_run_length_quality_golden(codec, name):
+    parity.check_decode_rle_golden(codec, name)
+
+
 def test_config0_se_50k_reads(codec):
     """BASELINE.json configs[0]: single-end 50k-read 150bp, encode == reference algorithm, decode restores the input"""
     from tools import fqgen

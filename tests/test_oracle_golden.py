@@ -80,3 +80,20 @@ def test_oracle_vs_live_reference(tmp_path):
     ref = O.ref_compress(str(tmp_path), bytes(r1), bytes(r2))
     assert O.compress(r1, r2) == ref
     assert O.decompress(ref, pe_out=True) == O.ref_decompress(str(tmp_path), ref, pe_out=True)
+
+
+RLE_MAN = json.load(open(os.path.join(ROOT, "tests", "golden", "rle_manifest.json")))
+
+
+@pytest.mark.parametrize("name", sorted(RLE_MAN))
+def test_oracle_decodes_run_length_quality_like_the_reference(name):
+    """row a10: files whose header selects the quality run-length coder (never written under ALGORITHM_VER 2, still decoded by the
+    reference): made by tests/golden/make_rle_golden.py, decoded by the unmodified reference binary"""
+    m = RLE_MAN[name]
+    rfq = golden_rfq(name)
+    assert sha(rfq) == m["rfq_sha256"]
+    d = O.decompress(rfq, pe_out=False)
+    assert (len(d), sha(d)) == (m["dec_len"], m["dec_sha256"])
+    if "dec1_sha256" in m:
+        d1, d2 = O.decompress(rfq, pe_out=True)
+        assert (sha(d1), sha(d2)) == (m["dec1_sha256"], m["dec2_sha256"])
