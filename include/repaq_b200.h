@@ -199,6 +199,12 @@ typedef struct rpq_compare_out {
 
 int rpq_compare(rpq_ctx* ctx, const rpq_compare_in* in, rpq_compare_out* out);
 
+/* ---- page-locked host memory for callers that stream files through the library (the host<->device copies of rpq_encode /
+ * rpq_decode / rpq_compare run at full link speed from such buffers, and overlap with kernels).  No counterpart in the reference,
+ * whose reader refills a 1 MiB heap buffer (src/fastqreader.cpp:5,31-46). */
+void* rpq_host_alloc(size_t bytes);
+void rpq_host_free(void* p);
+
 /* ---- instrumentation for bench.py: kernels launched and device milliseconds (CUDA events on the context's
  * stream) of the last rpq_encode / rpq_decode call, split by stage. */
 typedef struct rpq_stats {

@@ -63,7 +63,8 @@ class Stats(C.Structure):
 
 
 EXPORTS = ["rpq_make_header", "rpq_header_write", "rpq_header_read", "rpq_create", "rpq_destroy", "rpq_last_error",
-           "rpq_set_header", "rpq_stream", "rpq_encode", "rpq_decode", "rpq_compare", "rpq_get_stats", "rpq_set_profiling", "rpq_get_profile"]
+           "rpq_set_header", "rpq_stream", "rpq_encode", "rpq_decode", "rpq_compare", "rpq_get_stats", "rpq_set_profiling", "rpq_get_profile",
+           "rpq_host_alloc", "rpq_host_free"]
 
 _libs = {}
 

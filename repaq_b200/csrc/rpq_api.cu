@@ -256,6 +256,9 @@ extern "C" const char* rpq_get_profile(rpq_ctx* c) {
     return c->prof_text.c_str();
 }
 
+extern "C" void* rpq_host_alloc(size_t bytes) { return rt_malloc_pinned(bytes); }
+extern "C" void rpq_host_free(void* p) { rt_free_pinned(p); }
+
 extern "C" int rpq_set_header(rpq_ctx* c, const rpq_header* h) {
     if (!c || !h) return RPQ_ERR_ARG;
     if (h->read_length_bytes != 1 && h->read_length_bytes != 2 && h->read_length_bytes != 4)
