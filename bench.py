@@ -930,6 +930,49 @@ def main():
         parity = dict(encode_bytes=acc["enc"], decode_bytes=acc["dec"], shards=acc["shards"], against="oracle/_ref/repaq (the unmodified reference binary)" if cpu["kind"] == "reference" else "oracle/ (C port)",
                       how="every shard of the cpu_baseline sample: GPU .rfq == the reference's .rfq file byte for byte, GPU decode of the reference's .rfq == the reference's decoded FASTQ")
 
+    # ---- the command-line drivers against each other (rank 0, N=1): repaq_b200_cli on the whole 3.4 GB pair, the unmodified reference
+    # binary on a bounded sample of it, files in /dev/shm, wall clock of the whole process (start-up, file I/O, copies included)
+    cli = None
+    cli_bin = os.path.join(ROOT, "repaq_b200", "repaq_b200_cli")
+    if rank == 0 and world == 1 and not args.no_cpu and os.path.exists(cli_bin) and os.path.isdir("/dev/shm"):
+        tmp = tempfile.mkdtemp(dir="/dev/shm")
+        try:
+            r1.tofile(os.path.join(tmp, "a.fq"))
+            r2.tofile(os.path.join(tmp, "b.fq"))
+
+            def wall(cmd):
+                t = time.perf_counter()
+                subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                return time.perf_counter() - t
+            t_c = wall([cli_bin, "-c", "-i", f"{tmp}/a.fq", "-I", f"{tmp}/b.fq", "-o", f"{tmp}/o.rfq", "--device=%d" % local])
+            t_d = wall([cli_bin, "-d", "-i", f"{tmp}/o.rfq", "-o", f"{tmp}/d1.fq", "-O", f"{tmp}/d2.fq", "--device=%d" % local])
+            same = all(np.array_equal(np.fromfile(os.path.join(tmp, a), dtype=np.uint8), b) for a, b in (("d1.fq", r1), ("d2.fq", r2)))
+            assert same, "repaq_b200_cli: decoded files differ from the inputs"
+            rfq_file = np.fromfile(os.path.join(tmp, "o.rfq"), dtype=np.uint8)
+            assert rfq_file.size == len(hb) + rfq_b and bytes(rfq_file[:len(hb)]) == hb
+            cli = dict(files="%.2f GB pair in /dev/shm" % (fastq_bytes / 1e9), gpu_cli=dict(encode_s=t_c, decode_s=t_d, encode_gbs=fastq_bytes / 1e9 / t_c, decode_gbs=fastq_bytes / 1e9 / t_d,
+                                                                                          roundtrip_gbs=fastq_bytes / 1e9 / (t_c + t_d)),
+                       verified="decoded files byte-identical to the inputs; .rfq size and header equal to the library's")
+            for n in ("o.rfq", "d1.fq", "d2.fq"):
+                os.unlink(os.path.join(tmp, n))
+            if O.have_ref():
+                n_pairs = min(hi - lo, 600000)                # ~0.43 GB: ~4 s per direction for the single-threaded reference
+                s1, s2 = fqgen.truncate_reads(r1, n_pairs), fqgen.truncate_reads(r2, n_pairs)
+                s1.tofile(os.path.join(tmp, "sa.fq"))
+                s2.tofile(os.path.join(tmp, "sb.fq"))
+                sb = int(s1.size + s2.size)
+                r_c = wall([O.REF_BIN, "-c", "-i", f"{tmp}/sa.fq", "-I", f"{tmp}/sb.fq", "-o", f"{tmp}/s.rfq"])
+                r_d = wall([O.REF_BIN, "-d", "-i", f"{tmp}/s.rfq", "-o", f"{tmp}/s1.fq", "-O", f"{tmp}/s2.fq"])
+                g_c = wall([cli_bin, "-c", "-i", f"{tmp}/sa.fq", "-I", f"{tmp}/sb.fq", "-o", f"{tmp}/g.rfq", "--device=%d" % local])
+                assert open(f"{tmp}/s.rfq", "rb").read() == open(f"{tmp}/g.rfq", "rb").read(), "repaq_b200_cli and the reference binary wrote different .rfq files"
+                cli["reference_cli"] = dict(sample="%.2f GB pair (the first %d pairs of the same files), one process, one thread" % (sb / 1e9, n_pairs), encode_s=r_c, decode_s=r_d,
+                                            encode_gbs=sb / 1e9 / r_c, decode_gbs=sb / 1e9 / r_d, roundtrip_gbs=sb / 1e9 / (r_c + r_d))
+                cli["same_sample_gpu_cli_encode_s"] = g_c
+                cli["verified"] += "; on the sample both drivers wrote the same .rfq file byte for byte"
+                cli["roundtrip_ratio"] = cli["gpu_cli"]["roundtrip_gbs"] / cli["reference_cli"]["roundtrip_gbs"]
+        finally:
+            subprocess.call(["rm", "-rf", tmp])
+
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=W, ms_per_step=dev_ms / args.steps,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8", data="synthetic",
@@ -944,7 +987,7 @@ def main():
                                   verified="every rank: first and last 6 chunks bit-exact against the oracle run with the broadcast header; decode == input; offsets from the gathered lengths" + ("; " + seam_note if seam_note else "")),
                     parity_checked_bytes=dict(oracle_per_rank=oracle_checked, reference_binary=parity),
                     decode_chunk_walk={1: "one warp on the mSize chain", 2: "16 warps on the mSize chain (k_dec_walk_par)", 3: "exact sequential walk"}.get(state.get("dec_walk"), "host"), clocks=clk, e2e=e2e, roofline=roofline, cpu_baseline=cpu,
-                    configs=extra or None)
+                    configs=extra or None, cli_e2e=cli)
         print(json.dumps(line))
     xch.close()
     enc.close()

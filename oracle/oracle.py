@@ -19,6 +19,17 @@ def build(force=False):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
 
 
+REF_GPU_BIN = os.path.join(HERE, "_ref_gpu", "repaq")
+REF_GPU_EMU_BIN = os.path.join(HERE, "_ref_gpu", "repaq_emu")
+
+
+def build_ref_gpu():
+    """The reference's own main / Options / Writer with Repaq::run routed into librepaq_b200 (integration/repaq_gpu.cpp): built from
+    the reference sources where they lie, when they are present; the GPU box uses the prebuilt binaries."""
+    if os.path.isdir("/root/reference/src"):
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref_gpu"])
+
+
 class Header(C.Structure):
     _fields_ = [("read_length_bytes", C.c_uint8), ("flags", C.c_uint16), ("name2_diff_pos", C.c_uint8),
                 ("name2_diff_char", C.c_char), ("n_base_qual", C.c_int8), ("overlap_shift", C.c_int8),
