@@ -8,8 +8,8 @@
  * program through the `xz` executable (src/main.cpp:133-178), the compare report of reportCompareResult (src/repaq.cpp:235-259).
  *
  * Where it differs by design: files are STREAMED.  A reader thread per input fills page-locked windows (rpq_host_alloc) while the
- * GPU works on the previous one, results leave through a writer thread; host memory is bounded whatever the file size
- * (the reference's reader refills one 1 MiB buffer, src/fastqreader.cpp:5,31-46).
+ * GPU works on the previous one (64 MiB of text per file and window, 16 MiB of .rfq when decoding), results leave through a writer
+ * thread; host memory is bounded whatever the file size (the reference's reader refills one 1 MiB buffer, src/fastqreader.cpp:5,31-46).
  * -v / -f: every batch is decoded again and checked against its input on the GPU (rpq_compare) after it has been written, the
  * first difference is reported on stderr in the words of completeCheckAndOutput (src/repaq.cpp:430-528); like the reference, the
  * output is written either way.  (The reference's -f checks every tenth chunk to save CPU time, src/repaq.cpp:575; here -f checks
@@ -93,6 +93,12 @@ struct Sink {
     void close() { if (gz) { gzflush(gz, Z_FINISH); gzclose(gz); } else if (f) { if (f == stdout) fflush(f); else fclose(f); } gz = nullptr; f = nullptr; }
 };
 
+#include <chrono>
+static void stamp(const char* what) {                    /* RPQ_CLI_TIMING=1: where the wall time of a run goes */
+    static const bool on = getenv("RPQ_CLI_TIMING") != NULL;
+    static const auto t0 = std::chrono::steady_clock::now();
+    if (on) fprintf(stderr, "[cli %8.1f ms] %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), what);
+}
 static size_t env_size(const char* name, size_t dflt) { const char* e = getenv(name); if (!e) return dflt; const unsigned long long v = strtoull(e, NULL, 10); return v ? (size_t)v : dflt; }
 
 /*
@@ -109,8 +115,7 @@ public:
     void start(const std::string& path, size_t head_bytes, size_t cap_bytes, int n_windows) {
         src_.open(path); head = head_bytes; cap = cap_bytes;
         win_.resize(n_windows); state_.assign(n_windows, 0); want_.assign(n_windows, cap_bytes);
-        for (Window& w : win_) { w.base = (char*)rpq_host_alloc(head + cap + 64); if (!w.base) error_exit("out of page-locked host memory (no CUDA device?): repaq_b200 has no CPU fallback"); }
-        th_ = std::thread([this] { run(); });
+        th_ = std::thread([this] { run(); });             /* a window's buffer is page-locked when the reader first needs it: short inputs pay for one */
     }
     /* window k (in order); blocks until it has been read */
     Window* get(uint64_t k) {
@@ -142,6 +147,7 @@ private:
                 state_[s] = 1; want = want_[s];
             }
             Window& w = win_[s];
+            if (!w.base) { w.base = (char*)rpq_host_alloc(head + cap + 64); if (!w.base) error_exit("out of page-locked host memory (no CUDA device?): repaq_b200 has no CPU fallback"); }
             w.n = src_.read(w.base + head, want);
             w.eof = w.n < want;
             {
@@ -228,17 +234,20 @@ static int do_compress(const Opt& o) {
     const uint32_t chunk_bases = (uint32_t)(o.k < 100 ? 100 : o.k) * 1000u;        /* src/main.cpp:69 */
     /* a window holds at least six chunks of text (a chunk of b bases is ~2.5 b bytes of FASTQ per file); the room in front of it
      * takes what a call leaves uncovered: at most a chunk, plus the drift between two files whose records differ in length */
-    size_t win = env_size("RPQ_CLI_FQ_WINDOW", 256u << 20), head = env_size("RPQ_CLI_FQ_HEAD", 64u << 20);
+    size_t win = env_size("RPQ_CLI_FQ_WINDOW", 64u << 20), head = env_size("RPQ_CLI_FQ_HEAD", 32u << 20);
     if (!getenv("RPQ_CLI_FQ_WINDOW") && (uint64_t)chunk_bases * 15 > win) win = (size_t)chunk_bases * 15;
     if (!getenv("RPQ_CLI_FQ_HEAD") && (uint64_t)chunk_bases * 16 > head) head = (size_t)chunk_bases * 16;
     if (win + head >= (3ull << 30)) error_exit("chunk size too large for the streaming windows (< 4 GiB of text per file and call)");
     Feed fd[2];
+    stamp("start");
     fd[0].rd.start(o.in1, head, win, 3);
     if (two) fd[1].rd.start(o.in2, head, win, 3);
     const int nf = two ? 2 : 1;
     /* the header is made from the first chunk (src/repaq.cpp:554-566): the first text holds it whole - 15 bytes of text per base of a
      * chunk (256-byte names on 20-base reads), or the whole input */
+    stamp("windows allocated, readers running");
     for (int f = 0; f < nf; f++) { fd[f].first(); fd[f].at_least((size_t)chunk_bases * 15); }
+    stamp("first windows read");
 
     char err[768];
     rpq_header h;
@@ -251,6 +260,7 @@ static int do_compress(const Opt& o) {
     rpq_ctx* ctx = NULL;
     if (rpq_create(o.device, &ctx)) error_exit("no CUDA device: repaq_b200 has no CPU fallback");
     if (rpq_set_header(ctx, &h)) error_exit(rpq_last_error(ctx));
+    stamp("header made, context created");
     rpq_ctx* check = NULL;                                 /* -v / -f: the reference's codec4check */
     for (;;) {
         /* the window after this one must be there (or the input must have ended) before this one is encoded: only then is it
@@ -287,6 +297,7 @@ static int do_compress(const Opt& o) {
             if (all) last_call = true;
             else { in.final = 0; if (rpq_encode(ctx, &in, &res)) error_exit(rpq_last_error(ctx)); }
         }
+        stamp("batch encoded");
         if (res.bytes) out.put(std::vector<char>((const char*)res.data, (const char*)res.data + res.bytes));
         if (o.verify && res.bytes) {
             /* the check of completeCheckAndOutput: decode what was just written, compare it read by read with what it was made from */
@@ -327,9 +338,12 @@ static int do_compress(const Opt& o) {
         }
     }
     out.finish();
+    stamp("output written");
+    if (!getenv("RPQ_CLI_TEARDOWN")) _exit(0);             /* everything is on disk: unpinning windows and freeing device memory one by one only costs time */
     for (int f = 0; f < nf; f++) fd[f].rd.stop();
     if (check) rpq_destroy(check);
     rpq_destroy(ctx);
+    stamp("done");
     return 0;
 }
 
@@ -340,7 +354,7 @@ static int do_compress(const Opt& o) {
  * decoded again as the first chunk of the next batch. */
 static int do_decompress(const Opt& o) {
     const bool pe = !o.out2.empty();
-    const size_t win = env_size("RPQ_CLI_RFQ_WINDOW", 64u << 20), head = env_size("RPQ_CLI_RFQ_HEAD", 64u << 20);
+    const size_t win = env_size("RPQ_CLI_RFQ_WINDOW", 16u << 20), head = env_size("RPQ_CLI_RFQ_HEAD", 32u << 20);
     StreamReader rd;
     rd.start(o.in1, head, win, 3);
     uint64_t k = 0;
@@ -418,6 +432,7 @@ static int do_decompress(const Opt& o) {
         k++; cur = nxt; text = dst; len = rest + nxt->n; eof = nxt->eof;
     }
     w1.finish(); if (pe) w2.finish();
+    if (!getenv("RPQ_CLI_TEARDOWN")) _exit(0);
     rd.stop();
     rpq_destroy(ctx[0]); rpq_destroy(ctx[1]);
     return 0;
