@@ -443,3 +443,14 @@ def test_dense_hint_follows_the_data(codec):
         parity.check_against_oracle(codec, data, k=1000)
 
 
+
+
+def test_read_longer_than_the_header_can_store(codec):
+    """the header's read length width comes from the first chunk (src/rfqcodec.cpp:48-53): a later read of more than 255 bases would be
+    written truncated (the reference writes a file it cannot decode); refused instead of losing data silently"""
+    short = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, b"ACGT" * 25, b"F" * 100) for i in range(1200))       # 120 kb: the whole first chunk
+    long_ = b"@long\n%s\n+\n%s\n" % (b"ACGT" * 150, b"F" * 600)
+    with pytest.raises(K.RepaqError) as e:
+        K.compress(short + long_, k=100, codec=codec)
+    assert "does not fit the header" in str(e.value)
+    assert len(K.compress(long_ + short, k=100, codec=codec)) > 0                                       # two-byte lengths from the start: fine

@@ -53,7 +53,10 @@ def probe(name, r1, r2=None, steps=3):
 
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4000000
-    r1, _ = fqgen.generate(n, seed=5, shape=fqgen.BGI)
-    probe("bgi_se_100bp", r1)
-    r1, _ = fqgen.generate(n, seed=1)
-    probe("nova_se_150bp", r1)
+    which = sys.argv[2] if len(sys.argv) > 2 else "both"
+    if which in ("both", "bgi"):
+        r1, _ = fqgen.generate(n, seed=5, shape=fqgen.BGI)
+        probe("bgi_se_100bp", r1)
+    if which in ("both", "nova"):
+        r1, _ = fqgen.generate(n, seed=1)
+        probe("nova_se_150bp", r1)
