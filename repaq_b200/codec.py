@@ -257,6 +257,8 @@ def compress(r1, r2=None, k=1000, interleaved=False, codec=None, device=0, lib_p
     own = codec is None
     codec = codec or Codec(device, lib_path)
     try:
+        if r2 is not None and len(r2) == 0:
+            return b""                                         # compressPE reads pairs: no R2 record, no pair, nothing written (src/repaq.cpp:640-759)
         h = make_header(r1, r2, interleaved, chunk_bases, lib_path=codec.lib_path)
         if h is None:
             return b""                                         # no record: nothing is written, not even the header

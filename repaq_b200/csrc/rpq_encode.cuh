@@ -535,10 +535,19 @@ __device__ inline void stage_positions(const EncBatchDev& b, const HeaderDev& h,
     const u32* offs = mode ? b.seqoff : b.qualoff;
     u32 a = 0, z = ck.count;            /* first read that can contain `lo`: largest rel with offs <= lo */
     while (z - a > 1) { const u32 mid = (a + z) >> 1; if (offs[ck.first + mid] <= lo) a = mid; else z = mid; }
+    /* N positions: a read of plain bases only has none (k_meta3 has looked at every character), so the window is cleared and
+     * only the other reads - a few per thousand - are staged */
+    const bool sparse = mode != 0 && b.unclean != nullptr;
+    if (sparse) {
+        const u32 n16 = (hi - lo + 15u) >> 4;
+        for (u32 k = threadIdx.x; k < n16; k += blockDim.x) reinterpret_cast<uint4*>(sm)[k] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+    }
     for (u32 rel = a + warp; rel < ck.count; rel += nwarps) {
         const u32 i = ck.first + rel;
         const u32 off = offs[i];
         if (off >= hi) break;
+        if (sparse && !b.unclean[i]) continue;
         const u32 rl = b.rlen[i];
         const u32 n = mode ? kept_bases(b, h, ck.interleaved != 0, i, rel) : rl;
         if (off + n <= lo) continue;

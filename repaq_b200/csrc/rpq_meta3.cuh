@@ -334,6 +334,7 @@ __global__ void __launch_bounds__(256) k_meta3(EncBatchDev b, HeaderDev h, u32 n
         const u32 so = s_seq[r] & 0xFFFFu;
         const bool clean = pack_read_c(words, so, rlen, rc_odd && (r & 1u), pkS + (size_t)r * cfg.pkw, (int)cfg.pkw);
         s_flag[r] = (u8)((eq0 ? 1u : 0u) | (clean ? 2u : 0u));
+        if (b.unclean) b.unclean[i] = clean ? 0 : 1;                  /* the N-position coder only stages these reads */
     }
     __syncthreads();
     if (rc_odd) {

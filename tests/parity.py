@@ -85,3 +85,27 @@ def check_decode_rle_golden(codec, name):
     if "dec1_sha256" in m:
         d1, d2 = K.decompress(rfq, pe_out=True, codec=codec)
         assert (sha(d1), sha(d2)) == (m["dec1_sha256"], m["dec2_sha256"])
+
+
+def check_n_positions_in_few_reads(codec, n_pairs=12000):
+    """ENCODE_N_POS headers (an N whose quality is not the N quality): the N-position coder only stages the reads k_meta3 saw a
+    character other than a plain base in.  Paired end (overlaps, reverse strand) and single end, N at read ends included."""
+    import random
+    from tools import fqgen
+    r1, r2 = fqgen.generate(n_pairs, seed=5, paired=True)
+    rnd = random.Random(3)
+    out = []
+    for r in (r1, r2):
+        lines = bytes(r).split(b"\n")
+        for k in range(1, len(lines) - 1, 4):
+            if rnd.random() < 0.03:
+                s = bytearray(lines[k])
+                for j in rnd.sample(range(len(s)), 3):
+                    s[j] = ord("N")
+                if rnd.random() < 0.3:
+                    s[0] = s[-1] = ord("N")
+                lines[k] = bytes(s)
+        out.append(b"\n".join(lines))
+    assert K.make_header(out[0], out[1]).flags & (1 << 9)
+    check_against_oracle(codec, out[0], out[1], k=1000)
+    check_against_oracle(codec, out[0], None, k=1000)

@@ -454,3 +454,7 @@ def test_read_longer_than_the_header_can_store(codec):
         K.compress(short + long_, k=100, codec=codec)
     assert "does not fit the header" in str(e.value)
     assert len(K.compress(long_ + short, k=100, codec=codec)) > 0                                       # two-byte lengths from the start: fine
+
+
+def test_n_positions_in_few_reads(codec):
+    parity.check_n_positions_in_few_reads(codec)

@@ -177,3 +177,7 @@ def test_library_really_ran_on_gpu(codec):
     s = codec.stats()
     assert s.launches > 0
     assert os.path.basename(_lib.LIB_PATH) == "librepaq_b200.so"
+
+
+def test_n_positions_in_few_reads(codec):
+    parity.check_n_positions_in_few_reads(codec, n_pairs=60000)
