@@ -638,7 +638,7 @@ def main():
             "k_index_lines": fq_b + 4 * 4 * n_reads,                             # text in, line index out
             "k_unit_lengths": (16 + 16 + 4 + 4) * n_reads,                       # line index in, record index + lengths out
             "k_meta3": head_b + (16 + 44) * n_reads,                             # record heads in, ReadMeta + packed read out
-            "k_streams3": qual_b + stream_b, "k_streams4": qual_b + stream_b, "k_streams5": qual_b + stream_b,   # qualities in, tokens out
+            "k_streams3": qual_b + stream_b, "k_streams4": qual_b + stream_b, "k_streams7": qual_b + stream_b,   # qualities in, tokens out
             "k_emit2": 44 * n_reads + seq_b / 4,                                 # packed reads in, 2-bit stream out
             "k_emit_names": 2 * (fq_b - 2 * bases), "k_gather": 2 * stream_b,
             "k_chunk_finish": 44 * n_reads, "k_coords": 9 * n_reads,

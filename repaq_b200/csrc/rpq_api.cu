@@ -14,7 +14,7 @@
 #include "rpq_streams2.cuh"
 #include "rpq_streams3.cuh"
 #include "rpq_streams4.cuh"
-#include "rpq_streams6.cuh"
+#include "rpq_streams7.cuh"
 #include "rpq_meta2.cuh"
 #include "rpq_meta3.cuh"
 #include "rpq_decode.cuh"
@@ -54,11 +54,11 @@ struct rpq_ctx {
     DevBuf loc, pk, pk_rc, text[2], nl[2], tile_state, counters, rlen, unit_bases, prefix, scan_tmp, ustats, chunk_first, chunks, meta, meta0, ov,
         seqoff, qualoff, n1off, n2off, soff, errbits, tmpx, tmpy, span_first[2], span_chunk[2], dir[2], slots[2], span_slot[2], span_read0[2], redo_list[2], dense_list, unclean, misc, out,
         d_in, d_desc, d_tmp[8], d_tmp2, out2, d_slabs, d_ckpt, d_dir, canon[2], nl2[2], canon_len, canon_pre;
-    int streams5 = 1;                      /* RPQ_DEBUG_STREAMS5=0: dense quality spans go to k_streams3 (A/B); =2: k_streams6 codes every quality span (test coverage) */
+    int streams5 = 1;                      /* RPQ_DEBUG_STREAMS5=0: every span k_streams4 cannot code goes to k_streams3 (A/B, at most 46 streams); =2: k_streams7 codes every quality span (test coverage) */
     bool no_streams4 = false;              /* RPQ_DEBUG_NO_STREAMS4=1: k_streams3 codes every span (test coverage, A/B) */
-    bool dense_hint = false;               /* most quality spans of the last batch were dense: the next one goes to k_streams6 directly (k_streams4 would stage
+    bool dense_hint = false;               /* most quality spans of the last batch were dense: the next one goes to k_streams7 directly (k_streams4 would stage
                                               and count every span only to hand it over) */
-    u64 stats_dense_spans = 0;             /* spans k_streams4 handed to k_streams6 */
+    u64 stats_dense_spans = 0;             /* spans k_streams4 handed to k_streams7 (dense ones and those with long runs) */
     u64 stats_redo_spans = 0;              /* spans k_streams4 handed to k_streams3 */
     u32 fmt_reads = 0;                     /* RPQ_DEBUG_FMT_READS=n: reads per formatter CTA (tuning experiments) */
     bool no_par_walk = false;              /* RPQ_DEBUG_NO_PAR_WALK=1: the chunk chain of a device-resident body is followed by one warp (A/B) */
@@ -196,6 +196,7 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     cudaFuncSetAttribute(k_streams2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_streams3, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_streams4, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_streams7, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_meta3, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_dec_format4, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
     cudaFuncSetAttribute(k_dec_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);

@@ -131,8 +131,11 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams4(EncBatchDev b, HeaderDe
     const u32 n_runs = total;
     if (s_redo || n_runs > (u32)RL_CAP) {
         if (tid == 0) {
-            if (!s_redo && mode == 0 && job.dense_list) { const u32 at = atomicAdd(job.dense_count, 1u); job.dense_list[at] = span; }   /* too many runs: k_streams5 */
-            else { const u32 at = atomicAdd(job.redo_count, 1u); job.redo_list[at] = span; }                                           /* long runs: k_streams3 */
+            const bool dense = !s_redo;                              /* too many runs for the list: the dense coder's */
+            if (mode == 0 && job.dense_list && (dense || job.list_takes_redo)) {
+                if (dense) atomicAdd(job.dense_count, 1u);
+                const u32 at = atomicAdd(job.list_count, 1u); job.dense_list[at] = span;
+            } else { const u32 at = atomicAdd(job.redo_count, 1u); job.redo_list[at] = span; }                                         /* long runs: k_streams3 */
         }
         return;
     }

@@ -109,3 +109,40 @@ def check_n_positions_in_few_reads(codec, n_pairs=12000):
     assert K.make_header(out[0], out[1]).flags & (1 << 9)
     check_against_oracle(codec, out[0], out[1], k=1000)
     check_against_oracle(codec, out[0], None, k=1000)
+
+
+def adversarial_quality_column(n_reads=16000, rl=150, seed=11, alphabet=b"F,:#5", rare=b"~!", dense=False):
+    """single-end FASTQ whose quality column - read boundaries ignored - is a sequence of runs with heavy-tailed lengths (1 .. several
+    spans of 16384 positions), so that runs cross segment (64), span (16384) and chunk boundaries in every phase, start at positions
+    0 / 1 of chunks (Q16), and hold values the header (made from the first chunk) does not list (exception records)"""
+    import numpy as np
+    rnd = np.random.RandomState(seed)
+    total = n_reads * rl
+    col = np.empty(total, dtype=np.uint8)
+    pos = 0
+    first_chunk = 1000000 // 10            # callers use k=100: the alphabet is that of the first 100 k bases
+    while pos < total:
+        kind = rnd.randint(100)
+        if dense:
+            ln = 1 if kind < 90 else int(rnd.randint(2, 70)) if kind < 99 else int(rnd.randint(70, 40000))
+        else:
+            ln = int(rnd.randint(1, 4)) if kind < 50 else int(rnd.randint(4, 200)) if kind < 95 else int(rnd.randint(200, 40000))
+        v = alphabet[rnd.randint(len(alphabet))]
+        if pos > first_chunk + 2000 and rnd.randint(400) == 0:
+            v = rare[rnd.randint(len(rare))]
+        col[pos:pos + ln] = v
+        pos += ln
+    bases = np.frombuffer(b"ACGT", dtype=np.uint8)[rnd.randint(0, 4, total)]
+    out = []
+    for i in range(n_reads):
+        out.append(b"@r%d\n" % i + bases[i * rl:(i + 1) * rl].tobytes() + b"\n+\n" + col[i * rl:(i + 1) * rl].tobytes() + b"\n")
+    return b"".join(out)
+
+
+def check_adversarial_quality_columns(codec, n_reads=16000):
+    import string
+    check_against_oracle(codec, adversarial_quality_column(n_reads), k=100)
+    check_against_oracle(codec, adversarial_quality_column(n_reads, rl=100, seed=12, alphabet=b"F"), k=100)           # a single value: no stream but exceptions
+    dense = (string.ascii_uppercase + string.digits + "#$%&").encode()
+    check_against_oracle(codec, adversarial_quality_column(n_reads, rl=100, seed=13, alphabet=dense, dense=True), k=100)
+    check_against_oracle(codec, adversarial_quality_column(n_reads, rl=37, seed=14, alphabet=dense[:12], dense=True), k=100)

@@ -191,8 +191,8 @@ def _dense_cases(cd, lib_path):
         lines[4 * rec + 3] = bytes(q)
     q = bytearray(lines[3]); q[0:2] = bytes([q[0]]) * 2; lines[3] = bytes(q)      # Q16: a run over positions 0 and 1 of the chunk
     parity.check_against_oracle(cd, b"\n".join(lines), k=100)
-    # 56 quality values: more streams than two [block][stream] tables have room for (k_streams5 then uses one for both purposes);
-    # 42: the most that two tables hold, i.e. the largest shared-memory footprint of the kernel
+    # 56 quality values (57 KB of per-stream table columns in k_streams7);
+    # 42: about what BGI-SEQ columns hold
     r1, _ = fqgen.generate(12000, seed=8, shape=fqgen.BGI)
     for nvalues in (56, 42):
         lines = bytes(r1).split(b"\n")
@@ -204,8 +204,8 @@ def _dense_cases(cd, lib_path):
 
 
 def test_dense_quality_spans(monkeypatch):
-    """k_streams5 takes the spans with more runs than k_streams4 lists (the default), RPQ_DEBUG_STREAMS5=0 leaves them to k_streams3,
-    =2 lets k_streams5 code every quality span of ordinary inputs too: all three must give the reference's bytes"""
+    """k_streams7 takes the spans with more runs than k_streams4 lists (the default), RPQ_DEBUG_STREAMS5=0 leaves them to k_streams3,
+    =2 lets k_streams7 code every quality span of ordinary inputs too: all three must give the reference's bytes"""
     for knob, names in (("1", ("bgi_se_k100", "bgi_se_varlen_k100")), ("0", ("bgi_se_k100",)),
                         ("2", ("nova_pe_k1000", "nova_pe_k100_npos", "bgi_se_varlen_k100", "nova_se_late_quality", "kat_pe", "one_read", "nova_pe_300bp_varlen_k100"))):
         monkeypatch.setenv("RPQ_DEBUG_STREAMS5", knob)
@@ -434,7 +434,7 @@ def test_crlf_on_reader_buffer_edges(codec):
 
 
 def test_dense_hint_follows_the_data(codec):
-    """after a batch whose quality spans were mostly dense the next batch goes to k_streams5 directly, and back to k_streams4 after a
+    """after a batch whose quality spans were mostly dense the next batch goes to k_streams7 directly, and back to k_streams4 after a
     sparse one: the bytes are the reference's whichever coder takes the spans"""
     from tools import fqgen
     dense, _ = fqgen.generate(24000, seed=5, shape=fqgen.BGI)
@@ -458,3 +458,7 @@ def test_read_longer_than_the_header_can_store(codec):
 
 def test_n_positions_in_few_reads(codec):
     parity.check_n_positions_in_few_reads(codec)
+
+
+def test_adversarial_quality_columns(codec):
+    parity.check_adversarial_quality_columns(codec)

@@ -148,7 +148,7 @@ def test_parallel_chunk_walk(monkeypatch):
 
 
 def test_dense_quality_spans(monkeypatch):
-    """k_streams5 on the GPU: dense inputs against the oracle (default hand-over from k_streams4) and every quality span of ordinary
+    """k_streams7 on the GPU: dense inputs against the oracle (default hand-over from k_streams4) and every quality span of ordinary
     golden inputs (RPQ_DEBUG_STREAMS5=2)"""
     from tests import test_emu_parity as E
     for knob in ("1", "2"):
@@ -181,3 +181,7 @@ def test_library_really_ran_on_gpu(codec):
 
 def test_n_positions_in_few_reads(codec):
     parity.check_n_positions_in_few_reads(codec, n_pairs=60000)
+
+
+def test_adversarial_quality_columns(codec):
+    parity.check_adversarial_quality_columns(codec, n_reads=60000)

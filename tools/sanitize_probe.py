@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A small pass through every kernel family for compute-sanitizer (memcheck / racecheck / initcheck):
 paired-end NovaSeq-shape encode, decode from host and from device memory (parallel chunk walk forced), compare, and a BGI-shape
-encode (dense spans: k_streams5).  usage: compute-sanitizer --tool memcheck python tools/sanitize_probe.py"""
+encode (dense spans: k_streams7).  usage: compute-sanitizer --tool memcheck python tools/sanitize_probe.py"""
 import os
 import sys
 
@@ -32,7 +32,7 @@ assert e.bytes == len(rfq) - used
 b1, _ = fqgen.generate(20000, seed=5, shape=fqgen.BGI)
 rb = K.compress(b1, k=100, codec=cd)
 assert K.decompress(rb, codec=cd) == bytes(b1)
-rb2 = K.compress(b1, k=100, codec=cd)                  # second batch: the dense hint sends every span to k_streams5
+rb2 = K.compress(b1, k=100, codec=cd)                  # second batch: the dense hint sends every span to k_streams7
 assert rb2 == rb
 cd.close()
 print("sanitize probe ok")
