@@ -51,10 +51,11 @@ struct rpq_ctx {
     bool have_hdr = false;
     HeaderDev hd;
     /* grow-only device buffers */
-    DevBuf loc, pk, pk_rc, text[2], nl[2], tile_state, counters, rlen, unit_bases, prefix, scan_tmp, ustats, chunk_first, chunks, meta, meta0, ov,
+    DevBuf loc, pk, pk_rc, text[2], nl[2], nl_local, tile_state, counters, rlen, unit_bases, prefix, scan_tmp, ustats, chunk_first, chunks, meta, meta0, ov,
         seqoff, qualoff, n1off, n2off, soff, errbits, tmpx, tmpy, span_first[2], span_chunk[2], dir[2], slots[2], span_slot[2], span_read0[2], redo_list[2], dense_list, unclean, misc, out,
         d_in, d_desc, d_tmp[8], d_tmp2, out2, d_slabs, d_ckpt, d_dir, canon[2], nl2[2], canon_len, canon_pre;
     int streams5 = 1;                      /* RPQ_DEBUG_STREAMS5=0: every span k_streams4 cannot code goes to k_streams3 (A/B, at most 46 streams); =2: k_streams7 codes every quality span (test coverage) */
+    u32 meta_units = 0;                    /* RPQ_DEBUG_META_UNITS: units per CTA of k_meta3 (A/B) */
     bool no_streams4 = false;              /* RPQ_DEBUG_NO_STREAMS4=1: k_streams3 codes every span (test coverage, A/B) */
     bool dense_hint = false;               /* most quality spans of the last batch were dense: the next one goes to k_streams7 directly (k_streams4 would stage
                                               and count every span only to hand it over) */
@@ -187,6 +188,7 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     { const char* e = getenv("RPQ_DEBUG_PAR_WALK_MIN"); c->par_walk_min = e ? strtoull(e, nullptr, 10) : (32ull << 20); }
     { const char* e = getenv("RPQ_DEBUG_STREAMS5"); if (e) c->streams5 = atoi(e); }
     { const char* e = getenv("RPQ_DEBUG_NO_STREAMS4"); c->no_streams4 = e && e[0] == '1'; }
+    { const char* e = getenv("RPQ_DEBUG_META_UNITS"); c->meta_units = e ? (u32)atoi(e) : 0u; }
     { const char* e = getenv("RPQ_DEBUG_FMT_READS"); c->fmt_reads = e ? (u32)atoi(e) : 0u; }
     { const char* e = getenv("RPQ_NO_PIPELINE"); c->no_pipeline = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_D2H_DEPTH"); if (e) c->d2h_depth = (u32)atoi(e) > 8u ? 8u : (u32)atoi(e); }
@@ -213,7 +215,7 @@ extern "C" void rpq_destroy(rpq_ctx* c) {
     c->lanes.clear();
     if (c->copy_stream_ok) { rt_stream_sync(c->copy_stream); rt_stream_destroy(c->copy_stream); for (auto& e : c->win_ev) rt_event_destroy(&e); for (auto& e : c->cp_ev) rt_event_destroy(&e); }
     if (c->side_stream_ok) { rt_stream_sync(c->side_stream); rt_stream_destroy(c->side_stream); rt_event_destroy(&c->side_ev); rt_event_destroy(&c->fork_ev); }
-    DevBuf* all[] = {&c->loc, &c->pk, &c->pk_rc, &c->text[0], &c->text[1], &c->nl[0], &c->nl[1], &c->tile_state, &c->counters, &c->rlen, &c->unit_bases, &c->prefix, &c->scan_tmp,
+    DevBuf* all[] = {&c->loc, &c->pk, &c->pk_rc, &c->text[0], &c->text[1], &c->nl[0], &c->nl[1], &c->nl_local, &c->tile_state, &c->counters, &c->rlen, &c->unit_bases, &c->prefix, &c->scan_tmp,
                      &c->ustats, &c->chunk_first, &c->chunks, &c->meta, &c->meta0, &c->ov, &c->seqoff, &c->qualoff, &c->n1off, &c->n2off, &c->soff,
                      &c->errbits, &c->tmpx, &c->tmpy, &c->span_first[0], &c->span_first[1], &c->span_chunk[0], &c->span_chunk[1], &c->dir[0], &c->dir[1],
                      &c->slots[0], &c->slots[1], &c->span_slot[0], &c->span_slot[1], &c->span_read0[0], &c->span_read0[1], &c->redo_list[0], &c->redo_list[1], &c->dense_list, &c->unclean, &c->misc, &c->out, &c->d_in, &c->d_desc, &c->out2, &c->d_slabs, &c->d_ckpt, &c->d_dir, &c->canon[0], &c->canon[1], &c->nl2[0], &c->nl2[1], &c->canon_len, &c->canon_pre,
@@ -297,19 +299,28 @@ int fetch_table(rpq_ctx* c, const void* dev, size_t bytes) {
 
 int index_text(rpq_ctx* c, int f, const u8* d_text, u64 len, u64 file_off, IndexCounters* hc, bool eof) {
     const u32 tiles = (u32)((len + IDX_TILE - 1) / IDX_TILE);
-    if (!ensure(c, c->tile_state, sizeof(u64) * (tiles + 1)) || !ensure(c, c->counters, sizeof(IndexCounters) * 2)) return RPQ_ERR_NOMEM;
+    if (!ensure(c, c->tile_state, sizeof(u32) * 2 * ((size_t)tiles + 1)) || !ensure(c, c->counters, sizeof(IndexCounters) * 2)) return RPQ_ERR_NOMEM;
+    u32* tile_count = c->tile_state.as<u32>();
+    u32* tile_first = tile_count + tiles + 1;
+    /* a tile's region of the tile-local index: lines of 16 bytes and more fit (IDX_TILE / 16 entries); a text with shorter lines
+     * is indexed again with room for a line end at every byte */
     size_t cap = (size_t)(len / 16) + 4096;
+    u32 lcap = IDX_TILE / 16;
     for (int attempt = 0; attempt < 2; attempt++) {
-        if (!ensure(c, c->nl[f], sizeof(u32) * cap)) return RPQ_ERR_NOMEM;
+        if (!ensure(c, c->nl[f], sizeof(u32) * cap) || !ensure(c, c->nl_local, sizeof(u32) * (size_t)lcap * tiles + 64)) return RPQ_ERR_NOMEM;
         cap = c->nl[f].cap / sizeof(u32);
         IndexCounters* dc = c->counters.as<IndexCounters>() + f;
-        rt_memset(c->tile_state.p, 0, sizeof(u64) * (tiles + 1), c->stream);
         rt_memset(dc, 0, sizeof(IndexCounters), c->stream);
-        LAUNCH(c, k_index_lines, tiles, IDX_THREADS, IDX_SMEM, d_text, len, file_off, c->nl[f].as<u32>(), (u32)cap, c->tile_state.as<u64>(), dc);
+        if (tiles) {
+            LAUNCH(c, k_index_lines, tiles, IDX_THREADS, IDX_SMEM, d_text, len, file_off, c->nl_local.as<u32>(), lcap, tile_count, dc);
+            LAUNCH(c, k_index_scan, 1, IDX_SCAN_THREADS, 0, (const u32*)tile_count, tiles, tile_first, dc);
+            LAUNCH(c, k_index_compact, tiles, 256, 0, (const u32*)c->nl_local.as<u32>(), lcap, (const u32*)tile_count, (const u32*)tile_first, c->nl[f].as<u32>(), (u32)cap);
+        }
         LAUNCH(c, k_index_finish, 1, 32, 0, d_text, len, c->nl[f].as<u32>(), (u32)cap, dc, eof ? 1 : 0);
         if (int rc = read_back(c, dc, hc)) return rc;
-        if ((size_t)hc->n_nl + 2 <= cap) return RPQ_OK;
+        if ((size_t)hc->n_nl + 2 <= cap && !hc->overflow) return RPQ_OK;
         cap = (size_t)hc->n_nl + 16;           /* pathological line density: index again with room for every line */
+        lcap = IDX_TILE;
     }
     return RPQ_OK;
 }

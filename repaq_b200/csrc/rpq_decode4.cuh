@@ -205,6 +205,7 @@ struct Fmt4Cfg {
     u32 out_cap;           /* shared bytes per output stream staging (incl. 16 bytes of alignment slack) */
     u32 nbits_words;       /* shared words of the N bitmap (0 unless the header has ENCODE_N_POS) */
     u32 n_streams;         /* checkpoint layout: streams per chunk (quality streams + exceptions + N positions) */
+    u32 seq_cap;           /* k_dec_format4: shared bytes of the tile's piece of the 2-bit column (incl. alignment slack) */
 };
 
 /*
@@ -278,7 +279,11 @@ __device__ __forceinline__ void qx_decode_step(const DecBatchDev& b, const u8* s
     qx_step(S, base, cura, nexta, skip, next, lane, [&](u32 first, u32 end1) {
         const u32 x = first > lo ? first : lo, y = end1 < hi ? end1 : hi;
         if (BITS) { for (u32 p = x; p < y; p++) atomicOr(&bits[(p - org) >> 5], 1u << ((p - org) & 31u)); }
-        else { for (u32 p = x; p < y; p++) tile[p - org] = q; }
+        else if (x < y) {                                              /* mostly one position (a distance token) */
+            u8* o = tile + (x - org);
+            o[0] = q;
+            for (u32 k = 1; k < y - x; k++) o[k] = q;
+        }
     });
 }
 
@@ -346,13 +351,13 @@ __global__ void __launch_bounds__(PL_THREADS) k_dec_planes(DecBatchDev b, Header
         const u32 total = s_pre[n_tasks];
         const u8* cbase = b.body + ck.in_off;
         const uint2* cck = ckpt + qx_chunk_base(ck, c, cfg.n_streams);
+        u32 t = 0;                                                     /* the stream of task k: the last one with s_pre[t] <= k; tasks come in increasing order */
         for (;;) {
             u32 k = 0;
             if (lane == 0) k = atomicAdd(&s_task, 1u);
             k = __shfl_sync(0xffffffffu, k, 0);
             if (k >= total) break;
-            u32 t = 0;                                                 /* the stream of task k: the last one with s_pre[t] <= k */
-            { u32 a = 0, z = n_tasks; while (z - a > 1u) { const u32 m = (a + z) >> 1; if (s_pre[m] <= k) a = m; else z = m; } t = a; }
+            while (t + 1u < n_tasks && s_pre[t + 1u] <= k) t++;
             const TileDir& d = s_dir[t];
             const u32 j = k - s_pre[t];
             const u32 st = t < n_q ? t : (u32)h.nb + 1u;
@@ -397,6 +402,7 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
     u32* s_nbits = reinterpret_cast<u32*>(dyn + cfg.plane_cap);
     u8* s_out[2] = {dyn + cfg.plane_cap + 4u * cfg.nbits_words, dyn + cfg.plane_cap + 4u * cfg.nbits_words + cfg.out_cap};
     const u32 nstreams = b.split_pairs ? 2u : 1u;
+    u8* s_seq = dyn + cfg.plane_cap + 4u * cfg.nbits_words + nstreams * cfg.out_cap;
     const u8* in = b.body + ck.in_off;
     const u32 fl = ck.flags;
     const bool raw_qual = (h.flags & RPQ_DONT_ENCODE_QUAL) != 0;
@@ -428,11 +434,28 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
     u32 r = 0, rl = 0, stream = 0, olen = 0;
     u64 oabs = 0;
     u32 qrel = 0;
+    /* everything the thread will need from the per-read tables and the chunk's columns is requested here, in one go: the loads are
+     * independent, their latencies overlap each other and the two barriers that follow */
+    u32 pre_so = 0, pre_x = 0, pre_y = 0, pre_prev_rl = 0, pre_ls = 0, pre_l1 = 0, pre_lane = 0, pre_tile = 0;
+    int pre_ov = 0;
     if (active) {
         r = r0 + rt; rl = b.rlen[i]; olen = b.olen[i];
         stream = b.split_pairs ? (r & 1u) : 0u;
         oabs = ck.out_off[stream] + b.outoff[i];
         qrel = b.qualoff[i];
+        const bool il = (fl & RPQ_PE_INTERLEAVED) != 0;
+        const u32 xy = il ? r >> 1 : r;
+        pre_ls = (fl & (RPQ_STRAND_SAME | RPQ_STRAND_LEN_SAME)) ? in[ck.off_slen] : in[ck.off_slen + r];
+        if (half == 1) {
+            pre_l1 = (fl & (RPQ_NAME1_SAME | RPQ_NAME1_LEN_SAME)) ? in[ck.off_n1len] : in[ck.off_n1len + r];
+            if (h.flags & RPQ_HAS_LANE) pre_lane = (fl & RPQ_LANE_SAME) ? in[ck.off_lane] : in[ck.off_lane + xy];
+            if (h.flags & RPQ_HAS_TILE) { const u32 k = (fl & RPQ_TILE_SAME) ? 0u : xy; pre_tile = (u32)in[ck.off_tile + 2 * k] | ((u32)in[ck.off_tile + 2 * k + 1] << 8); }
+            if (h.flags & RPQ_HAS_X) pre_x = b.xs[ck.read_base + xy];
+            if (h.flags & RPQ_HAS_Y) pre_y = b.ys[ck.read_base + xy];
+        } else {
+            pre_so = b.seqoff[i];
+            if (il && (h.flags & RPQ_ENCODE_PE_BY_OVERLAP) && (r & 1u)) { pre_ov = (int)(signed char)in[ck.off_ov + (r >> 1)] - (int)h.overlap_shift; pre_prev_rl = b.rlen[i - 1]; }
+        }
         if (half == 0) {
             if ((u32)rt < nstreams) s_start[stream] = oabs;
             if ((u32)rt + nstreams >= n_here) s_end[stream] = oabs + olen;
@@ -440,15 +463,30 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
     }
     __syncthreads();
 
-    /* ---- the tile's slot: one TMA bulk copy */
+    /* ---- the tile's slot and its piece of the 2-bit column: two TMA bulk copies counted on one mbarrier.  The piece: the bytes
+     * that hold the compact bases [C0, C1) of the tile's reads (an overlapped mate reads its partner's bases: pairs never straddle
+     * tiles) plus the 8 bytes a 16-base load may reach past them, from a 16-byte aligned address, never past the end of the body;
+     * whatever a (damaged) chunk makes a read look for outside the piece comes from the body itself. */
     const u32 slot_n = slot_bytes(cfg);
     const u8* slot = planes + (size_t)(tile_index(ck, c, G) + blockIdx.x) * slot_n;
+    const u8* seqcol = in + ck.off_seq;
+    const u8* sq_src; u32 sq_n = 0;
+    {
+        const uintptr_t want0 = reinterpret_cast<uintptr_t>(seqcol + (C0 >> 2)), want1 = reinterpret_cast<uintptr_t>(seqcol + ((C1 + 3u) >> 2)) + 8u;
+        const uintptr_t end_body = reinterpret_cast<uintptr_t>(b.body + b.body_len) & ~(uintptr_t)15;
+        const uintptr_t a0 = want0 & ~(uintptr_t)15;
+        uintptr_t a1 = (want1 + 15u) & ~(uintptr_t)15;
+        if (a1 > end_body) a1 = end_body;
+        sq_src = reinterpret_cast<const u8*>(a0);
+        if (a1 > a0 && C1 > C0) { sq_n = (u32)(a1 - a0); if (sq_n > cfg.seq_cap) sq_n = cfg.seq_cap & ~15u; }
+    }
 #ifdef RPQ_EMU
     {
         const uint4* src = reinterpret_cast<const uint4*>(slot);
         uint4* dst = reinterpret_cast<uint4*>(s_plane);
         for (u32 k = tid; k < plane_bytes / 16u; k += blockDim.x) dst[k] = src[k];
         for (u32 k = tid; k < cfg.nbits_words / 4u; k += blockDim.x) dst[cfg.plane_cap / 16u + k] = src[cfg.plane_cap / 16u + k];
+        for (u32 k = tid; k < sq_n; k += blockDim.x) s_seq[k] = sq_src[k];
     }
     __syncthreads();
     auto plane_ready = [&]() {};
@@ -459,9 +497,12 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
         const u32 nbytes = cfg.nbits_words ? slot_n : plane_bytes;
         asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(mbar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(mbar), "r"(nbytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(mbar), "r"(nbytes + sq_n) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"((u32)__cvta_generic_to_shared(s_plane)), "l"(slot), "r"(nbytes), "r"(mbar) : "memory");
+        if (sq_n)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((u32)__cvta_generic_to_shared(s_seq)), "l"(sq_src), "r"(sq_n), "r"(mbar) : "memory");
     }
     __syncthreads();                                           /* the barrier object is initialised for everybody */
     auto plane_ready = [&]() {
@@ -478,19 +519,19 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
         const u32 xy = il ? r >> 1 : r;
         o = s_out[stream] + (u32)(oabs - (s_start[stream] & ~15ull));
         /* ---- strand length first: it fixes where every part of the record lies */
-        ls = (fl & (RPQ_STRAND_SAME | RPQ_STRAND_LEN_SAME)) ? in[ck.off_slen] : in[ck.off_slen + r];
+        ls = pre_ls;
         name_end = olen - (2u * rl + ls + 3u);          /* bytes of the name line including its line break */
         if (half == 1) {
             u32 w_at = 0;
             /* ---- name (reference src/rfqcodec.cpp:1157-1231) */
-            const u32 l1 = (fl & (RPQ_NAME1_SAME | RPQ_NAME1_LEN_SAME)) ? in[ck.off_n1len] : in[ck.off_n1len + r];
+            const u32 l1 = pre_l1;
             const u8* n1 = in + ck.off_n1 + ((fl & RPQ_NAME1_SAME) ? 0u : b.n1off[i]);
             for (u32 k = 0; k < l1; k++) o[w_at + k] = n1[k];
             w_at += l1;
-            if (h.flags & RPQ_HAS_LANE) { o[w_at++] = ':'; w_at += put_dec(o + w_at, (fl & RPQ_LANE_SAME) ? in[ck.off_lane] : in[ck.off_lane + xy]); }
-            if (h.flags & RPQ_HAS_TILE) { const u32 k = (fl & RPQ_TILE_SAME) ? 0u : xy; o[w_at++] = ':'; w_at += put_dec(o + w_at, (u32)in[ck.off_tile + 2 * k] | ((u32)in[ck.off_tile + 2 * k + 1] << 8)); }
-            if (h.flags & RPQ_HAS_X) { o[w_at++] = ':'; w_at += put_dec(o + w_at, b.xs[ck.read_base + xy]); }
-            if (h.flags & RPQ_HAS_Y) { o[w_at++] = ':'; w_at += put_dec(o + w_at, b.ys[ck.read_base + xy]); }
+            if (h.flags & RPQ_HAS_LANE) { o[w_at++] = ':'; w_at += put_dec(o + w_at, pre_lane); }
+            if (h.flags & RPQ_HAS_TILE) { o[w_at++] = ':'; w_at += put_dec(o + w_at, pre_tile); }
+            if (h.flags & RPQ_HAS_X) { o[w_at++] = ':'; w_at += put_dec(o + w_at, pre_x); }
+            if (h.flags & RPQ_HAS_Y) { o[w_at++] = ':'; w_at += put_dec(o + w_at, pre_y); }
             if (h.flags & RPQ_HAS_NAME2) {
                 const u32 l2 = (fl & (RPQ_NAME2_SAME | RPQ_NAME2_LEN_SAME)) ? in[ck.off_n2len] : in[ck.off_n2len + r];
                 const u8* n2 = in + ck.off_n2 + ((fl & RPQ_NAME2_SAME) ? 0u : b.n2off[i]);
@@ -516,10 +557,12 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
         u8* o_seq = o + name_end;
         u8* o_qual = o_seq + rl + 1 + ls + 1;
         /* ---- sequence + quality, four positions per step */
-        const u8* seqb = in + ck.off_seq;
-        const long long so = b.seqoff[i];
+        const u8* seqb = seqcol;
+        const long long sq_off = sq_src - seqb;                        /* column byte the staged piece starts at */
+        auto code_byte = [&](long long bi) -> u32 { const long long d = bi - sq_off; return (d >= 0 && d < (long long)sq_n) ? s_seq[d] : seqb[bi]; };
+        const long long so = half == 0 ? pre_so : 0;
         int ov = 0; u32 prev_rl = 0;
-        if (ov_on && odd) { ov = (int)(signed char)in[ck.off_ov + (r >> 1)] - (int)h.overlap_shift; prev_rl = b.rlen[i - 1]; }
+        if (ov_on && odd) { ov = pre_ov; prev_rl = pre_prev_rl; }
         const bool rc = il && odd;
         const u8 nq = (u8)h.n_base_qual;
         const u32 nq4 = 0x01010101u * nq;
@@ -535,7 +578,7 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
         auto slow_base = [&](u32 jo) -> u8 {
             const long long ci = (jo < bnd ? cA : cB) + (long long)sgn * jo;
             u8 base = 'N';
-            if (ci >= 0 && ci < unpacked) { const u32 code = (seqb[ci >> 2] >> (2 * (ci & 3))) & 3u; base = code == 0 ? 'G' : code == 1 ? 'A' : code == 2 ? 'T' : 'C'; }
+            if (ci >= 0 && ci < unpacked) { const u32 code = (code_byte(ci >> 2) >> (2 * (ci & 3))) & 3u; base = code == 0 ? 'G' : code == 1 ? 'A' : code == 2 ? 'T' : 'C'; }
             if (npos_mode) { if (nbit(ci)) base = 'N'; }
             else if (q[rc ? rl - 1 - jo : jo] == nq) base = 'N';
             return rc ? complement_base(base) : base;
@@ -570,9 +613,13 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
                 if (lim > safe) lim = safe;
             }
             /* words [m0, m1) of the piece jo in [jlo, jhi) with compact base cb whose four positions can take the fast path */
+            /* ... and inside the staged piece of the column, whose loads of 8 bytes must stay inside it too */
+            long long lim_lo = 4 * sq_off;
+            if (lim_lo < 0) lim_lo = 0;
+            { const long long st_hi = 4 * (sq_off + (long long)sq_n) - 32; if (lim > st_hi) lim = st_hi; }
             auto range = [&](long long cb, long long jlo, long long jhi, u32& m0, u32& m1) {
                 long long a, z;                                    /* allowed first positions jo of a word: a <= jo <= z */
-                if (!rc) { a = -cb; z = lim - cb - 4; } else { a = cb - lim + 1; z = cb - 3; }
+                if (!rc) { a = lim_lo - cb; z = lim - cb - 4; } else { a = cb - lim + 1; z = cb - 3 - lim_lo; }
                 if (npos_mode) {                                   /* and inside the N bitmap */
                     if (!rc) { if (a < (long long)corg - cb) a = (long long)corg - cb; if (z > cend - cb - 4) z = cend - cb - 4; }
                     else { if (a < cb - cend + 1) a = cb - cend + 1; if (z > cb - 3 - (long long)corg) z = cb - 3 - (long long)corg; }
@@ -601,7 +648,7 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
                 const u32* qw = reinterpret_cast<const u32*>(p0 & ~(uintptr_t)3);
                 const u32 qsel = (rc ? 0x0123u : 0x3210u) + 0x1111u * (u32)(p0 & 3u);
                 const long long ci0 = rc ? cb - (long long)jo0 - 15 : cb + (long long)jo0;     /* lowest compact index of the first 16 */
-                const uintptr_t ca = reinterpret_cast<uintptr_t>(seqb) + (uintptr_t)(ci0 >> 2);
+                const uintptr_t ca = reinterpret_cast<uintptr_t>(s_seq + ((ci0 >> 2) - sq_off));     /* shared memory; same 16-byte phase as the body */
                 const u32* cw = reinterpret_cast<const u32*>(ca & ~(uintptr_t)3);
                 const u32 sh = 8u * (u32)(ca & 3u) + 2u * (u32)(ci0 & 3);
                 for (u32 m = m0; m < m1; m += 4) {

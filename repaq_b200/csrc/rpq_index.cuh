@@ -21,7 +21,7 @@ constexpr int IDX_TILE = IDX_THREADS * IDX_ROW;              /* 64 KiB per CTA *
 constexpr int IDX_SMEM = IDX_TILE;                            /* the tile */
 
 struct IndexCounters {
-    u32 ticket;     /* dynamic tile id */
+    u32 overflow;   /* a tile holds more line breaks than its region of the tile-local index: the host indexes again with full regions */
     u32 n_nl;       /* line breaks */
     u32 n_w2;       /* line breaks of two bytes (the second one a swallowed '\n') */
     u32 pad0;
@@ -32,7 +32,6 @@ struct IndexCounters {
     u32 pad;
 };
 
-constexpr u64 TS_AGG = 1ull << 62, TS_PREFIX = 2ull << 62, TS_MASK = 3ull << 62;
 constexpr u64 RD_BUF = 1ull << 20;                           /* FQ_BUF_SIZE of the reference's reader (src/fastqreader.cpp:5) */
 
 /* exact per-byte equality, SIMD in a register: bit 7 of every byte of the result is set iff that byte of v equals c.
@@ -69,22 +68,27 @@ __device__ __forceinline__ bool rd_may_swallow(u64 q) { const u64 r = q & (RD_BU
  * byte of its break, so that the next line starts one byte later.
  * A CTA per 64 KiB tile, brought into shared memory by one TMA bulk copy per warp (4 KiB); a thread owns 128 contiguous bytes
  * (its pieces read in a lane-rotated order, so that the 128-bit shared loads of a quarter warp fall into eight different bank
- * groups), turns them into exact 128-bit masks with SIMD-in-register compares, and counts.  The rank base of a tile is the
- * chained scan over tiles with a decoupled look-back (warp 0).  Rows without '\r' and without two break characters in a row
- * (every row of a plain file) never leave the '\n' mask.
+ * groups), turns them into exact 128-bit masks with SIMD-in-register compares, and counts.  Rows without '\r' and without two
+ * break characters in a row (every row of a plain file) never leave the '\n' mask.
+ *
+ * No CTA waits for another one.  The rank of a line among all lines of the text needs the counts of all earlier tiles; the
+ * single-pass version got them from a chained scan with decoupled look-back and spent half of every CTA's life there: with ~450
+ * tiles in flight and 1.5 us of work per tile a tile always finds its predecessors still looking back themselves, and sums
+ * hundreds of aggregates in dependent rounds (r02: 46 % of the stall samples at the barrier behind the look-back, 2.8 TB/s).  Here a
+ * tile writes its line ends into its own region of a tile-local index (lcap entries per tile) and its count into a table;
+ * k_index_scan turns the counts into ranks (one CTA, 52 K tiles of a 3.4 GB text) and k_index_compact moves the entries to their
+ * ranks (4 bytes per line in and out: 3 % of the text's bytes).
  */
-__global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines(const u8* __restrict__ text, u64 len, u64 file_off, u32* __restrict__ nl, u32 nl_cap,
-                                                               u64* tile_state, IndexCounters* ctr) {
+__global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines(const u8* __restrict__ text, u64 len, u64 file_off, u32* __restrict__ nl_local, u32 lcap,
+                                                               u32* __restrict__ tile_count, IndexCounters* ctr) {
     RPQ_DYN_SMEM(dyn);
-    __shared__ u32 s_tile;
     __shared__ u32 s_wtot[IDX_THREADS / 32];
-    __shared__ u32 s_prefix;
     __shared__ u32 s_w2;
 #ifndef RPQ_EMU
     __shared__ __align__(8) unsigned long long s_mbar[IDX_THREADS / 32];
 #endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_tile = atomicAdd(&ctr->ticket, 1u); s_w2 = 0; }
+    if (tid == 0) s_w2 = 0;
 #ifndef RPQ_EMU
     if (tid < IDX_THREADS / 32) {
         asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"((u32)__cvta_generic_to_shared(&s_mbar[tid])) : "memory");
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines(const u8* __rest
     }
 #endif
     __syncthreads();
-    const u32 tile = s_tile;
+    const u32 tile = blockIdx.x;
     const u64 tbase = (u64)tile * IDX_TILE;
     u8* row = dyn + (size_t)tid * IDX_ROW;
 
@@ -177,52 +181,58 @@ __global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines(const u8* __rest
     const u32 w2w = warp_sum(w2);
     if (lane == 0) { s_wtot[warp] = wtot; if (w2w) atomicAdd(&s_w2, w2w); }
     __syncthreads();
-    u32 btot = 0, wpre = 0;
-#pragma unroll
-    for (int w = 0; w < IDX_THREADS / 32; w++) { const u32 t = s_wtot[w]; btot += t; if (w < warp) wpre += t; }
+    /* line ends in the warps before this one, and in the tile: every warp scans the 16 warp totals in its lanes */
+    u32 btot;
+    const u32 wscan = warp_excl_scan(lane < IDX_THREADS / 32 ? s_wtot[lane] : 0u, lane, btot);
+    const u32 wpre = __shfl_sync(0xffffffffu, wscan, warp);
 
-    if (warp == 0) {
-        volatile u64* st = tile_state;
-        u32 prefix = 0;
-        if (tile > 0) {
-            if (lane == 0) { st[tile] = TS_AGG | btot; __threadfence(); }
-            int j = (int)tile - 1;                       /* newest predecessor not yet accounted for */
-            for (;;) {
-                const int idx = j - lane;
-                u64 s = 2ull << 62;                       /* before tile 0: an empty prefix (TS_PREFIX | 0) */
-                if (idx >= 0) s = st[idx];
-                const u32 unset = __ballot_sync(0xffffffffu, (s & TS_MASK) == 0);
-                const u32 pre = __ballot_sync(0xffffffffu, (s & TS_MASK) == TS_PREFIX);
-                /* usable lanes: those before the first unset one, up to and including the first prefix */
-                const int first_unset = unset ? __ffs((int)unset) - 1 : 32;
-                const int first_pre = pre ? __ffs((int)pre) - 1 : 32;
-                const int upto = first_pre < first_unset ? first_pre + 1 : first_unset;   /* lanes [0, upto) are summed */
-                u32 v = lane < upto ? (u32)s : 0u;
-                prefix += warp_sum(v);
-                if (first_pre < first_unset) break;
-                j -= upto;
-                if (upto == 0) RPQ_SPIN_HINT();
-            }
-        }
-        if (lane == 0) {
-            __threadfence();
-            st[tile] = TS_PREFIX | (u64)(prefix + btot);
-            s_prefix = prefix;
-            if (s_w2) atomicAdd(&ctr->n_w2, s_w2);
-            if ((u64)(tile + 1) * IDX_TILE >= len) ctr->n_nl = prefix + btot;     /* the last tile knows the total */
-        }
+    if (tid == 0) {
+        tile_count[tile] = btot;
+        if (btot > lcap) atomicOr(&ctr->overflow, 1u);
+        if (s_w2) atomicAdd(&ctr->n_w2, s_w2);
     }
-    __syncthreads();
 
-    /* ---- positions, in text order: the last byte of every break */
+    /* ---- positions, in text order: the last byte of every break, into the tile's region */
     if (cnt) {
-        u32 o = s_prefix + wpre + ex_in_warp;
+        u32 o = wpre + ex_in_warp;
+        u32* out = nl_local + (size_t)tile * lcap;
         const u32 base = (u32)p0;
-        u64 m = elo;
-        while (m) { const int bb = __ffsll((long long)m) - 1; m &= m - 1; if (o < nl_cap) nl[o] = base + (u32)bb + (u32)((swn_lo >> bb) & 1ull); o++; }
-        m = ehi;
-        while (m) { const int bb = __ffsll((long long)m) - 1; m &= m - 1; if (o < nl_cap) nl[o] = base + 64u + (u32)bb + (u32)((swn_hi >> bb) & 1ull); o++; }
+        /* 32 positions at a time: a line end every ~90 bytes, one to three per row */
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            u32 m = q == 0 ? (u32)elo : q == 1 ? (u32)(elo >> 32) : q == 2 ? (u32)ehi : (u32)(ehi >> 32);
+            const u32 sw = q == 0 ? (u32)swn_lo : q == 1 ? (u32)(swn_lo >> 32) : q == 2 ? (u32)swn_hi : (u32)(swn_hi >> 32);
+            while (m) { const int bb = __ffs((int)m) - 1; m &= m - 1u; if (o < lcap) out[o] = base + 32u * (u32)q + (u32)bb + ((sw >> bb) & 1u); o++; }
+        }
     }
+}
+
+/* ranks of the tiles' first lines: exclusive scan of the tile counts, one CTA (a thread takes a contiguous piece) */
+constexpr int IDX_SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(IDX_SCAN_THREADS) k_index_scan(const u32* __restrict__ tile_count, u32 tiles, u32* __restrict__ tile_first, IndexCounters* ctr) {
+    __shared__ u32 s_w[IDX_SCAN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 per = (tiles + IDX_SCAN_THREADS - 1) / IDX_SCAN_THREADS;
+    const u32 a = (u32)tid * per, z = a + per < tiles ? a + per : tiles;
+    u32 sum = 0;
+    for (u32 k = a; k < z; k++) sum += tile_count[k];
+    u32 wtot; const u32 ex = warp_excl_scan(sum, lane, wtot);
+    if (lane == 0) s_w[warp] = wtot;
+    __syncthreads();
+    u32 run = ex, total = 0;
+#pragma unroll
+    for (int w = 0; w < IDX_SCAN_THREADS / 32; w++) { const u32 t = s_w[w]; if (w < warp) run += t; total += t; }
+    for (u32 k = a; k < z; k++) { tile_first[k] = run; run += tile_count[k]; }
+    if (tid == 0) { tile_first[tiles] = total; ctr->n_nl = total; }
+}
+
+/* the tile-local entries to their ranks: a CTA per tile */
+__global__ void __launch_bounds__(256) k_index_compact(const u32* __restrict__ nl_local, u32 lcap, const u32* __restrict__ tile_count, const u32* __restrict__ tile_first,
+                                                      u32* __restrict__ nl, u32 nl_cap) {
+    const u32 tile = blockIdx.x;
+    const u32 n = tile_count[tile] < lcap ? tile_count[tile] : lcap, first = tile_first[tile];
+    const u32* src = nl_local + (size_t)tile * lcap;
+    for (u32 k = threadIdx.x; k < n; k += blockDim.x) if (first + k < nl_cap) nl[first + k] = src[k];
 }
 
 /* is the break that ends a line at text offset e (its last byte) two bytes long?  Only a swallowed '\n' can follow the byte that

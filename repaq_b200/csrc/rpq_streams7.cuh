@@ -57,13 +57,13 @@ struct S7Seg {
  * the table (stride S7_THREADS).
  * !WRITE: cells {last occurrence in the segment (15 bits, span relative) | bytes << 15 | start without predecessor << 25}; exc = bytes
  * of exception records; starts = run starts of values other than the major one.
- * WRITE: cells {offset of the next byte inside the span's bytes of the stream (17 bits) | last occurrence << 17}; exc = offset of the
- * next exception record.
+ * WRITE: cells {offset of the stream's next byte inside the span's slot (17 bits) | last occurrence << 17}; exc = offset of the next
+ * exception record.
  * Which positions head a token of their run (src/rfqcodec.cpp:677-700): position 1 of a run that starts at position 0 (a zero byte,
  * Q16), then every 32nd - kept as "the next head" nh, set at every run start whatever the value.
  */
 template <bool WRITE>
-__device__ __forceinline__ void s7_walk(const S7Seg& g, const u8* s_lut, u32* cell, u32 nb, u8* slot, const u32* s_base, u32& exc, u32& starts) {
+__device__ __forceinline__ void s7_walk(const S7Seg& g, const u8* s_lut, u32* cell, u8* slot, u32& exc, u32& starts) {
     u32 nh = g.nh;
     bool q16 = g.q16;
 #pragma unroll 1
@@ -73,23 +73,26 @@ __device__ __forceinline__ void s7_walk(const S7Seg& g, const u8* s_lut, u32* ce
         /* 64 bits of E from the piece's first position on: enough for every length token headed in the piece (32 positions) */
         const u64 ewin = piece ? (g.E >> (16u * piece)) | (g.Enext << (64u - 16u * piece)) : g.E;
         const uint4 q = *reinterpret_cast<const uint4*>(g.row + 16u * piece);
+        const u32 ewl = (u32)ewin, ewh = (u32)(ewin >> 32);
+        const bool col0 = g.s == 0 && piece == 0;                   /* the piece starts the column: positions 0 and 1 are special */
 #pragma unroll
         for (int jj = 0; jj < 16; jj++) {
             if (!((v16 >> jj) & 1u)) break;
             const u32 word = jj < 4 ? q.x : jj < 8 ? q.y : jj < 12 ? q.z : q.w;
             const u32 v = (word >> (8 * (jj & 3))) & 0xFFu;
-            const bool cont = ((ewin >> jj) & 1ull) != 0;
+            const bool cont = ((ewl >> jj) & 1u) != 0;
             const u32 j = 16u * piece + (u32)jj;
             const u32 p = g.s + j;
+            const bool p_is_0 = jj == 0 && col0;
             const bool head = cont && p == nh;
-            const bool zero = head && q16 && p == 1u;               /* Q16 */
-            if (!cont) { nh = p + 1u; q16 = p == 0; }
+            const bool zero = jj == 1 && col0 && head && q16;       /* Q16 */
+            if (!cont) { nh = p + 1u; if (jj == 0) q16 = col0; else q16 = false; }
             else if (head) nh = zero ? 2u : p + 32u;
             const u32 l = s_lut[v];
             if (l == LUT_SKIP) continue;                             /* the major quality: the decoder's fill value, no token */
             if (!WRITE && !cont) starts++;
             if (l == LUT_EXC) {
-                if (WRITE) { u8* o = slot + s_base[nb] + exc; o[0] = (u8)v; o[1] = (u8)p; o[2] = (u8)(p >> 8); o[3] = (u8)(p >> 16); o[4] = (u8)(p >> 24); }
+                if (WRITE) { u8* o = slot + exc; o[0] = (u8)v; o[1] = (u8)p; o[2] = (u8)(p >> 8); o[3] = (u8)(p >> 16); o[4] = (u8)(p >> 24); }
                 exc += 5u;
                 continue;
             }
@@ -98,28 +101,27 @@ __device__ __forceinline__ void s7_walk(const S7Seg& g, const u8* s_lut, u32* ce
             if (!WRITE) {
                 u32 add = head ? 1u : 0u;
                 if (!cont) {
-                    if ((ent & 0x7FFFu) != S7_NOLAST || p == 0) add = 1u;           /* a predecessor less than 64 positions back: one byte */
+                    if ((ent & 0x7FFFu) != S7_NOLAST || p_is_0) add = 1u;           /* a predecessor less than 64 positions back: one byte */
                     else ent = (ent & ~(0x7Fu << 25)) | (j << 25);                 /* sized by the scan */
                 }
                 ent = ((ent & ~0x7FFFu) | (p - g.lo)) + (add << 15);
             } else {
                 u32 at = ent & 0x1FFFFu;
                 const u32 lastb = ent >> 17;
-                u8* o = slot + s_base[l] + at;
+                u8* o = slot + at;
                 if (!cont) {
                     if (lastb != S7_NOLAST) {
                         const u32 dm = (p - g.lo) - lastb - 1u;
                         if (dm < 128u) { o[0] = (u8)dm; at += 1u; }
                         else if (dm < (1u << 14)) { o[0] = (u8)(0x80u | (dm >> 8)); o[1] = (u8)dm; at += 2u; }
                         else { o[0] = (u8)(0xE0u | (dm >> 24)); o[1] = (u8)(dm >> 16); o[2] = (u8)(dm >> 8); o[3] = (u8)dm; at += 4u; }
-                    } else if (p == 0) { o[0] = 0; at += 1u; }
+                    } else if (p_is_0) { o[0] = 0; at += 1u; }
                     /* else: the stream's first token of the span, k_layout's */
                 } else if (head) {
                     if (zero) o[0] = 0;
                     else {
-                        /* the positions of the run from here on, at most 32 */
-                        const u64 z = ~(ewin >> (jj + 1));
-                        const u32 more = (u32)(__ffsll((long long)z) - 1);             /* z != 0: the shift brought a zero in */
+                        /* the positions of the run after this one, as far as the token counts them (31) */
+                        const u32 more = (u32)(__ffs((int)~__funnelshift_r(ewl, ewh, jj + 1)) - 1);      /* no zero among 32: 0 - 1, clipped */
                         o[0] = (u8)(0xC0u | (more < 31u ? more : 31u));
                     }
                     at += 1u;
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(S7_THREADS) k_streams7(EncBatchDev b, HeaderDe
 
     /* ---- pass 1: count */
     u32 exc = 0, starts = 0;
-    s7_walk<false>(g, s_lut, T + tid, nb, nullptr, nullptr, exc, starts);
+    s7_walk<false>(g, s_lut, T + tid, nullptr, exc, starts);
     T[nb * S7_THREADS + tid] = S7_NOLAST | (exc << 15) | (S7_NOFIRST << 25);      /* exception records: 5 bytes per position (:750-758) */
     if (!list) {
         /* coding every span of the batch (the last batch was mostly dense): count the spans k_streams4 would have coded itself, so
@@ -285,9 +287,10 @@ __global__ void __launch_bounds__(S7_THREADS) k_streams7(EncBatchDev b, HeaderDe
     if (s_slot == ~0ull || s_bytes == 0) return;
     for (u32 st = tid; st < nstreams; st += S7_THREADS) job.dir[(size_t)span * nstreams + st].slot_off = s_base[st];
 
-    /* ---- pass 2: the bytes */
+    /* ---- pass 2: the bytes.  The cells' offsets become offsets inside the slot */
+    for (u32 st = 0; st < nstreams; st++) T[st * S7_THREADS + tid] += s_base[st];
     exc = T[nb * S7_THREADS + tid] & 0x1FFFFu;
-    s7_walk<true>(g, s_lut, T + tid, nb, job.slots + s_slot, s_base, exc, starts);
+    s7_walk<true>(g, s_lut, T + tid, job.slots + s_slot, exc, starts);
 }
 
 }  // namespace rpq
