@@ -651,7 +651,7 @@ def main():
     def roofline_of(prof, alg, fq_b, rfq_b, traffic=None, both_ways=True):
         kern_total = sum(ms for _, ms in prof.values())
         name, (n, ms) = max(prof.items(), key=lambda kv: kv[1][1])
-        ab = float(alg.get(name, fq_b))
+        ab = float(alg.get(name, fq_b)) / n                                     # the table holds bytes per step; per launch like the time
         ach = ab / 1e9 / (ms / n / 1e3)
         pipe_b = (fq_b + rfq_b) * (2 if both_ways else 1)
         return dict(bound="hbm", kernel=name, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=(traffic or {}).get(name), peak_source=peak_src,

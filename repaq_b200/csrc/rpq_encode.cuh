@@ -19,7 +19,8 @@ namespace rpq {
 /* ================================================================== FastqMeta::parse on a warp ==== */
 
 /* atoi as glibc does it: (int)strtol(s, 0, 10) - isspace skip, sign, digits, saturating at LONG_MIN/MAX */
-__device__ inline int atoi_like(const u8* s, int n) {
+/* (not inlined: the rare path of four call sites per kernel, a fifth of k_meta3's code otherwise - its warps wait for instructions) */
+__device__ __noinline__ int atoi_like(const u8* s, int n) {
     int i = 0;
     while (i < n && (s[i] == ' ' || (s[i] >= '\t' && s[i] <= '\r'))) i++;
     bool neg = false;

@@ -90,7 +90,7 @@ __device__ inline bool stage_quality_flat(const EncBatchDev& b, const ChunkDev& 
     u32* smw = reinterpret_cast<u32*>(sm);
     const bool pe_files = b.is_pe && b.two_files;
     const bool il = ck.interleaved != 0;
-    /* pass 1: the words that lie inside one read.  The read of a group's first position is guessed from the mean read length
+    /* pass 1: the groups of 16 positions that lie inside one read.  The read of a group's first position is guessed from the mean read length
      * (exact when all reads are equally long) and corrected by stepping. */
     const u32 ngroups = (hi - lo + 15u) >> 4;
     const u32 off0 = s_off[0];
@@ -105,35 +105,33 @@ __device__ inline bool stage_quality_flat(const EncBatchDev& b, const ChunkDev& 
         u32 off = s_off[r];
         const u8* q = b.t[pe_files ? ((first_rel + r) & 1u) : 0u].text + s_q[r];
         bool rev = il && ((first_rel + r) & 1u);
-#pragma unroll
-        for (u32 w = 0; w < 4; w++) {
-            const u32 pos = pos0 + 4u * w;
-            if (pos + 4u > hi) break;                              /* the last, partial word: pass 2 */
-            if (pos >= nxt) {
-                do { r++; nxt = s_off[r + 1]; } while (pos >= nxt);
-                off = s_off[r];
-                q = b.t[pe_files ? ((first_rel + r) & 1u) : 0u].text + s_q[r];
-                rev = il && ((first_rel + r) & 1u);
-            }
-            if (pos + 4u <= nxt) {
-                const u32 j = pos - off;
-                const uintptr_t ga = reinterpret_cast<uintptr_t>(rev ? q + ((nxt - off) - 4u - j) : q + j);
-                const u32* al = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
-                const u32 sh = (u32)(ga & 3u) * 8u;
-                u32 v = al[0];
-                if (sh) v = __funnelshift_r(v, al[1], sh);
-                smw[(pos - lo) >> 2] = rev ? __byte_perm(v, 0, 0x0123) : v;
-            }
+        if (pos0 + 16u <= nxt && pos0 + 16u <= hi) {
+            /* the whole group lies inside one read (eight or nine of ten groups of 150-base reads): five aligned words, four funnel
+             * shifts, one 128-bit store; the reverse strand reads the 16 bytes that end where the group's first position lies */
+            const u32 j = pos0 - off;
+            const uintptr_t ga = reinterpret_cast<uintptr_t>(rev ? q + ((nxt - off) - 16u - j) : q + j);
+            const u32* al = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
+            const u32 sh = (u32)(ga & 3u) * 8u;
+            const u32 a0 = al[0], a1 = al[1], a2 = al[2], a3 = al[3], a4 = al[4];
+            const u32 w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh), w2 = __funnelshift_r(a2, a3, sh), w3 = __funnelshift_r(a3, a4, sh);
+            uint4 v;
+            if (rev) v = make_uint4(__byte_perm(w3, 0, 0x0123), __byte_perm(w2, 0, 0x0123), __byte_perm(w1, 0, 0x0123), __byte_perm(w0, 0, 0x0123));
+            else v = make_uint4(w0, w1, w2, w3);
+            *reinterpret_cast<uint4*>(smw + ((pos0 - lo) >> 2)) = v;
+            continue;
         }
     }
-    /* pass 2: the words that hold the end of a read (bytes of two or more reads), and the partial word at hi: a thread each */
+    /* pass 2: the groups that hold the end of a read (bytes of two or more reads), and the partial group at hi: a thread per read
+     * end, byte by byte.  (Taking them inside pass 1, word by word, cost as much as the whole of pass 1: one lane in ten had such a
+     * group, so every warp walked the slow path with two or three lanes.) */
     for (u32 r = tid; r <= n; r += nthreads) {
         const u32 bnd = r < n ? s_off[r + 1] : hi;                 /* end of read r; r == n: the end of the window */
         if (r < n && bnd >= hi) continue;                          /* beyond the window (the window's end is r == n's) */
-        const u32 wpos = bnd & ~3u;
-        if (wpos == bnd || wpos < lo) continue;
+        if (bnd <= lo) continue;
+        const u32 gpos = lo + ((bnd - lo) & ~15u);
+        if (gpos == bnd) continue;                                 /* the read ends where a group ends */
         u32 r2 = r < n ? r : n - 1u;
-        for (u32 pp = wpos; pp < wpos + 4u && pp < hi; pp++) {
+        for (u32 pp = gpos; pp < gpos + 16u && pp < hi; pp++) {
             while (r2 > 0 && s_off[r2] > pp) r2--;
             while (pp >= s_off[r2 + 1]) r2++;
             const u32 off = s_off[r2], rl = s_off[r2 + 1] - off, j = pp - off;

@@ -140,8 +140,11 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams4(EncBatchDev b, HeaderDe
         return;
     }
     {
-        u64 m = starts; u32 k = base;
-        while (m) { const int i = __ffsll((long long)m) - 1; m &= m - 1; rs[k++] = (unsigned short)(s - lo + (u32)i); }
+        u32 m = (u32)starts, k = base;
+        const u32 rel = s - lo;
+        while (m) { const int i = __ffs((int)m) - 1; m &= m - 1u; rs[k++] = (unsigned short)(rel + (u32)i); }
+        m = (u32)(starts >> 32);
+        while (m) { const int i = __ffs((int)m) - 1; m &= m - 1u; rs[k++] = (unsigned short)(rel + 32u + (u32)i); }
     }
     const u32 nblocks = (n_runs + 31u) >> 5;
     for (u32 k = tid; k < nblocks * nstreams; k += S2_THREADS) { t_last[k] = (unsigned short)RL_NONE; t_bytes[k] = 0; }
@@ -219,9 +222,18 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams4(EncBatchDev b, HeaderDe
                 if (head < stop) bytes += (stop - head + 31u) / 32u;
             }
         }
-        /* byte offset inside (block, stream): exclusive scan per stream present in the warp */
-        u32 todo = __ballot_sync(0xffffffffu, valid);
+        /* byte offset inside (block, stream): the bytes of the lower lanes of the same stream.  Runs of up to 7 bytes (nearly all:
+         * a distance token and a few length tokens) by population counts over the bit planes of the byte counts; else an exclusive
+         * scan per stream present in the warp */
         u32 myoff = 0;
+        u32 todo = 0;
+        if (__any_sync(0xffffffffu, bytes >= 8u)) todo = __ballot_sync(0xffffffffu, valid);
+        else {
+            const u32 lower = peers & ((1u << lane) - 1u);
+            const u32 b1 = __ballot_sync(0xffffffffu, bytes & 1u), b2 = __ballot_sync(0xffffffffu, bytes & 2u), b4 = __ballot_sync(0xffffffffu, bytes & 4u);
+            myoff = (u32)__popc(lower & b1) + 2u * (u32)__popc(lower & b2) + 4u * (u32)__popc(lower & b4);
+            if (valid && (peers >> lane) <= 1u) t_bytes[(k >> 5) * nstreams + cls] = (unsigned short)(myoff + bytes);
+        }
         while (todo) {
             const int leader = __ffs((int)todo) - 1;
             const u32 c0 = __shfl_sync(0xffffffffu, cls, leader);
