@@ -470,17 +470,13 @@ __global__ void __launch_bounds__(CO_THREADS) k_coords(EncBatchDev b, HeaderDev 
  *   the rest, from s0 = (p==0 ? 2 : 1), in groups of <= 32: one byte 0xC0|(len-1) per group.
  * A token is owned by its head position.  A CTA takes a SPAN of consecutive positions of one chunk, stages them in
  * shared memory (for the quality column: gathered from the reads' quality lines, reversed for R2 of an interleaved
- * chunk; for N positions: the kept, possibly reverse-complemented bases), and every (segment, stream) work item walks
- * its segment sequentially with SIMD byte compares.  Only the very first distance token of a stream inside a span can
- * depend on data left of the span; it is left to k_layout (`firstpos`).
+ * chunk; for N positions: the kept, possibly reverse-complemented bases) and codes them (k_streams4: run-parallel from bit
+ * masks; k_streams7: dense columns, a thread per 64 positions; k_streams3 / k_streams2: the earlier generations, kept for the
+ * spans and inputs those cannot take).  Only the very first distance token of a stream inside a span can depend on data left
+ * of the span; it is left to k_layout (`firstpos`).
  */
-constexpr int ST_THREADS = 256;
 constexpr int ST_SPAN = 16384;       /* positions per CTA */
-constexpr int ST_SEG = 512;          /* positions per work item */
-constexpr int ST_NSEG = ST_SPAN / ST_SEG;
 constexpr int ST_HALO = 64;          /* staged on both sides of the span (look-back for run starts, look-ahead for run ends) */
-constexpr u32 ST_SLOT_BYTES = 5u * ST_SPAN + 64u;   /* worst case: every position an exception record (5 bytes) */
-constexpr u32 ST_DEFERRED = NONE32 - 1u;           /* it_first marker: first token of the stream in this span, sized by k_layout */
 
 struct SpanDir {                     /* per (span, stream): what the span produced */
     u32 bytes;                       /* token bytes written to the slot for this stream (without the deferred token) */
@@ -582,190 +578,6 @@ __device__ __forceinline__ void put_distance(TokSink& s, u32 dm1) {           /*
 }
 __device__ __forceinline__ u32 distance_len(u32 dm1) { return dm1 < 128u ? 1u : dm1 < (1u << 14) ? 2u : 4u; }
 
-/*
- * Walk one segment [s, e) for stream value v.  `sm` holds positions [sm_lo, sm_hi) of the chunk; n = chunk positions.
- * Tokens headed inside [s, e) go to `sink`.  Returns firstpos (deferred distance token) and lastpos via refs.
- */
-__device__ inline void walk_segment(const EncBatchDev& b, const ChunkDev& ck, u32 mode, const u8* sm, u32 sm_lo, u32 sm_hi, u32 n,
-                                    u32 s, u32 e, u8 v, TokSink& sink, u32& firstpos, u32& lastpos) {
-    auto at = [&](u32 p) -> u8 { return (p >= sm_lo && p < sm_hi) ? sm[p - sm_lo] : stream_byte_slow(b, ck, mode, p); };
-    firstpos = NONE32; lastpos = NONE32;
-    u32 last = NONE32;              /* previous position of v; NONE32 = unknown (left of the segment) */
-    bool last_known = false;
-    u32 p = s;
-    const u32 vv = 0x01010101u * v;
-    if (s > 0 && at(s) == v && at(s - 1) == v) {
-        /* a run crosses into the segment: find its start, emit the group tokens headed at or after s */
-        u32 p0 = s - 1;
-        while (p0 > 0 && at(p0 - 1) == v) p0--;
-        u32 r_end = s;                                         /* first position >= s not equal to v */
-        const u32 s0 = p0 == 0 ? 2u : 1u;
-        u32 head = p0 + s0;
-        if (head < s) head += ((s - head + 31u) / 32u) * 32u;
-        /* the run's end is needed only up to the last head in the segment + 32 */
-        while (r_end < n && at(r_end) == v && r_end < e + 32u) r_end++;
-        for (; head < e && head < r_end; head += 32u) { const u32 len = r_end - head < 32u ? r_end - head : 32u; sink.put((u8)(0xC0u | (len - 1u))); }
-        /* continue after the run (its true end may lie beyond what was scanned; then nothing of it is left in [s,e)) */
-        if (r_end >= e) { lastpos = e - 1; return; }
-        last = r_end - 1; last_known = true; lastpos = last;
-        p = r_end + 1;
-    }
-    while (p < e) {
-        /* next position m >= p with value v, word at a time (sm is 4-byte aligned at sm_lo, sm_lo % 4 == 0) */
-        u32 m = NONE32;
-        {
-            u32 q = p;
-            while (q < e) {
-                const u32 wbase = q & ~3u;
-                u32 wv;
-                if (wbase >= sm_lo && wbase + 4 <= sm_hi) wv = *reinterpret_cast<const u32*>(sm + (wbase - sm_lo));
-                else { wv = 0; for (u32 k = 0; k < 4; k++) { const u32 pp = wbase + k; const u8 by = (pp < n) ? at(pp) : (u8)~v; wv |= (u32)by << (8 * k); } }
-                u32 eq = __vcmpeq4(wv, vv) & 0x01010101u;
-                eq &= 0xFFFFFFFFu << (8 * (q & 3u));
-                if (eq) { const u32 cand = wbase + (u32)(__ffs((int)eq) - 1) / 8u; if (cand < e && cand < n) m = cand; break; }
-                q = wbase + 4;
-            }
-        }
-        if (m == NONE32) break;
-        u32 r_end = m + 1;
-        while (r_end < n && r_end < e + 34u && at(r_end) == v) r_end++;
-        /* distance token at m */
-        if (last_known) put_distance(sink, m - last - 1u);
-        else if (m == 0) put_distance(sink, 0u);                      /* last = -1: d = 1 */
-        else {
-            /* previous position unknown unless the run start is the very first position examined after chunk start */
-            firstpos = m;
-        }
-        const u32 s0 = m == 0 ? 2u : 1u;
-        if (m == 0 && r_end > 1 && 1u < e) sink.put(0x00);              /* position 1 of a run starting at 0 */
-        for (u32 head = m + s0; head < e && head < r_end; head += 32u) { const u32 len = r_end - head < 32u ? r_end - head : 32u; sink.put((u8)(0xC0u | (len - 1u))); }
-        if (r_end >= e) { lastpos = e - 1; return; }
-        last = r_end - 1; last_known = true; lastpos = last;
-        p = r_end + 1;
-    }
-}
-
-/* exceptions of a segment: {q, u32 LE pos} for bytes that are neither a stream value nor the major quality (:750-758) */
-__device__ inline void walk_exceptions(const HeaderDev& h, const u8* sm, u32 sm_lo, u32 n, u32 s, u32 e, TokSink& sink) {
-    const u32 hi = e < n ? e : n;
-    for (u32 p = s; p < hi; p++) {
-        const u8 q = sm[p - sm_lo];
-        if (h.lut[q] == LUT_EXC) { sink.put(q); sink.put((u8)p); sink.put((u8)(p >> 8)); sink.put((u8)(p >> 16)); sink.put((u8)(p >> 24)); }
-    }
-}
-
-/*
- * grid = total spans.  Dynamic shared memory: staged bytes (ST_SPAN + 2*ST_HALO) + per-item tables.
- * Item order inside the slot: stream-major, then segment, so every stream's bytes are contiguous.
- */
-__global__ void __launch_bounds__(ST_THREADS) k_streams(EncBatchDev b, HeaderDev h, StreamJob job, const u32* __restrict__ span_chunk) {
-    RPQ_DYN_SMEM(dyn);
-    __shared__ u32 s_wtot[ST_THREADS / 32];
-    __shared__ u32 s_carry;
-    __shared__ u64 s_slot;
-    const u32 span = blockIdx.x;
-    if (span >= *job.n_spans) return;
-    const u32 c = span_chunk[span];
-    const ChunkDev& ck = b.chunks[c];
-    const u32 n = job.mode ? ck.seq_kept : ck.total_len;
-    const u32 lo = (span - job.span_first[c]) * ST_SPAN;
-    const u32 hi = lo + ST_SPAN < n ? lo + ST_SPAN : n;
-    const u32 sm_lo = lo >= ST_HALO ? lo - ST_HALO : 0, sm_hi = hi + ST_HALO < n ? hi + ST_HALO : n;
-    u8* sm = dyn;                                       /* [ST_SPAN + 2*ST_HALO], 16-byte aligned; sm_lo is a multiple of 4 */
-    u32* it_bytes = reinterpret_cast<u32*>(dyn + ST_SPAN + 2 * ST_HALO);
-    const u32 nstreams = job.nstreams, nseg = (hi - lo + ST_SEG - 1) / ST_SEG, nitems = nstreams * ST_NSEG;
-    u32* it_first = it_bytes + nitems; u32* it_last = it_first + nitems; u32* it_off = it_last + nitems;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    stage_positions(b, h, ck, job.mode, sm_lo, sm_hi, sm);
-    __syncthreads();
-
-    /* pass 1: count */
-    for (u32 it = tid; it < nitems; it += ST_THREADS) {
-        const u32 st = it / ST_NSEG, sg = it % ST_NSEG;
-        u32 bytes = 0, fp = NONE32, lp = NONE32;
-        if (sg < nseg) {
-            const u32 s = lo + sg * ST_SEG, e = s + ST_SEG < hi ? s + ST_SEG : hi;
-            TokSink sink{nullptr, 0};
-            if (job.mode == 0 && st == nstreams - 1) walk_exceptions(h, sm, sm_lo, n, s, e, sink);
-            else walk_segment(b, ck, job.mode, sm, sm_lo, sm_hi, n, s, e, job.mode ? (u8)'N' : h.normal_bins[st], sink, fp, lp);
-            bytes = sink.n;
-        }
-        it_bytes[it] = bytes; it_first[it] = fp; it_last[it] = lp;
-    }
-    __syncthreads();
-    /* resolve, inside the span, the deferred first token of every segment but the stream's first one that has any:
-     * its previous position is the lastpos of an earlier segment of the same span.  Done by one thread per stream. */
-    for (u32 st = tid; st < nstreams; st += ST_THREADS) {
-        u32 prev_last = NONE32; bool have = false; u32 span_first = NONE32, span_last = NONE32;
-        const bool is_exc = job.mode == 0 && st == nstreams - 1;
-        for (u32 sg = 0; sg < ST_NSEG && !is_exc; sg++) {
-            const u32 it = st * ST_NSEG + sg;
-            const u32 fp = it_first[it];
-            if (fp != NONE32) {
-                if (have) it_bytes[it] += distance_len(fp - prev_last - 1u);     /* pass 2 emits it, then the rest */
-                else { span_first = fp; it_first[it] = ST_DEFERRED; }            /* left to k_layout */
-            }
-            if (it_last[it] != NONE32) { prev_last = it_last[it]; have = true; span_last = prev_last; }
-        }
-        SpanDir d; d.bytes = 0; d.slot_off = 0; d.firstpos = span_first; d.lastpos = span_last; d.dst = 0; d.first_tok = 0; d.first_len = 0; d.pad = 0;
-        job.dir[(size_t)span * nstreams + st] = d;
-    }
-    __syncthreads();
-    /* exclusive scan of item bytes in item order */
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (u32 base = 0; base < nitems; base += ST_THREADS) {
-        const u32 it = base + tid;
-        const u32 v = it < nitems ? it_bytes[it] : 0;
-        u32 wt; const u32 ex = warp_excl_scan(v, lane, wt);
-        if (lane == 0) s_wtot[warp] = wt;
-        __syncthreads();
-        u32 off = s_carry;
-        for (int q = 0; q < warp; q++) off += s_wtot[q];
-        if (it < nitems) it_off[it] = off + ex;
-        __syncthreads();
-        if (tid == 0) { u32 o = s_carry; for (int q = 0; q < ST_THREADS / 32; q++) o += s_wtot[q]; s_carry = o; }
-        __syncthreads();
-    }
-    for (u32 st = tid; st < nstreams; st += ST_THREADS) {
-        SpanDir& d = job.dir[(size_t)span * nstreams + st];
-        d.slot_off = it_off[st * ST_NSEG];
-        const u32 endoff = (st + 1 < nstreams) ? it_off[(st + 1) * ST_NSEG] : s_carry;
-        d.bytes = endoff - d.slot_off;
-    }
-    /* pass 2: write */
-    if (tid == 0) {
-        const u64 at = atomicAdd(job.slot_cursor, (u64)s_carry);
-        job.span_slot[span] = at;
-        if (at + s_carry > job.slot_cap) { atomicOr(job.overflow, 1u); s_slot = ~0ull; } else s_slot = at;
-    }
-    __syncthreads();
-    if (s_slot == ~0ull) return;
-    u8* slot = job.slots + s_slot;
-    for (u32 it = tid; it < nitems; it += ST_THREADS) {
-        const u32 st = it / ST_NSEG, sg = it % ST_NSEG;
-        if (sg >= nseg || it_bytes[it] == 0) continue;
-        const u32 s = lo + sg * ST_SEG, e = s + ST_SEG < hi ? s + ST_SEG : hi;
-        TokSink sink{slot + it_off[it], 0};
-        if (job.mode == 0 && st == nstreams - 1) { walk_exceptions(h, sm, sm_lo, n, s, e, sink); continue; }
-        const u32 fp_state = it_first[it];
-        if (fp_state != NONE32 && fp_state != ST_DEFERRED) {
-            /* first token of this segment resolved inside the span: previous position = lastpos of the nearest earlier segment */
-            u32 prev_last = NONE32;
-            for (int q = (int)sg - 1; q >= 0; q--) { const u32 lp = it_last[st * ST_NSEG + q]; if (lp != NONE32) { prev_last = lp; break; } }
-            put_distance(sink, fp_state - prev_last - 1u);
-        }
-        u32 fp, lp;
-        walk_segment(b, ck, job.mode, sm, sm_lo, sm_hi, n, s, e, job.mode ? (u8)'N' : h.normal_bins[st], sink, fp, lp);
-    }
-}
-
-/* ================================================================== k_layout ==== */
-/*
- * One CTA per chunk.  For every stream: walk its spans in order, size the deferred first tokens (they need the
- * previous span's lastpos), place every piece; then the column sizes, mSize (Q2) and the serialised size.
- */
 constexpr int LAY_THREADS = 128;
 
 __device__ inline void layout_stream_set(const StreamJob& job, u32 c, u32 st, u32 table_bytes, u32* stream_len) {
