@@ -117,37 +117,52 @@ __device__ __forceinline__ void qx_step(const QCursor& S, u32 base, u32 cura, u3
     if (left < 8u) B = left ? B & ((1ull << (8u * left)) - 1ull) : 0ull;
     const u32 nv = left < 4u ? left : 4u;
     const u32 cur = (u32)B;
-    u32 L[4];
+    u32 adv[4], run[4]; u32 lane_adv = 0;
+    /* a step of one-byte tokens only (0xxxxxxx distances, 110xxxxx lengths: the rule in the dense streams of columns with ~40
+     * values) with nothing spilling in needs no token chain: every byte heads a token */
+    const u32 multi = cur & (~(cur << 1) | (cur << 2)) & 0x80808080u;       /* bit 7 of the bytes 10xxxxxx and 111xxxxx */
+    if (skip == 0u && __ballot_sync(0xffffffffu, multi != 0u) == 0u) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) { const u32 b0 = (cur >> (8 * k)) & 0xFFu; L[k] = !(b0 & 0x80u) ? 1u : !(b0 & 0x40u) ? 2u : !(b0 & 0x20u) ? 1u : 4u; }
-    /* exit spill if the first token of the lane starts at byte r */
-    const u32 e3 = L[3] - 1u;
-    const u32 e2 = L[2] == 1u ? e3 : L[2] - 2u;
-    const u32 e1 = L[1] == 1u ? e2 : (L[1] == 2u ? e3 : 1u);
-    const u32 e0 = L[0] == 1u ? e1 : (L[0] == 2u ? e2 : 0u);
-    const u32 f = e0 | (e1 << 2) | (e2 << 4) | (e3 << 6);
-    const bool is_const = f == e0 * 0x55u;
-    u32 r_in = lane == 0 ? skip : 4u;                    /* 4 = not known yet */
-    for (;;) {
-        const u32 mine = r_in < 4u ? (f >> (2u * r_in)) & 3u : (is_const ? e0 : 4u);
-        const u32 got = __shfl_up_sync(0xffffffffu, mine, 1);
-        if (r_in == 4u && lane > 0) r_in = got;
-        if (__ballot_sync(0xffffffffu, r_in == 4u) == 0u) break;
-    }
-    skip = __shfl_sync(0xffffffffu, (f >> (2u * r_in)) & 3u, 31);
-    u32 adv[4], run[4]; u32 lane_adv = 0; u32 next_head = r_in;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        adv[k] = 0; run[k] = 0;
-        if ((u32)k == next_head && (u32)k < nv) {
-            const u32 t = (u32)(B >> (8 * k));            /* the token's bytes, first byte lowest */
-            const u32 b0 = t & 0xFFu;
-            if (!(b0 & 0x80u)) adv[k] = b0 + 1u;
-            else if (!(b0 & 0x40u)) adv[k] = (((b0 & 0x3Fu) << 8) | ((t >> 8) & 0xFFu)) + 1u;
-            else if (!(b0 & 0x20u)) { run[k] = (b0 & 0x1Fu) + 1u; adv[k] = run[k]; }
-            else adv[k] = (((b0 & 0x1Fu) << 24) | (((t >> 8) & 0xFFu) << 16) | (((t >> 16) & 0xFFu) << 8) | ((t >> 24) & 0xFFu)) + 1u;
+        for (int k = 0; k < 4; k++) {
+            const u32 b0 = (cur >> (8 * k)) & 0xFFu;
+            const bool len_tok = (b0 & 0x80u) != 0;
+            adv[k] = (u32)k < nv ? (b0 & (len_tok ? 0x1Fu : 0x7Fu)) + 1u : 0u;
+            run[k] = len_tok ? adv[k] : 0u;
             lane_adv += adv[k];
-            next_head = (u32)k + L[k];
+        }
+    } else {
+        u32 L[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const u32 b0 = (cur >> (8 * k)) & 0xFFu; L[k] = !(b0 & 0x80u) ? 1u : !(b0 & 0x40u) ? 2u : !(b0 & 0x20u) ? 1u : 4u; }
+        /* exit spill if the first token of the lane starts at byte r */
+        const u32 e3 = L[3] - 1u;
+        const u32 e2 = L[2] == 1u ? e3 : L[2] - 2u;
+        const u32 e1 = L[1] == 1u ? e2 : (L[1] == 2u ? e3 : 1u);
+        const u32 e0 = L[0] == 1u ? e1 : (L[0] == 2u ? e2 : 0u);
+        const u32 f = e0 | (e1 << 2) | (e2 << 4) | (e3 << 6);
+        const bool is_const = f == e0 * 0x55u;
+        u32 r_in = lane == 0 ? skip : 4u;                    /* 4 = not known yet */
+        for (;;) {
+            const u32 mine = r_in < 4u ? (f >> (2u * r_in)) & 3u : (is_const ? e0 : 4u);
+            const u32 got = __shfl_up_sync(0xffffffffu, mine, 1);
+            if (r_in == 4u && lane > 0) r_in = got;
+            if (__ballot_sync(0xffffffffu, r_in == 4u) == 0u) break;
+        }
+        skip = __shfl_sync(0xffffffffu, (f >> (2u * r_in)) & 3u, 31);
+        u32 next_head = r_in;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            adv[k] = 0; run[k] = 0;
+            if ((u32)k == next_head && (u32)k < nv) {
+                const u32 t = (u32)(B >> (8 * k));            /* the token's bytes, first byte lowest */
+                const u32 b0 = t & 0xFFu;
+                if (!(b0 & 0x80u)) adv[k] = b0 + 1u;
+                else if (!(b0 & 0x40u)) adv[k] = (((b0 & 0x3Fu) << 8) | ((t >> 8) & 0xFFu)) + 1u;
+                else if (!(b0 & 0x20u)) { run[k] = (b0 & 0x1Fu) + 1u; adv[k] = run[k]; }
+                else adv[k] = (((b0 & 0x1Fu) << 24) | (((t >> 8) & 0xFFu) << 16) | (((t >> 16) & 0xFFu) << 8) | ((t >> 24) & 0xFFu)) + 1u;
+                lane_adv += adv[k];
+                next_head = (u32)k + L[k];
+            }
         }
     }
     u32 tot; const u32 ex = warp_excl_scan(lane_adv, lane, tot);

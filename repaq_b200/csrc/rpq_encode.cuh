@@ -528,20 +528,25 @@ __device__ inline u8 stream_byte_slow(const EncBatchDev& b, const ChunkDev& ck, 
 }
 
 /* stage positions [lo, hi) of the chunk's concatenation into sm[pos - lo] */
-__device__ inline void stage_positions(const EncBatchDev& b, const HeaderDev& h, const ChunkDev& ck, u32 mode, u32 lo, u32 hi, u8* sm) {
+/* returns false when nothing but cleared bytes was staged (N positions of a window whose reads are all plain bases): the caller may
+ * skip the span.  Called by every thread of the CTA. */
+__device__ inline bool stage_positions(const EncBatchDev& b, const HeaderDev& h, const ChunkDev& ck, u32 mode, u32 lo, u32 hi, u8* sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    if (hi <= lo) return;
+    if (hi <= lo) return true;
     const u32* offs = mode ? b.seqoff : b.qualoff;
     u32 a = 0, z = ck.count;            /* first read that can contain `lo`: largest rel with offs <= lo */
     while (z - a > 1) { const u32 mid = (a + z) >> 1; if (offs[ck.first + mid] <= lo) a = mid; else z = mid; }
     /* N positions: a read of plain bases only has none (k_meta3 has looked at every character), so the window is cleared and
      * only the other reads - a few per thousand - are staged */
     const bool sparse = mode != 0 && b.unclean != nullptr;
+    __shared__ int s_staged;
     if (sparse) {
+        if (threadIdx.x == 0) s_staged = 0;
         const u32 n16 = (hi - lo + 15u) >> 4;
         for (u32 k = threadIdx.x; k < n16; k += blockDim.x) reinterpret_cast<uint4*>(sm)[k] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
     }
+    int staged = 0;
     for (u32 rel = a + warp; rel < ck.count; rel += nwarps) {
         const u32 i = ck.first + rel;
         const u32 off = offs[i];
@@ -550,6 +555,7 @@ __device__ inline void stage_positions(const EncBatchDev& b, const HeaderDev& h,
         const u32 rl = b.rlen[i];
         const u32 n = mode ? kept_bases(b, h, ck.interleaved != 0, i, rel) : rl;
         if (off + n <= lo) continue;
+        staged = 1;
         u32 f, rec; read_locus(b, i, f, rec);
         const TextDev& t = b.t[f];
         const bool rev = ck.interleaved && (rel & 1u);
@@ -564,6 +570,10 @@ __device__ inline void stage_positions(const EncBatchDev& b, const HeaderDev& h,
             else for (u32 j = j0 + lane; j < j1; j += 32) sm[off + j - lo] = s[j];
         }
     }
+    if (!sparse) return true;
+    if (staged && lane == 0) s_staged = 1;
+    __syncthreads();
+    return s_staged != 0;
 }
 
 struct TokSink {            /* count-only or writing */

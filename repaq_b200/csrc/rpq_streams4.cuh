@@ -76,7 +76,15 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams4(EncBatchDev b, HeaderDe
         u32* s_off = reinterpret_cast<u32*>(arrays);
         if (!stage_quality_flat(b, ck, sm_lo, sm_hi, sm, job.span_read0[span], s_off, s_off + SQ_CAP + 1, &s_tmp))
             stage_quality_words(b, ck, sm_lo, sm_hi, sm, job.span_read0[span]);
-    } else stage_positions(b, h, ck, mode, sm_lo, sm_hi, sm);
+    } else if (!stage_positions(b, h, ck, mode, sm_lo, sm_hi, sm)) {
+        /* N positions, and every read that reaches into the span is plain bases: an empty span */
+        if (tid == 0) {
+            SpanDir d; d.bytes = 0; d.slot_off = 0; d.firstpos = NONE32; d.lastpos = NONE32; d.dst = 0; d.first_tok = 0; d.first_len = 0; d.pad = 0;
+            job.dir[(size_t)span * nstreams] = d;
+            job.span_slot[span] = 0;
+        }
+        return;
+    }
     __syncthreads();
 
     /* ---- masks of the thread's 64 positions (as in k_streams3) */

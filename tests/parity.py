@@ -146,3 +146,21 @@ def check_adversarial_quality_columns(codec, n_reads=16000):
     dense = (string.ascii_uppercase + string.digits + "#$%&").encode()
     check_against_oracle(codec, adversarial_quality_column(n_reads, rl=100, seed=13, alphabet=dense, dense=True), k=100)
     check_against_oracle(codec, adversarial_quality_column(n_reads, rl=37, seed=14, alphabet=dense[:12], dense=True), k=100)
+
+
+def check_control_bytes_in_names(codec):
+    """the line index flags the bytes 0x08..0x0F with one compare and then looks at each: tabs, form feeds ... in names and strand
+    lines are ordinary characters, only line feeds and carriage returns end lines"""
+    from tools import fqgen
+    r1, r2 = fqgen.generate(3000, seed=9, paired=True)
+    out = []
+    for r in (r1, r2):
+        lines = bytes(r).split(b"\n")
+        for k in range(0, len(lines) - 1, 4):
+            if (k // 4) % 3 == 0:
+                lines[k] = lines[k] + b"\tx\x0by\x0cz\x08\x0e\x0f"
+            if (k // 4) % 5 == 0:
+                lines[k + 2] = b"+\t" + lines[k][1:10]
+        out.append(b"\n".join(lines))
+    check_against_oracle(codec, out[0], out[1], k=100)
+    check_against_oracle(codec, out[0].replace(b"\n", b"\r\n"), None, k=100, roundtrip=False)

@@ -462,3 +462,7 @@ def test_n_positions_in_few_reads(codec):
 
 def test_adversarial_quality_columns(codec):
     parity.check_adversarial_quality_columns(codec)
+
+
+def test_control_bytes_in_names(codec):
+    parity.check_control_bytes_in_names(codec)

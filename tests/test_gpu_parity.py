@@ -185,3 +185,7 @@ def test_n_positions_in_few_reads(codec):
 
 def test_adversarial_quality_columns(codec):
     parity.check_adversarial_quality_columns(codec, n_reads=60000)
+
+
+def test_control_bytes_in_names(codec):
+    parity.check_control_bytes_in_names(codec)
