@@ -29,7 +29,9 @@ extern "C" {
 #define RPQ_ERR_FASTQ (-4)         /* input outside the supported FASTQ domain */
 #define RPQ_ERR_COORD (-5)         /* "The X/Y coordinate cannot be larger than 2M" (src/rfqcodec.cpp:1316) */
 #define RPQ_ERR_HEADER (-6)        /* bad .rfq header (src/rfqheader.cpp:23-25,40-42; src/rfqcodec.cpp:1065) */
-#define RPQ_ERR_RFQ (-7)           /* truncated / malformed .rfq chunk */
+#define RPQ_ERR_RFQ (-7)           /* an .rfq the decoder cannot take (too many reads for one call, an empty run-length column ...); columns that merely
+                                      disagree with each other are decoded with the reference's tolerances (positions past the chunk ignored, sizes
+                                      clamped to the chunk: SURVEY Q20), not rejected */
 #define RPQ_ERR_QUALITY (-8)       /* header construction: bad quality / base characters (src/rfqheader.cpp:141,155-166,204) */
 
 /* RfqHeader flag bits (src/rfqheader.h:24-42) */

@@ -179,6 +179,7 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     c->device = device;
     if (rt_stream_create(&c->stream)) { delete c; return RPQ_ERR_CUDA; }
     c->pinned_small = rt_malloc_pinned(65536);
+    if (!c->pinned_small) { rt_stream_destroy(c->stream); delete c; return RPQ_ERR_NOMEM; }      /* every scalar read-back goes through it */
     for (auto& e : c->ev) rt_event_create(&e);
     memset(&c->stats, 0, sizeof c->stats);
     memset(&c->hdr, 0, sizeof c->hdr);
@@ -200,6 +201,7 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     cudaFuncSetAttribute(k_streams4, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_streams7, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_meta3, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_emit2, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_dec_format4, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
     cudaFuncSetAttribute(k_dec_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
 #endif

@@ -244,14 +244,25 @@ int host_walk_chunk(const rpq_header* h, const uint8_t* in, uint64_t len, HostCh
         if (len_same && !all_same) t *= n;
         return t;
     };
-    c->n1_size = (uint32_t)arena(c->off_n1len, c->n1len_size, fl & RPQ_NAME1_LEN_SAME, fl & RPQ_NAME1_SAME); TAKE(off_n1, c->n1_size);
-    if (h->flags & RPQ_HAS_NAME2) { c->n2_size = (uint32_t)arena(c->off_n2len, c->n2len_size, fl & RPQ_NAME2_LEN_SAME, fl & RPQ_NAME2_SAME); TAKE(off_n2, c->n2_size); }
-    c->strand_size = (uint32_t)arena(c->off_slen, c->slen_size, fl & RPQ_STRAND_LEN_SAME, fl & RPQ_STRAND_SAME); TAKE(off_strand, c->strand_size);
+    /* an arena of 4 GiB or more (a crafted length byte times a crafted read count) does not fit the chunk whatever follows: it must
+     * not wrap to a small 32-bit size that passes the checks */
+    const uint64_t a1 = arena(c->off_n1len, c->n1len_size, fl & RPQ_NAME1_LEN_SAME, fl & RPQ_NAME1_SAME);
+    if (a1 > len) return 1;
+    c->n1_size = (uint32_t)a1; TAKE(off_n1, c->n1_size);
+    if (h->flags & RPQ_HAS_NAME2) {
+        const uint64_t a2 = arena(c->off_n2len, c->n2len_size, fl & RPQ_NAME2_LEN_SAME, fl & RPQ_NAME2_SAME);
+        if (a2 > len) return 1;
+        c->n2_size = (uint32_t)a2; TAKE(off_n2, c->n2_size);
+    }
+    const uint64_t a3 = arena(c->off_slen, c->slen_size, fl & RPQ_STRAND_LEN_SAME, fl & RPQ_STRAND_SAME);
+    if (a3 > len) return 1;
+    c->strand_size = (uint32_t)a3; TAKE(off_strand, c->strand_size);
     TAKE(off_seq, c->seq_size);
     TAKE(off_qual, c->qual_size);
     if (il && (h->flags & RPQ_ENCODE_PE_BY_OVERLAP)) { c->ov_size = n / 2; TAKE(off_ov, c->ov_size); }
     if (h->flags & RPQ_ENCODE_N_POS) TAKE(off_npos, c->npos_size);
 #undef TAKE
+    if (at > 0xFFFFFFFFull) return 1;
     c->bytes = (uint32_t)at;
     return 0;
 }

@@ -41,12 +41,6 @@ __device__ __forceinline__ u32 eq_lowascii(u32 v, u32 cccc) {
     const u32 t = ((v ^ cccc) & 0x7f7f7f7fu) + 0x7f7f7f7fu;
     return ~(t | v) & 0x80808080u;
 }
-/* bit 7 of every byte set iff the byte is one of 0x08..0x0F (backspace, tab, line feed, vertical tab, form feed, carriage return, SO,
- * SI): (v ^ 0x08) & 0x78 is zero exactly for them among the bytes below 0x80 */
-__device__ __forceinline__ u32 ctl_lowascii(u32 v) {
-    const u32 t = ((v ^ 0x08080808u) & 0x78787878u) + 0x7f7f7f7fu;
-    return ~(t | v) & 0x80808080u;
-}
 /* bit 7 of every byte CLEAR iff that byte equals c (the complement of eq_lowascii before masking): lets four words be
  * AND-ed together for an "any byte equals c" test */
 __device__ __forceinline__ u32 ne_lowascii(u32 v, u32 cccc) {
@@ -131,32 +125,20 @@ __global__ void __launch_bounds__(IDX_THREADS, 3) k_index_lines(const u8* __rest
     const int lim = p0 >= len ? 0 : (len - p0 >= IDX_ROW ? IDX_ROW : (int)(len - p0));
     if (lim < IDX_ROW) for (int i = lim; i < IDX_ROW; i++) row[i] = 0;     /* the end of the text: zeros match nothing */
 
-    /* ---- masks of the row: '\n' and (rarely) '\r'.  ONE exact compare per word finds the bytes 0x08..0x0F (three instructions, the
-     * price of one character: the kernel is bound by the ALU pipe); the one or two bytes a row has of them are then looked at: line
-     * feed, carriage return, or a tab in a name */
+    /* ---- masks of the row: '\n' and (rarely) '\r' */
     u64 nlo = 0, nhi = 0, clo = 0, chi = 0;
-    {
-        u32 f0 = 0, f1 = 0, f2 = 0, f3 = 0;                       /* flags of the row's 128 bytes */
 #pragma unroll
-        for (int k = 0; k < IDX_PIECES; k++) {
-            const int kk = (k + lane) & (IDX_PIECES - 1);
-            const uint4 v = *reinterpret_cast<const uint4*>(row + 16 * kk);
-            const u32 m = mask16(ctl_lowascii(v.x), ctl_lowascii(v.y), ctl_lowascii(v.z), ctl_lowascii(v.w)) << (16 * (kk & 1));
-            const int w = kk >> 1;
-            if (w == 0) f0 |= m; else if (w == 1) f1 |= m; else if (w == 2) f2 |= m; else f3 |= m;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            u32 m = q == 0 ? f0 : q == 1 ? f1 : q == 2 ? f2 : f3, nl32 = 0, cr32 = 0;
-            while (m) {
-                const int bb = __ffs((int)m) - 1;
-                m &= m - 1u;
-                const u8 c = row[32 * q + bb];
-                nl32 |= (c == '\n' ? 1u : 0u) << bb;
-                cr32 |= (c == '\r' ? 1u : 0u) << bb;
-            }
-            if (q == 0) { nlo = nl32; clo = cr32; } else if (q == 1) { nlo |= (u64)nl32 << 32; clo |= (u64)cr32 << 32; }
-            else if (q == 2) { nhi = nl32; chi = cr32; } else { nhi |= (u64)nl32 << 32; chi |= (u64)cr32 << 32; }
+    for (int k = 0; k < IDX_PIECES; k++) {
+        const int kk = (k + lane) & (IDX_PIECES - 1);
+        const uint4 v = *reinterpret_cast<const uint4*>(row + 16 * kk);
+        const u32 m = mask16(eq_lowascii(v.x, 0x0A0A0A0Au), eq_lowascii(v.y, 0x0A0A0A0Au), eq_lowascii(v.z, 0x0A0A0A0Au), eq_lowascii(v.w, 0x0A0A0A0Au));
+        const u32 nocr = ne_lowascii(v.x, 0x0D0D0D0Du) & ne_lowascii(v.y, 0x0D0D0D0Du) & ne_lowascii(v.z, 0x0D0D0D0Du) & ne_lowascii(v.w, 0x0D0D0D0Du);
+        const u64 placed = (u64)m << (16 * (kk & 3));
+        if (kk & 4) nhi |= placed; else nlo |= placed;
+        if (~nocr & 0x80808080u) {
+            const u32 c = mask16(eq_lowascii(v.x, 0x0D0D0D0Du), eq_lowascii(v.y, 0x0D0D0D0Du), eq_lowascii(v.z, 0x0D0D0D0Du), eq_lowascii(v.w, 0x0D0D0D0Du));
+            const u64 pc = (u64)c << (16 * (kk & 3));
+            if (kk & 4) chi |= pc; else clo |= pc;
         }
     }
     /* ---- line ends E and, per line end, whether the byte after it belongs to the break (swn) */
