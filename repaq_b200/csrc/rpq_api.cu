@@ -201,7 +201,6 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     cudaFuncSetAttribute(k_streams4, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_streams7, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_meta3, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(k_emit2, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_dec_format4, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
     cudaFuncSetAttribute(k_dec_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
 #endif

@@ -159,24 +159,16 @@ __device__ __forceinline__ u32 packed_window(const u32* src, u32 j0, u32 pkw) {
     return __funnelshift_r(lo, hi, sh);
 }
 
-__global__ void __launch_bounds__(256) k_emit2(EncBatchDev b, HeaderDev h, u8* out, u32 stage) {
-    RPQ_DYN_SMEM(dyn);
+__global__ void __launch_bounds__(256) k_emit2(EncBatchDev b, HeaderDev h, u8* out) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    /* the packed words of the CTA's reads, coalesced into shared memory (they are contiguous: pkw words per read, pkw odd): a
-     * thread walking its own row in global memory is one dependent 44-byte-strided load after the other (r02: 26 warps waiting
-     * on memory per instruction issued) */
-    u32* s_pk = reinterpret_cast<u32*>(dyn);
-    const u32 i_first = blockIdx.x * blockDim.x;
-    const u32 n_staged = !stage ? 0u : b.n_reads - i_first < blockDim.x ? b.n_reads - i_first : blockDim.x;      /* stage == 0: rows too long for shared memory */
-    if (n_staged) {
-        const uint4* g4 = reinterpret_cast<const uint4*>(b.pk + (size_t)i_first * b.pkw);      /* 256 * pkw * 4 bytes per CTA: 16-byte aligned */
-        const u32 nw = n_staged * b.pkw;
-        for (u32 k = threadIdx.x; k < nw / 4u; k += blockDim.x) reinterpret_cast<uint4*>(s_pk)[k] = g4[k];
-        for (u32 k = (nw & ~3u) + threadIdx.x; k < nw; k += blockDim.x) s_pk[k] = b.pk[(size_t)i_first * b.pkw + k];
-    }
-    __syncthreads();
     if (i >= b.n_reads) return;
-    auto pk_row = [&](u32 ii) -> const u32* { return (ii >= i_first && ii - i_first < n_staged) ? s_pk + (size_t)(ii - i_first) * b.pkw : b.pk + (size_t)ii * b.pkw; };
+#ifndef RPQ_EMU
+    {   /* the read's packed words (two or three sectors) are on their way while the chunk and per-read tables are fetched */
+        const char* row = reinterpret_cast<const char*>(b.pk + (size_t)i * b.pkw);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 4 * b.pkw - 4));
+    }
+#endif
     const u32 c = chunk_of_read(b, i);
     const ChunkDev& ck = b.chunks[c];
     const u32 rel = i - ck.first;
@@ -206,7 +198,7 @@ __global__ void __launch_bounds__(256) k_emit2(EncBatchDev b, HeaderDev h, u8* o
     auto window = [&](u32 ii, u32 rr, u32 j0) -> u32 {
         if (il && (rr & 1u)) {
             const int ov = (h.flags & RPQ_ENCODE_PE_BY_OVERLAP) ? (int)b.ov[ii >> 1] : 0;
-            return packed_window(pk_row(ii), j0 + (ov > 0 ? (u32)ov : 0u), pkw);
+            return packed_window(b.pk + (size_t)ii * pkw, j0 + (ov > 0 ? (u32)ov : 0u), pkw);
         }
         if (rc_file && (rr & 1u)) {
             u32 f, rec; read_locus(b, ii, f, rec);
@@ -216,7 +208,7 @@ __global__ void __launch_bounds__(256) k_emit2(EncBatchDev b, HeaderDev h, u8* o
             for (u32 k = 0; k < 16u && j0 + k < rl2; k++) w |= base_code(sq[j0 + k]) << (2 * k);
             return w;
         }
-        return packed_window(pk_row(ii), j0, pkw);
+        return packed_window(b.pk + (size_t)ii * pkw, j0, pkw);
     };
     u8* col = o + ck.off_seq;
     /* The column starts wherever the chunk layout puts it; output words are therefore counted from the 4-byte boundary at or
@@ -266,7 +258,7 @@ __global__ void __launch_bounds__(256) k_emit2(EncBatchDev b, HeaderDev h, u8* o
     if (w1 > w0 && !(rc_file && (rel & 1u) && !il)) {
         const int ov = (il && (rel & 1u) && (h.flags & RPQ_ENCODE_PE_BY_OVERLAP)) ? (int)b.ov[i >> 1] : 0;
         const u32 a = 16u * w0 - sh_so + (ov > 0 ? (u32)ov : 0u);
-        const u32* src = pk_row(i);
+        const u32* src = b.pk + (size_t)i * pkw;
         const u32 sh = (a & 15u) * 2u;
         u32 k = a >> 4;
         u32 lo = k < pkw ? src[k] : 0u;

@@ -95,44 +95,31 @@ __device__ inline bool stage_quality_flat(const EncBatchDev& b, const ChunkDev& 
     const u32 ngroups = (hi - lo + 15u) >> 4;
     const u32 off0 = s_off[0];
     const float per_pos = n ? (float)n / (float)(s_off[n] - off0) : 0.f;
-    /* two groups per iteration: their ten loads are in flight together (the loop is otherwise one dependent chain per group:
-     * table look-ups, loads, store) */
-    auto locate = [&](u32 g, const u32*& al, u32& sh, bool& rev) -> bool {
+    for (u32 g = tid; g < ngroups; g += nthreads) {
         const u32 pos0 = lo + 16u * g;
         u32 r = (u32)((float)(pos0 - off0) * per_pos);
         if (r >= n) r = n - 1u;
         while (s_off[r] > pos0) r--;
         u32 nxt = s_off[r + 1];
         while (pos0 >= nxt) { r++; nxt = s_off[r + 1]; }
-        if (!(pos0 + 16u <= nxt && pos0 + 16u <= hi)) return false;     /* holds a read end, or the window's: pass 2 */
-        /* the whole group lies inside one read (eight or nine of ten groups of 150-base reads): five aligned words, four funnel
-         * shifts, one 128-bit store; the reverse strand reads the 16 bytes that end where the group's first position lies */
-        const u32 off = s_off[r];
+        u32 off = s_off[r];
         const u8* q = b.t[pe_files ? ((first_rel + r) & 1u) : 0u].text + s_q[r];
-        rev = il && ((first_rel + r) & 1u);
-        const u32 j = pos0 - off;
-        const uintptr_t ga = reinterpret_cast<uintptr_t>(rev ? q + ((nxt - off) - 16u - j) : q + j);
-        al = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
-        sh = (u32)(ga & 3u) * 8u;
-        return true;
-    };
-    auto finish = [&](u32 g, u32 a0, u32 a1, u32 a2, u32 a3, u32 a4, u32 sh, bool rev) {
-        const u32 w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh), w2 = __funnelshift_r(a2, a3, sh), w3 = __funnelshift_r(a3, a4, sh);
-        uint4 v;
-        if (rev) v = make_uint4(__byte_perm(w3, 0, 0x0123), __byte_perm(w2, 0, 0x0123), __byte_perm(w1, 0, 0x0123), __byte_perm(w0, 0, 0x0123));
-        else v = make_uint4(w0, w1, w2, w3);
-        *reinterpret_cast<uint4*>(smw + 4u * g) = v;
-    };
-    for (u32 g = tid; g < ngroups; g += 2u * nthreads) {
-        const u32 g2 = g + nthreads;
-        const u32* alA = nullptr; const u32* alB = nullptr; u32 shA = 0, shB = 0; bool revA = false, revB = false;
-        const bool okA = locate(g, alA, shA, revA);
-        const bool okB = g2 < ngroups && locate(g2, alB, shB, revB);
-        u32 a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0;
-        if (okA) { a0 = alA[0]; a1 = alA[1]; a2 = alA[2]; a3 = alA[3]; a4 = alA[4]; }
-        if (okB) { b0 = alB[0]; b1 = alB[1]; b2 = alB[2]; b3 = alB[3]; b4 = alB[4]; }
-        if (okA) finish(g, a0, a1, a2, a3, a4, shA, revA);
-        if (okB) finish(g2, b0, b1, b2, b3, b4, shB, revB);
+        bool rev = il && ((first_rel + r) & 1u);
+        if (pos0 + 16u <= nxt && pos0 + 16u <= hi) {
+            /* the whole group lies inside one read (eight or nine of ten groups of 150-base reads): five aligned words, four funnel
+             * shifts, one 128-bit store; the reverse strand reads the 16 bytes that end where the group's first position lies */
+            const u32 j = pos0 - off;
+            const uintptr_t ga = reinterpret_cast<uintptr_t>(rev ? q + ((nxt - off) - 16u - j) : q + j);
+            const u32* al = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
+            const u32 sh = (u32)(ga & 3u) * 8u;
+            const u32 a0 = al[0], a1 = al[1], a2 = al[2], a3 = al[3], a4 = al[4];
+            const u32 w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh), w2 = __funnelshift_r(a2, a3, sh), w3 = __funnelshift_r(a3, a4, sh);
+            uint4 v;
+            if (rev) v = make_uint4(__byte_perm(w3, 0, 0x0123), __byte_perm(w2, 0, 0x0123), __byte_perm(w1, 0, 0x0123), __byte_perm(w0, 0, 0x0123));
+            else v = make_uint4(w0, w1, w2, w3);
+            *reinterpret_cast<uint4*>(smw + ((pos0 - lo) >> 2)) = v;
+            continue;
+        }
     }
     /* pass 2: the groups that hold the end of a read (bytes of two or more reads), and the partial group at hi: a thread per read
      * end, byte by byte.  (Taking them inside pass 1, word by word, cost as much as the whole of pass 1: one lane in ten had such a
