@@ -55,7 +55,6 @@ struct rpq_ctx {
         seqoff, qualoff, n1off, n2off, soff, errbits, tmpx, tmpy, span_first[2], span_chunk[2], dir[2], slots[2], span_slot[2], span_read0[2], redo_list[2], dense_list, unclean, misc, out,
         d_in, d_desc, d_tmp[8], d_tmp2, out2, d_slabs, d_ckpt, d_dir, canon[2], nl2[2], canon_len, canon_pre;
     int streams5 = 1;                      /* RPQ_DEBUG_STREAMS5=0: every span k_streams4 cannot code goes to k_streams3 (A/B, at most 46 streams); =2: k_streams7 codes every quality span (test coverage) */
-    u32 meta_units = 0;                    /* RPQ_DEBUG_META_UNITS: units per CTA of k_meta3 (A/B) */
     bool no_streams4 = false;              /* RPQ_DEBUG_NO_STREAMS4=1: k_streams3 codes every span (test coverage, A/B) */
     bool dense_hint = false;               /* most quality spans of the last batch were dense: the next one goes to k_streams7 directly (k_streams4 would stage
                                               and count every span only to hand it over) */
@@ -189,7 +188,6 @@ extern "C" int rpq_create(int device, rpq_ctx** out) {
     { const char* e = getenv("RPQ_DEBUG_PAR_WALK_MIN"); c->par_walk_min = e ? strtoull(e, nullptr, 10) : (32ull << 20); }
     { const char* e = getenv("RPQ_DEBUG_STREAMS5"); if (e) c->streams5 = atoi(e); }
     { const char* e = getenv("RPQ_DEBUG_NO_STREAMS4"); c->no_streams4 = e && e[0] == '1'; }
-    { const char* e = getenv("RPQ_DEBUG_META_UNITS"); c->meta_units = e ? (u32)atoi(e) : 0u; }
     { const char* e = getenv("RPQ_DEBUG_FMT_READS"); c->fmt_reads = e ? (u32)atoi(e) : 0u; }
     { const char* e = getenv("RPQ_NO_PIPELINE"); c->no_pipeline = e && e[0] == '1'; }
     { const char* e = getenv("RPQ_D2H_DEPTH"); if (e) c->d2h_depth = (u32)atoi(e) > 8u ? 8u : (u32)atoi(e); }

@@ -466,3 +466,16 @@ def test_adversarial_quality_columns(codec):
 
 def test_control_bytes_in_names(codec):
     parity.check_control_bytes_in_names(codec)
+
+
+@pytest.mark.parametrize("reads", ["64", "32"])
+def test_small_formatter_tiles(monkeypatch, reads):
+    """RPQ_DEBUG_FMT_READS: formatter tiles of 64 / 32 reads instead of 128 (what reads of a few hundred bases get by themselves: a
+    tile's records must fit shared memory); more tiles per chunk, more steps decoded twice at tile seams"""
+    monkeypatch.setenv("RPQ_DEBUG_FMT_READS", reads)
+    cd = K.Codec(lib_path=EMU)
+    try:
+        for name in ("nova_pe_k1000", "nova_pe_k100_npos", "bgi_se_varlen_k100", "nova_pe_300bp_varlen_k100", "nova_se_late_quality"):
+            parity.check_decode_golden(cd, name)
+    finally:
+        cd.close()
