@@ -34,5 +34,17 @@ rb = K.compress(b1, k=100, codec=cd)
 assert K.decompress(rb, codec=cd) == bytes(b1)
 rb2 = K.compress(b1, k=100, codec=cd)                  # second batch: the dense hint sends every span to k_streams7
 assert rb2 == rb
+# runs that cross segments, spans and chunks, exception records, Q16 (k_streams4 -> k_streams7 hand-over, the walk back through the text)
+from tests import parity  # noqa: E402
+adv = parity.adversarial_quality_column(6000)
+ra = K.compress(adv, k=100, codec=cd)
+assert K.decompress(ra, codec=cd) == adv
+# N positions in few reads (sparse staging of the N-position coder, empty spans)
+lines = bytes(r1).split(b"\n")
+for k in range(1, len(lines) - 1, 4 * 37):
+    lines[k] = b"N" + lines[k][1:-1] + b"N"
+nn = b"\n".join(lines)
+rn = K.compress(nn, k=100, codec=cd)
+assert K.decompress(rn, codec=cd) == nn
 cd.close()
 print("sanitize probe ok")
