@@ -189,3 +189,24 @@ def test_adversarial_quality_columns(codec):
 
 def test_control_bytes_in_names(codec):
     parity.check_control_bytes_in_names(codec)
+
+
+def test_read_longer_than_the_header_can_store(codec):
+    """the header's read length width comes from the first chunk (src/rfqcodec.cpp:48-53): a later read of more than 255 bases is refused"""
+    short = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, b"ACGT" * 25, b"F" * 100) for i in range(1200))
+    long_ = b"@long\n%s\n+\n%s\n" % (b"ACGT" * 150, b"F" * 600)
+    with pytest.raises(K.RepaqError) as e:
+        K.compress(short + long_, k=100, codec=codec)
+    assert "does not fit the header" in str(e.value)
+    parity.check_against_oracle(codec, long_ + short, k=100)
+
+
+@pytest.mark.parametrize("reads", ["64", "32"])
+def test_small_formatter_tiles(monkeypatch, reads):
+    monkeypatch.setenv("RPQ_DEBUG_FMT_READS", reads)
+    cd = K.Codec(device=0)
+    try:
+        for name in ("nova_pe_k1000", "nova_pe_k100_npos", "bgi_se_varlen_k100", "nova_pe_300bp_varlen_k100"):
+            parity.check_decode_golden(cd, name)
+    finally:
+        cd.close()
