@@ -122,12 +122,25 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams4(EncBatchDev b, HeaderDe
     if (lane == 0) s_warp[warp] = wtot;
     bool redo = (nm & eq) == ~0ull;                         /* a run covers the whole segment: long-run machinery of k_streams3 */
     u32 has_cross = 0;
-    if (tid == 0 && (nm & eq & 1ull)) {
-        const u8 v0 = sm[lo - sm_lo];
-        u32 p0 = lo;
-        while (p0 > sm_lo && sm[p0 - 1 - sm_lo] == v0) p0--;
-        if (p0 == sm_lo && sm_lo > 0) redo = true;           /* starts before the halo */
-        s_cross_p = p0; has_cross = 1;
+    if (warp == 0) {
+        /* the run that crosses into the span: its start, 32 positions of the halo per step */
+        const bool cross = __shfl_sync(0xffffffffu, (u32)(nm & eq & 1ull), 0) != 0;
+        if (cross) {
+            const u8 v0 = sm[lo - sm_lo];
+            u32 p0 = lo;
+            for (;;) {
+                const bool ok = p0 >= sm_lo + 1u + (u32)lane;
+                const bool same = ok && sm[p0 - 1u - (u32)lane - sm_lo] == v0;
+                const u32 m = __ballot_sync(0xffffffffu, same);
+                const u32 take = m == 0xffffffffu ? 32u : (u32)(__ffs((int)~m) - 1);
+                p0 -= take;
+                if (take < 32u) break;
+            }
+            if (tid == 0) {
+                if (p0 == sm_lo && sm_lo > 0) redo = true;   /* starts before the halo */
+                s_cross_p = p0; has_cross = 1;
+            }
+        }
     }
     if (redo) atomicOr(&s_redo, 1u);
     if (tid == 0) s_tmp = has_cross;
@@ -191,11 +204,24 @@ __global__ void __launch_bounds__(S2_THREADS) k_streams4(EncBatchDev b, HeaderDe
         if (valid && (peers >> lane) <= 1u) t_last[(k >> 5) * nstreams + cls] = (unsigned short)k;       /* highest lane of its group */
     }
     __syncthreads();
-    /* ---- P1: last run of the stream BEFORE each block */
-    for (u32 st = tid; st < nstreams; st += S2_THREADS) {
-        u32 running = RL_NONE;
-        for (u32 j = 0; j < nblocks; j++) { const u32 t = t_last[j * nstreams + st]; t_last[j * nstreams + st] = (unsigned short)running; if (t != RL_NONE) running = t; }
-        s_total[st] = running;                               /* the stream's last run of the span (for lastpos) */
+    /* ---- P1: last run of the stream BEFORE each block (a warp per stream, a lane per block: "latest entry that is not NONE",
+     * exclusive; one thread per stream walking the blocks was 48 dependent shared-memory round trips with the CTA waiting) */
+    for (u32 st = warp; st < nstreams; st += S2_THREADS / 32) {
+        u32 carry = RL_NONE;
+        for (u32 j0 = 0; j0 < nblocks; j0 += 32) {
+            const u32 j = j0 + (u32)lane;
+            const u32 t = j < nblocks ? (u32)t_last[j * nstreams + st] : RL_NONE;
+            u32 incl = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const u32 u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d && incl == RL_NONE) incl = u; }
+            u32 excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = RL_NONE;
+            if (excl == RL_NONE) excl = carry;
+            if (j < nblocks) t_last[j * nstreams + st] = (unsigned short)excl;
+            const u32 last = __shfl_sync(0xffffffffu, incl, 31);
+            if (last != RL_NONE) carry = last;
+        }
+        if (lane == 0) s_total[st] = carry;                  /* the stream's last run of the span (for lastpos) */
     }
     __syncthreads();
     /* ---- B */

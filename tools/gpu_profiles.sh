@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2 profiles: the ncu launch list of one full-size step with DRAM byte counters (-> profiles/r02_traffic.json, kernel shares),
+# profiles of a build: the ncu launch list of one full-size step with DRAM byte counters (-> profiles/r02_traffic.json, kernel shares),
 # `--set full` captures with source of the top kernels (NovaSeq-shape bench step at 0.43 GB; BGI-shape probe), CSV summaries only
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2: selected GPU parity tests, both shapes, the device-resident bench line (and optional ncu captures: NCU_KERNELS="k_a k_b")
+# quick look at a build: selected GPU parity tests, both shapes, the device-resident bench line (and optional ncu captures: NCU_KERNELS="k_a k_b")
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 WANT=$(cat $(ls repaq_b200/csrc/*.cu repaq_b200/csrc/*.cuh repaq_b200/csrc/*.h repaq_b200/csrc/*.inc repaq_b200/csrc/*.cpp include/repaq_b200.h | sort) | sha1sum | cut -c1-40)

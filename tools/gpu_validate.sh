@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2: smoke, all GPU tests, the full default bench line
+# validation of a build on a B200 box: smoke, all GPU tests, the full default bench line (logs -> gpurun_out/)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 WANT=$(cat $(ls repaq_b200/csrc/*.cu repaq_b200/csrc/*.cuh repaq_b200/csrc/*.h repaq_b200/csrc/*.inc repaq_b200/csrc/*.cpp include/repaq_b200.h | sort) | sha1sum | cut -c1-40)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """DRAM bytes per launch of every kernel from an ncu launch list taken with
     --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv --log-file <csv>
-(tools/gpu_prof_all.sh).  Writes the JSON that bench.py reads for `roofline.traffic`.
+(tools/gpu_profiles.sh).  Writes the JSON that bench.py reads for `roofline.traffic`.
 
 usage: ncu_traffic.py launches.csv out.json pairs_per_gpu
 """
