@@ -895,12 +895,22 @@ __global__ void __launch_bounds__(256) k_gather(EncBatchDev b, StreamJob job, co
     u8* col = out + ck.out_offset + (is_npos ? ck.off_npos : ck.off_qual);
     const u8* slot = job.slots + job.span_slot[span];
     const u32 ns = job.nstreams;
-    for (u32 st = 0; st < ns; st++) {
-        const SpanDir d = job.dir[(size_t)span * ns + st];
-        if (threadIdx.x < d.first_len) col[d.dst + threadIdx.x] = (u8)(d.first_tok >> (8 * threadIdx.x));
+    /* the span's directory first (all entries in flight at once), then a warp per stream: forty streams of a dense column were
+     * forty dependent directory loads, one after the other, with a few hundred bytes of copying between them */
+    __shared__ SpanDir s_dir[MAX_BINS + 2];
+    {
+        const uint4* g = reinterpret_cast<const uint4*>(job.dir + (size_t)span * ns);
+        uint4* sd = reinterpret_cast<uint4*>(s_dir);
+        for (u32 k = threadIdx.x; k < 2u * ns; k += blockDim.x) sd[k] = g[k];
+    }
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (u32 st = warp; st < ns; st += nwarps) {
+        const SpanDir d = s_dir[st];
+        if (lane < d.first_len) col[d.dst + lane] = (u8)(d.first_tok >> (8 * lane));
         u8* dst = col + d.dst + d.first_len;
         const u8* src = slot + d.slot_off;
-        for (u32 k = threadIdx.x; k < d.bytes; k += blockDim.x) dst[k] = src[k];
+        for (u32 k = lane; k < d.bytes; k += 32u) dst[k] = src[k];
     }
     /* stream length table (quality only): written by the chunk's first span */
     if (!is_npos && span == job.span_first[c]) {
