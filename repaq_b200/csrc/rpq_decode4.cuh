@@ -403,8 +403,11 @@ __global__ void __launch_bounds__(PL_THREADS) k_dec_planes(DecBatchDev b, Header
  */
 __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h, Fmt4Cfg cfg, u32 chunk_first, const u8* __restrict__ planes) {
     RPQ_DYN_SMEM(dyn);
-    __shared__ u64 s_start[2], s_end[2];
     __shared__ u32 s_lut_fwd[256], s_lut_rc[256];
+#ifndef RPQ_EMU
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const u32 mbar = (u32)__cvta_generic_to_shared(&s_mbar);
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 G = cfg.reads_per_cta;
     const u32 c = chunk_first + blockIdx.y;
@@ -441,8 +444,13 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
         }
         s_lut_fwd[v] = f; s_lut_rc[v] = r;
     }
-    if (tid < 2) { s_start[tid] = ~0ull; s_end[tid] = 0; }
-    __syncthreads();
+#ifndef RPQ_EMU
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#endif
+    __syncthreads();                                           /* the tables and the barrier object are there for everybody: the only CTA-wide wait before the records are done */
 
     const bool active = rt < (int)n_here;
     const u32 i = i_first + rt;
@@ -471,12 +479,17 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
             pre_so = b.seqoff[i];
             if (il && (h.flags & RPQ_ENCODE_PE_BY_OVERLAP) && (r & 1u)) { pre_ov = (int)(signed char)in[ck.off_ov + (r >> 1)] - (int)h.overlap_shift; pre_prev_rl = b.rlen[i - 1]; }
         }
-        if (half == 0) {
-            if ((u32)rt < nstreams) s_start[stream] = oabs;
-            if ((u32)rt + nstreams >= n_here) s_end[stream] = oabs + olen;
-        }
     }
-    __syncthreads();
+    /* where the tile's records start and end in each output stream: from the tile's first and last reads of the stream (the same
+     * few table entries for every thread: no exchange through shared memory, no barrier behind the table loads) */
+    u64 t_start[2] = {~0ull, ~0ull}, t_end[2] = {0, 0};
+    for (u32 sidx = 0; sidx < nstreams; sidx++) {
+        if (sidx >= n_here) continue;                              /* a tile of one read has one stream */
+        const u32 rt_first = sidx;                                 /* r0 is even: the first read of stream s is read s of the tile */
+        const u32 rt_last = nstreams == 1u ? n_here - 1u : (((n_here - 1u) & 1u) == sidx ? n_here - 1u : n_here - 2u);
+        t_start[sidx] = ck.out_off[sidx] + b.outoff[i_first + rt_first];
+        t_end[sidx] = ck.out_off[sidx] + b.outoff[i_first + rt_last] + b.olen[i_first + rt_last];
+    }
 
     /* ---- the tile's slot and its piece of the 2-bit column: two TMA bulk copies counted on one mbarrier.  The piece: the bytes
      * that hold the compact bases [C0, C1) of the tile's reads (an overlapped mate reads its partner's bases: pairs never straddle
@@ -506,12 +519,8 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
     __syncthreads();
     auto plane_ready = [&]() {};
 #else
-    __shared__ __align__(8) unsigned long long s_mbar;
-    const u32 mbar = (u32)__cvta_generic_to_shared(&s_mbar);
     if (tid == 0) {
         const u32 nbytes = cfg.nbits_words ? slot_n : plane_bytes;
-        asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(mbar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(mbar), "r"(nbytes + sq_n) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"((u32)__cvta_generic_to_shared(s_plane)), "l"(slot), "r"(nbytes), "r"(mbar) : "memory");
@@ -519,7 +528,6 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"((u32)__cvta_generic_to_shared(s_seq)), "l"(sq_src), "r"(sq_n), "r"(mbar) : "memory");
     }
-    __syncthreads();                                           /* the barrier object is initialised for everybody */
     auto plane_ready = [&]() {
         u32 done = 0;
         while (!done)
@@ -532,7 +540,7 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
         const bool il = (fl & RPQ_PE_INTERLEAVED) != 0;
         const bool odd = (r & 1u) != 0;
         const u32 xy = il ? r >> 1 : r;
-        o = s_out[stream] + (u32)(oabs - (s_start[stream] & ~15ull));
+        o = s_out[stream] + (u32)(oabs - ((stream ? t_start[1] : t_start[0]) & ~15ull));
         /* ---- strand length first: it fixes where every part of the record lies */
         ls = pre_ls;
         name_end = olen - (2u * rl + ls + 3u);          /* bytes of the name line including its line break */
@@ -711,7 +719,7 @@ __global__ void __launch_bounds__(256) k_dec_format4(DecBatchDev b, HeaderDev h,
 #endif
     __syncthreads();
     for (u32 s = 0; s < nstreams; s++) {
-        const u64 a = s_start[s], e = s_end[s];
+        const u64 a = s ? t_start[1] : t_start[0], e = s ? t_end[1] : t_end[0];
         if (a == ~0ull || e <= a) continue;
         const u64 base = a & ~15ull;
         u8* g = b.out[s];
