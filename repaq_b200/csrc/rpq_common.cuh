@@ -136,6 +136,7 @@ struct EncBatchDev {
     u32* n1off; u32* n2off; u32* soff;
     ChunkDev* chunks;
     u32* err;             /* error bits */
+    u32 reach[2];         /* final batches: how far the reference's reader has read in each file when its loop ends (k_cut_ends; Q13) */
     u8* unclean;          /* [n_reads] 1: the read holds a character that is not a plain base (k_meta3); nullptr: not known */
     u32 uniform_reads_per_chunk;   /* != 0: chunk c = reads [c*u, (c+1)*u) */
 };

@@ -754,10 +754,15 @@ __global__ void __launch_bounds__(128) k_head(EncBatchDev b, HeaderDev h, u8* ou
     if (lane == 0) {
         /* Q13: NO_LINE_BREAK bits are OR-ed in after mSize was computed */
         u32 flags = ck.flags;
-        if ((u64)ck.r1_end >= params.nobreak_from[0]) flags |= RPQ_NO_LINE_BREAK_AT_END;
-        if (b.is_pe) { if ((u64)(b.two_files ? ck.r2_end : ck.r1_end) >= params.nobreak_from[b.two_files ? 1 : 0]) flags |= RPQ_NO_LINE_BREAK_AT_END_R2; }
-        /* tail_flags belong to the post-loop flush only (src/repaq.cpp:594-616,710-754): a last chunk that did not reach chunk_bases */
-        if (params.final && c == b.n_chunks - 1 && ck.total_len < params.chunk_bases) flags |= params.tail_flags;
+        /* the post-loop flush (src/repaq.cpp:594-616,710-754): a last chunk that did not reach chunk_bases.  The reader has by then
+         * tried the record after it: what counts is how far it got (k_cut_ends) */
+        const bool flush = params.final && c == b.n_chunks - 1 && ck.total_len < params.chunk_bases;
+        u64 e1 = ck.r1_end, e2 = b.two_files ? ck.r2_end : ck.r1_end;
+        if (flush) { if (b.reach[0] > e1) e1 = b.reach[0]; const u32 r2 = b.two_files ? b.reach[1] : b.reach[0]; if (r2 > e2) e2 = r2; }
+        if (e1 >= params.nobreak_from[0]) flags |= RPQ_NO_LINE_BREAK_AT_END;
+        if (b.is_pe && e2 >= params.nobreak_from[b.two_files ? 1 : 0]) flags |= RPQ_NO_LINE_BREAK_AT_END_R2;
+        /* tail_flags belong to the post-loop flush only */
+        if (flush) flags |= params.tail_flags;
         ck.flags = flags;
         put_u32le(o, ck.msize); put_u32le(o + 4, ck.count); put_u16le(o + 8, (u16)flags);
         put_u32le(o + 10, ck.seq_size); put_u32le(o + 14, ck.qual_size);

@@ -303,6 +303,7 @@ struct UnitStats {
     u32 n_chunks;         /* written by k_cut */
     u32 units_in_chunks;  /* units covered by the emitted chunks */
     u32 end[2];           /* written by k_cut_ends: offset of the line break that ends the last covered record, per file */
+    u32 reach[2];         /* written by k_cut_ends (final batches): how far the reference's reader has read in each file when its loop ends */
 };
 
 __global__ void k_unit_lengths(EncBatchDev b, u32 n_units, u32* __restrict__ rlen, u32* __restrict__ unit_bases, UnitStats* st) {
@@ -420,9 +421,38 @@ __global__ void k_cut(const u64* __restrict__ prefix, u32 n_units, u32 chunk_bas
 }
 
 /* where the text covered by the chunks ends (one launch behind k_cut, so that the host reads everything back at once) */
-__global__ void k_cut_ends(UnitStats* st, EncBatchDev b, int two, int pe) {
+/*
+ * Where the reference's reader stands when its loop ends (final batches only).  After the last good record it tries one more
+ * (FastqReader::read, src/fastqreader.cpp:166-196): name, sequence and strand line are read whatever they hold, the quality line
+ * only if none of the three is empty; a line that is not there is the end of the file.  What matters is the first break character
+ * of the last line it read: the buffer holding it has been loaded, and loading the file's last, short buffer raises
+ * NO_LINE_BREAK_AT_END when the file does not end in a line feed (:31-46) - which the post-loop flush then writes into its
+ * chunk (Q13).  An input that ends at an empty line, at a ragged record or because the mate file is shorter can so flag a chunk
+ * whose own last record ends before that buffer.
+ */
+__device__ inline u32 reader_attempt(const TextDev& t, u32 rec, u32 caller_len, bool& complete) {
+    const u32 L = 4u * rec;
+    complete = false;
+    if (L + 2u >= t.n_lines) return caller_len;
+    bool empty3 = false;
+    for (u32 k = 0; k < 3u; k++) if (line_end(t, L + k) == line_start(t, L + k)) empty3 = true;
+    if (empty3) return caller_break_first(t, L + 2u);
+    if (L + 3u >= t.n_lines) return caller_len;
+    complete = line_end(t, L + 3u) != line_start(t, L + 3u);
+    return caller_break_first(t, L + 3u);
+}
+
+__global__ void k_cut_ends(UnitStats* st, EncBatchDev b, int two, int pe, u32 n_units, int final, u32 len0, u32 len1) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     st->end[0] = st->end[1] = 0;
+    st->reach[0] = st->reach[1] = 0;
+    if (final) {
+        /* unit n_units is the one the reader fails on (an empty line, a ragged or missing record) */
+        bool ok;
+        if (two) { st->reach[0] = reader_attempt(b.t[0], n_units, len0, ok); st->reach[1] = reader_attempt(b.t[1], n_units, len1, ok); }
+        else if (pe) { u32 r = reader_attempt(b.t[0], 2u * n_units, len0, ok); if (ok) r = reader_attempt(b.t[0], 2u * n_units + 1u, len0, ok); st->reach[0] = r; }
+        else st->reach[0] = reader_attempt(b.t[0], n_units, len0, ok);
+    }
     if (st->units_in_chunks == 0) return;
     const u32 last_unit = st->units_in_chunks - 1;
     const u32 rec0 = two ? last_unit : (pe ? 2 * last_unit + 1 : last_unit);

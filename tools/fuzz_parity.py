@@ -68,6 +68,23 @@ def one(cd, seed):
         b2 = b2.replace(b"\n", b"\r\n") if b2 is not None else None
     if rnd.random() < 0.3 and b1.endswith(b"\n"):                         # no line break at the end of the file
         b1 = b1[:-2] if crlf else b1[:-1]
+    nl = b"\r\n" if crlf else b"\n"
+    tail = rnd.randrange(12)                                               # how the input ends (Q13: how far the reader gets before it stops)
+    if tail == 0:
+        b1 += nl * rnd.randint(1, 3)                                       # blank lines at the end
+    elif tail == 1:
+        b1 += (b"" if b1.endswith(b"\n") else nl) + b"@ragged" + nl + b"ACGT"      # a ragged last record, no break
+    elif tail == 2:
+        b1 += (b"" if b1.endswith(b"\n") else nl) + b"@ragged" + nl + b"ACGT" + nl + b"+" + nl
+    elif tail == 3 and b2 is not None:
+        cut_at = b2.rfind(b"@", 0, len(b2) - 1)                            # the mate file one record shorter
+        if cut_at > 0:
+            b2 = b2[:cut_at]
+    elif tail == 4:
+        cut_at = len(b1) * rnd.randint(40, 95) // 100                       # an empty line in the middle: the input ends there
+        p = b1.find(nl, cut_at)
+        if p > 0:
+            b1 = b1[:p] + nl + b1[p:]
     # (the mutated qualities may give an N base another quality than the N quality, or a base the N quality: the reference's own round
     # trip loses those, so only the reference's bytes are asked for, not the input back)
     parity.check_against_oracle(cd, b1, b2, k=k, interleaved=interleaved, roundtrip=False)
