@@ -88,6 +88,25 @@ def one(cd, seed):
     # (the mutated qualities may give an N base another quality than the N quality, or a base the N quality: the reference's own round
     # trip loses those, so only the reference's bytes are asked for, not the input back)
     parity.check_against_oracle(cd, b1, b2, k=k, interleaved=interleaved, roundtrip=False)
+    if not interleaved and rnd.random() < 0.5:
+        # compare mode (Repaq::compare / comparePE): the .rfq against the FASTQ it came from, or against one with a byte changed,
+        # a record dropped or a record added - the report must be the reference's, word for word
+        rfq = O.compress(b1, b2, chunk_bases=max(100, k) * 1000)
+        c1, c2 = b1, b2
+        how = rnd.randrange(4)
+        if how == 1 and len(c1) > 100:
+            p = rnd.randrange(len(c1))
+            if c1[p] not in b"\r\n@+":
+                c1 = c1[:p] + bytes([c1[p] ^ 1 if (c1[p] ^ 1) not in b"\r\n" else c1[p]]) + c1[p + 1:]
+        elif how == 2:
+            p = c1.rfind(b"@", 0, len(c1) - 1)
+            if p > 0:
+                c1 = c1[:p]
+        elif how == 3 and c2 is None:
+            c1 = c1 + (b"" if c1.endswith(b"\n") else b"\n") + b"@extra\nACGT\n+\nFFFF\n"
+        if len(rfq):
+            got, exp = K.compare(rfq, c1, c2, codec=cd), O.compare(rfq, c1, c2)
+            assert got == exp, "compare report differs:\n%s\n%s" % (got, exp)
     return len(b1) + (len(b2) if b2 else 0)
 
 
