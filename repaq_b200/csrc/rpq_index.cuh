@@ -294,7 +294,7 @@ __global__ void k_canon_copy(const u8* __restrict__ text, const u32* __restrict_
 /* per-unit (read, or pair) statistics */
 struct UnitStats {
     u32 first_empty;      /* first unit with an empty line: input ends there (src/fastqreader.cpp:180-181,190-191) */
-    u32 first_qual_len;   /* first unit whose quality length != sequence length */
+    u32 first_qual_len;   /* first unit whose quality line is shorter than its sequence */
     u32 first_name_len;   /* first unit with a name/strand line > 255 bytes */
     u32 first_read_len;   /* first unit with a read > 65535 bases */
     u32 min_bases, max_bases;
@@ -325,7 +325,7 @@ __global__ void k_unit_lengths(EncBatchDev b, u32 n_units, u32* __restrict__ rle
             const u32 brk = 1u + t.crlf;
             const u32 ln0 = lc.y - brk - lc.x, ln1 = lc.z - brk - lc.y, ln2 = lc.w - brk - lc.z, ln3 = e3 - lc.w;
             if (!ln0 || !ln1 || !ln2 || !ln3) empty = true;
-            if (ln1 != ln3) badq = true;
+            if (ln3 < ln1) badq = true;                       /* a longer quality line is cut to the sequence's length, as the reference does (src/rfqcodec.cpp:332-407 copies seq.length() bytes); a shorter one makes it read past its string */
             if (ln0 > 255 || ln2 > 255) badn = true;
             if (ln1 > 65535) badl = true;
             rlen[i] = ln1;

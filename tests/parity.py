@@ -164,3 +164,25 @@ def check_control_bytes_in_names(codec):
         out.append(b"\n".join(lines))
     check_against_oracle(codec, out[0], out[1], k=100)
     check_against_oracle(codec, out[0].replace(b"\n", b"\r\n"), None, k=100, roundtrip=False)
+
+
+def check_quality_longer_than_sequence(codec):
+    """a quality line longer than its sequence: the reference copies seq.length() quality bytes and drops the rest (src/rfqcodec.cpp:
+    332-407) - for the reverse strand of an interleaved pair the first seq.length() bytes, reversed; a shorter one makes it read past
+    its string and is refused here"""
+    import pytest
+    from tools import fqgen
+    r1, r2 = fqgen.generate(2400, seed=17, paired=True)
+    out = []
+    for r in (r1, r2):
+        lines = bytes(r).split(b"\n")
+        for k in range(3, len(lines) - 1, 4 * 7):
+            lines[k] = lines[k] + lines[k][:1 + (k // 4) % 3]
+        out.append(b"\n".join(lines))
+    check_against_oracle(codec, out[0], out[1], k=100, roundtrip=False)
+    check_against_oracle(codec, out[0], None, k=100, roundtrip=False)
+    lines = bytes(r1).split(b"\n")
+    lines[4 * 900 + 3] = lines[4 * 900 + 3][:-1]
+    with pytest.raises(K.RepaqError) as e:
+        K.compress(b"\n".join(lines), k=100, codec=codec)
+    assert "quality line shorter than the sequence in record 900" in str(e.value)

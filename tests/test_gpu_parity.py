@@ -210,3 +210,13 @@ def test_small_formatter_tiles(monkeypatch, reads):
             parity.check_decode_golden(cd, name)
     finally:
         cd.close()
+
+
+def test_quality_longer_than_sequence(codec):
+    parity.check_quality_longer_than_sequence(codec)
+
+
+def test_crlf_on_reader_buffer_edges(codec):
+    """the reference's reader at its 1 MiB refills, with and without a final line break (Q13 on the flush chunk): the CPU test's cases"""
+    from tests.test_emu_parity import test_crlf_on_reader_buffer_edges as cases
+    cases(codec)

@@ -26,10 +26,11 @@ def mutate_quality(buf, rnd, first_chunk_reads):
     nrec = (len(lines) - 1) // 4
     for _ in range(rnd.randint(0, 40)):
         rec = rnd.randrange(nrec)
-        q = bytearray(lines[4 * rec + 3])
+        cr = lines[4 * rec + 3].endswith(b"\r")                          # a text with CRLF line ends: the line's own bytes only
+        q = bytearray(lines[4 * rec + 3][:-1] if cr else lines[4 * rec + 3])
         if not q:
             continue
-        kind = rnd.randrange(5)
+        kind = rnd.randrange(6)
         a = rnd.randrange(len(q)); z = rnd.randint(a, len(q))
         if kind == 0:
             q[a:z] = bytes([q[a]]) * (z - a)
@@ -39,9 +40,11 @@ def mutate_quality(buf, rnd, first_chunk_reads):
             q[:] = bytes([q[0]]) * len(q)
         elif kind == 3:
             q[0:2] = bytes([q[0]]) * min(2, len(q))
+        elif kind == 5:
+            q += bytes([q[-1]]) * rnd.randint(1, 3)                         # a quality line longer than its sequence: cut by the reference
         else:
             q[-3:] = bytes([q[-1]]) * min(3, len(q))
-        lines[4 * rec + 3] = bytes(q)
+        lines[4 * rec + 3] = bytes(q) + (b"\r" if cr else b"")
     return b"\n".join(lines)
 
 
