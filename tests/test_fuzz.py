@@ -14,6 +14,9 @@ fuzz = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(fuzz)
 
 PINNED = []
+_spec2 = importlib.util.spec_from_file_location("fuzz_names", os.path.join(ROOT, "tools", "fuzz_names.py"))
+fuzz_names = importlib.util.module_from_spec(_spec2)
+_spec2.loader.exec_module(fuzz_names)
 
 
 def test_fuzz_emulated():
@@ -21,6 +24,8 @@ def test_fuzz_emulated():
     try:
         for seed in PINNED + list(range(300000, 300040)):
             fuzz.one(cd, seed)
+        for seed in range(310000, 310060):
+            fuzz_names.one(cd, seed)                     # names, other bases, overlapping mates
     finally:
         cd.close()
 
@@ -31,5 +36,7 @@ def test_fuzz_gpu():
     try:
         for seed in PINNED + list(range(400000, 400400)):
             fuzz.one(cd, seed)
+        for seed in range(410000, 410400):
+            fuzz_names.one(cd, seed)
     finally:
         cd.close()
