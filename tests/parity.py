@@ -186,3 +186,28 @@ def check_quality_longer_than_sequence(codec):
     with pytest.raises(K.RepaqError) as e:
         K.compress(b"\n".join(lines), k=100, codec=codec)
     assert "quality line shorter than the sequence in record 900" in str(e.value)
+
+
+def medium_density_quality(n_reads=8000, rl=150, seed=21, p_run=0.14):
+    """single-end FASTQ whose quality column holds 1537..3072 runs per 16384 positions: more than k_streams4's list, not more than
+    k_streams4w's (eight-level binned qualities look like this)"""
+    import numpy as np
+    rnd = np.random.RandomState(seed)
+    total = n_reads * rl
+    col = np.full(total, ord("F"), dtype=np.uint8)
+    starts = np.flatnonzero(rnd.random_sample(total) < p_run)
+    vals = np.frombuffer(b",:#5", dtype=np.uint8)[rnd.randint(0, 4, starts.size)]
+    lens = rnd.randint(1, 4, starts.size)
+    for k in range(3):
+        sel = lens > k
+        idx = np.minimum(starts[sel] + k, total - 1)
+        col[idx] = vals[sel]
+    bases = np.frombuffer(b"ACGT", dtype=np.uint8)[rnd.randint(0, 4, total)]
+    return b"".join(b"@r%d\n" % i + bases[i * rl:(i + 1) * rl].tobytes() + b"\n+\n" + col[i * rl:(i + 1) * rl].tobytes() + b"\n" for i in range(n_reads))
+
+
+def check_medium_density(codec):
+    for p_run, seed in ((0.14, 21), (0.10, 22), (0.21, 23), (0.30, 24)):    # around both list sizes: spans on either side of each
+        check_against_oracle(codec, medium_density_quality(seed=seed, p_run=p_run), k=1000)
+    st = codec.stats()
+    return st

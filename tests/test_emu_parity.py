@@ -491,3 +491,8 @@ def test_small_formatter_tiles(monkeypatch, reads):
 
 def test_quality_longer_than_sequence(codec):
     parity.check_quality_longer_than_sequence(codec)
+
+
+def test_medium_density_quality_columns(codec):
+    """spans with more runs than k_streams4's list holds but not more than twice as many: k_streams4w"""
+    parity.check_medium_density(codec)

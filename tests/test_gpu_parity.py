@@ -220,3 +220,7 @@ def test_crlf_on_reader_buffer_edges(codec):
     """the reference's reader at its 1 MiB refills, with and without a final line break (Q13 on the flush chunk): the CPU test's cases"""
     from tests.test_emu_parity import test_crlf_on_reader_buffer_edges as cases
     cases(codec)
+
+
+def test_medium_density_quality_columns(codec):
+    parity.check_medium_density(codec)
