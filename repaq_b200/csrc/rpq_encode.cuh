@@ -504,8 +504,6 @@ struct StreamJob {                   /* one per kind (quality / N positions) */
     u32* dense_count;                /* k_streams4: quality spans with more runs than its list holds, left to k_streams5 ... */
     u32* dense_list;                 /* ... and which (NULL: they go to the redo list) */
     u32* list_count;                 /* entries of dense_list */
-    u32* wide_list;                  /* k_streams4: spans with more runs than its list but not more than k_streams4w's ... */
-    u32* wide_count;                 /* ... and how many */
     u32 list_takes_redo;             /* the coder behind dense_list also takes the spans with long runs (k_streams7) */
     u32 nstreams;                    /* nb + 1 (exceptions) for quality; 1 for N positions */
     u32 mode;                        /* 0 quality, 1 N positions */

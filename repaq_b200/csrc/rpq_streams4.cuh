@@ -23,22 +23,20 @@
 
 namespace rpq {
 
-constexpr int RL_CAP = 1536;                 /* runs per span in the list (k_streams4) */
-constexpr int RL_CAP_WIDE = 3072;            /* ... in the list of k_streams4w, which takes the spans with more */
+constexpr int RL_CAP = 1536;                 /* runs per span in the list */
+constexpr int RL_BLOCKS = RL_CAP / 32;
 constexpr u32 RL_NONE = 0xFFFFu;
 
 /* dynamic shared memory of k_streams4 after the staged bytes (the staging tables of stage_quality_flat alias the run arrays) */
-__host__ __device__ inline size_t streams4_smem(u32 nstreams, u32 cap = RL_CAP) {
-    size_t run_arrays = (size_t)cap * (4 * sizeof(unsigned short) + 1);
+__host__ __device__ inline size_t streams4_smem(u32 nstreams) {
+    size_t run_arrays = (size_t)RL_CAP * (4 * sizeof(unsigned short) + 1);
     const size_t stage_tables = 2 * (SQ_CAP + 1) * sizeof(u32);
     if (run_arrays < stage_tables) run_arrays = stage_tables;
     run_arrays = (run_arrays + 15) & ~(size_t)15;
-    return (size_t)ST_SPAN + 2 * ST_HALO + 16 + run_arrays + 2 * (size_t)(cap / 32u) * nstreams * sizeof(unsigned short);
+    return (size_t)ST_SPAN + 2 * ST_HALO + 16 + run_arrays + 2 * (size_t)RL_BLOCKS * nstreams * sizeof(unsigned short);
 }
 
-template <int CAP>
-__device__ __forceinline__ void streams4_body(const EncBatchDev& b, const HeaderDev& h, const StreamJob& job, const u32* __restrict__ span_chunk, const u32* __restrict__ list) {
-    constexpr int RL_BLOCKS = CAP / 32;
+__global__ void __launch_bounds__(S2_THREADS) k_streams4(EncBatchDev b, HeaderDev h, StreamJob job, const u32* __restrict__ span_chunk) {
     RPQ_DYN_SMEM(dyn);
     __shared__ u8 s_lut[256];
     __shared__ u32 s_total[MAX_BINS + 2];
@@ -48,7 +46,7 @@ __device__ __forceinline__ void streams4_body(const EncBatchDev& b, const Header
     __shared__ u64 s_slot;
     __shared__ u64 s_eq[S2_THREADS];                    /* every thread's "equals the previous position" mask: run ends without byte loops */
     __shared__ u32 s_tmp, s_redo, s_cross_p;
-    const u32 span = list ? list[blockIdx.x] : blockIdx.x;
+    const u32 span = blockIdx.x;
     if (span >= *job.n_spans) return;
     const u32 c = span_chunk[span];
     const ChunkDev& ck = b.chunks[c];
@@ -61,12 +59,12 @@ __device__ __forceinline__ void streams4_body(const EncBatchDev& b, const Header
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     u8* sm = dyn;
     u8* arrays = dyn + ST_SPAN + 2 * ST_HALO + 16;
-    unsigned short* rs = reinterpret_cast<unsigned short*>(arrays);      /* [CAP] run start, span relative */
-    unsigned short* rend = rs + CAP;                                   /* [CAP] run end (exclusive, clipped to hi + 32), span relative */
-    unsigned short* roff = rend + CAP;                                 /* [CAP] byte offset inside (block, stream) */
-    unsigned short* rdm = roff + CAP;                                  /* [CAP] distance - 1 of the run's distance token, RL_NONE: none / deferred */
-    u8* rcls = reinterpret_cast<u8*>(rdm + CAP);                       /* [CAP] stream index */
-    size_t arr_bytes = (size_t)CAP * (4 * sizeof(unsigned short) + 1);
+    unsigned short* rs = reinterpret_cast<unsigned short*>(arrays);      /* [RL_CAP] run start, span relative */
+    unsigned short* rend = rs + RL_CAP;                                   /* [RL_CAP] run end (exclusive, clipped to hi + 32), span relative */
+    unsigned short* roff = rend + RL_CAP;                                 /* [RL_CAP] byte offset inside (block, stream) */
+    unsigned short* rdm = roff + RL_CAP;                                  /* [RL_CAP] distance - 1 of the run's distance token, RL_NONE: none / deferred */
+    u8* rcls = reinterpret_cast<u8*>(rdm + RL_CAP);                       /* [RL_CAP] stream index */
+    size_t arr_bytes = (size_t)RL_CAP * (4 * sizeof(unsigned short) + 1);
     { const size_t st = 2 * (SQ_CAP + 1) * sizeof(u32); if (arr_bytes < st) arr_bytes = st; arr_bytes = (arr_bytes + 15) & ~(size_t)15; }
     unsigned short* t_last = reinterpret_cast<unsigned short*>(arrays + arr_bytes);     /* [RL_BLOCKS][nstreams] last run of the stream in the block -> P1: before the block */
     unsigned short* t_bytes = t_last + (size_t)RL_BLOCKS * nstreams;                     /* [RL_BLOCKS][nstreams] bytes of the stream in the block -> P2: offset of the block */
@@ -152,14 +150,10 @@ __device__ __forceinline__ void streams4_body(const EncBatchDev& b, const Header
 #pragma unroll
     for (int w = 0; w < S2_THREADS / 32; w++) { const u32 t = s_warp[w]; if (w < warp) base += t; total += t; }
     const u32 n_runs = total;
-    if (s_redo || n_runs > (u32)CAP) {
+    if (s_redo || n_runs > (u32)RL_CAP) {
         if (tid == 0) {
-            /* more runs than this list holds: up to twice as many go to the wide list (k_streams4w: the same code with room for
-             * them, four CTAs per SM), beyond that the column is dense (k_streams7) */
-            const bool wide = !s_redo && CAP < RL_CAP_WIDE && n_runs <= (u32)RL_CAP_WIDE && mode == 0 && job.wide_list;
-            const bool dense = !s_redo && !wide;
-            if (wide) { const u32 at = atomicAdd(job.wide_count, 1u); job.wide_list[at] = span; }
-            else if (mode == 0 && job.dense_list && (dense || job.list_takes_redo)) {
+            const bool dense = !s_redo;                              /* too many runs for the list: the dense coder's */
+            if (mode == 0 && job.dense_list && (dense || job.list_takes_redo)) {
                 if (dense) atomicAdd(job.dense_count, 1u);
                 const u32 at = atomicAdd(job.list_count, 1u); job.dense_list[at] = span;
             } else { const u32 at = atomicAdd(job.redo_count, 1u); job.redo_list[at] = span; }                                         /* long runs: k_streams3 */
@@ -342,14 +336,6 @@ __device__ __forceinline__ void streams4_body(const EncBatchDev& b, const Header
         if (head < lo) head += ((lo - head + 31u) / 32u) * 32u;
         for (; head < stop; head += 32u) { const u32 len = r_end - head < 32u ? r_end - head : 32u; *o++ = (u8)(0xC0u | (len - 1u)); }
     }
-}
-
-__global__ void __launch_bounds__(S2_THREADS) k_streams4(EncBatchDev b, HeaderDev h, StreamJob job, const u32* __restrict__ span_chunk) {
-    streams4_body<RL_CAP>(b, h, job, span_chunk, nullptr);
-}
-/* the spans k_streams4 found to hold 1537..3072 runs (columns of medium density: twice the generator's NovaSeq columns and more) */
-__global__ void __launch_bounds__(S2_THREADS) k_streams4w(EncBatchDev b, HeaderDev h, StreamJob job, const u32* __restrict__ span_chunk, const u32* __restrict__ list) {
-    streams4_body<RL_CAP_WIDE>(b, h, job, span_chunk, list);
 }
 
 }  // namespace rpq

@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(S7_THREADS) k_streams7(EncBatchDev b, HeaderDe
         job.span_slot[span] = at;
         if (at + acc > job.slot_cap) { atomicOr(job.overflow, 1u); s_slot = ~0ull; } else s_slot = at;
         s_bytes = acc;
-        if (!list && s_runs <= (u32)RL_CAP_WIDE) atomicAdd(job.dense_count, 1u);
+        if (!list && s_runs <= (u32)RL_CAP) atomicAdd(job.dense_count, 1u);
     }
     __syncthreads();
     if (s_slot == ~0ull || s_bytes == 0) return;

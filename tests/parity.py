@@ -189,8 +189,8 @@ def check_quality_longer_than_sequence(codec):
 
 
 def medium_density_quality(n_reads=8000, rl=150, seed=21, p_run=0.14):
-    """single-end FASTQ whose quality column holds 1537..3072 runs per 16384 positions: more than k_streams4's list, not more than
-    k_streams4w's (eight-level binned qualities look like this)"""
+    """single-end FASTQ whose quality column holds a few thousand runs per 16384 positions: around and above what k_streams4's list holds
+    (binned qualities of older instruments look like this)"""
     import numpy as np
     rnd = np.random.RandomState(seed)
     total = n_reads * rl
@@ -207,7 +207,7 @@ def medium_density_quality(n_reads=8000, rl=150, seed=21, p_run=0.14):
 
 
 def check_medium_density(codec):
-    for p_run, seed in ((0.14, 21), (0.10, 22), (0.21, 23), (0.30, 24)):    # around both list sizes: spans on either side of each
+    for p_run, seed in ((0.14, 21), (0.10, 22), (0.21, 23), (0.30, 24)):    # around the list size: spans on either side of it
         check_against_oracle(codec, medium_density_quality(seed=seed, p_run=p_run), k=1000)
     st = codec.stats()
     return st

@@ -494,5 +494,5 @@ def test_quality_longer_than_sequence(codec):
 
 
 def test_medium_density_quality_columns(codec):
-    """spans with more runs than k_streams4's list holds but not more than twice as many: k_streams4w"""
+    """spans with more runs than k_streams4's list holds in a column of four values: the hand-over to k_streams7 at medium density"""
     parity.check_medium_density(codec)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Encode time per kernel on a quality column of medium density (1537..3072 runs per 16384 positions): k_streams4 -> k_streams4w.
+"""Encode time per kernel on a quality column of medium density (a few thousand runs per 16384 positions, four values): k_streams4 -> k_streams7.
 usage: medium_probe.py [reads] [p_run]"""
 import os
 import sys
