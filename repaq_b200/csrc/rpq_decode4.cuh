@@ -8,11 +8,14 @@
  *   k_dec_qindex   a warp per (chunk, stream) walks the tokens 128 stream bytes per step (decodeSingleQualByCol, reference
  *                  src/rfqcodec.cpp:957-1007, without storing anything) and leaves one 8-byte CHECKPOINT per step: where the
  *                  first token of the step starts and the position the stream has reached.  0.06 bytes per stream byte.
- *   k_dec_format4  the formatter (a CTA per tile of G reads of ONE chunk) finds, for each stream, the checkpoint its first
- *                  position lies behind (a 32-ary search by a warp), decodes the few hundred stream bytes that cover its
- *                  positions straight into its shared-memory quality tile (pre-filled with the major quality,
- *                  src/rfqcodec.cpp:1089), applies the exception records (:1034-1043) and the N positions (:856-858, into a
- *                  shared bitmap), and then emits the records as k_dec_format3 did.
+ *   k_dec_tiledir  per formatter tile (G reads of ONE chunk) and stream: which steps of the stream hold the tile's positions (two
+ *                  bisections over the checkpoints), which exception records are the tile's.
+ *   k_dec_planes   a small CTA per tile: the tile's qualities pre-filled with the major quality (src/rfqcodec.cpp:1089), every
+ *                  (stream, step) of the directory decoded from its checkpoint by whichever warp takes it, the exception records
+ *                  (:1034-1043) and the N positions (:856-858, a bitmap) applied; the finished tile goes to its slot in HBM
+ *                  (19 KB per 128 reads of 150 bases: written and read once).
+ *   k_dec_format4  the formatter: the tile's slot and its piece of the 2-bit column arrive by TMA while the name lines are written;
+ *                  two threads per read emit the records into shared memory, one TMA bulk store per output stream takes them out.
  */
 #pragma once
 #include "rpq_decode2.cuh"

@@ -501,7 +501,7 @@ struct StreamJob {                   /* one per kind (quality / N positions) */
     u32* span_read0;                 /* [spans] chunk-relative index of the first read whose positions reach into the span's staging window */
     u32* redo_count;                 /* k_streams4: spans left to k_streams3 ... */
     u32* redo_list;                  /* ... and which */
-    u32* dense_count;                /* k_streams4: quality spans with more runs than its list holds, left to k_streams5 ... */
+    u32* dense_count;                /* k_streams4: quality spans with more runs than its list holds, left to k_streams7 ... */
     u32* dense_list;                 /* ... and which (NULL: they go to the redo list) */
     u32* list_count;                 /* entries of dense_list */
     u32 list_takes_redo;             /* the coder behind dense_list also takes the spans with long runs (k_streams7) */

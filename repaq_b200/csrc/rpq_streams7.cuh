@@ -7,7 +7,7 @@
  *
  * A first attempt kept bit planes of a thread's 64 positions and walked the streams (occupancy mask of each value, tokens from bit
  * operations): loop-free only while no run is longer than one position, and a warp's 32 segments never all are - 2.7 G warp
- * instructions per 200 M positions with 11 active lanes (profiles/r02_bgi_*k_streams7_v1*), slower than k_streams6.  What is dense
+ * instructions per 200 M positions with 11 active lanes (profiles/README.md r02, the table of builds), slower than k_streams6.  What is dense
  * in these columns is the POSITIONS, so the thread walks positions, not streams:
  *
  *   - a thread owns 64 consecutive positions of the span, their bytes in 16 registers, their "equals the previous position" mask E
